@@ -1,0 +1,137 @@
+/*
+ * visreps_b200 -- C ABI of the B200-native RSA hot path.
+ *
+ * The reference (yashsmehta/visreps) has no FFI layer: its boundary for this path is
+ * four Python callables in visreps/analysis/rsa.py plus the bootstrap loop inlined in
+ * visreps/evals.py.  Each entry point below names the reference statement(s) it replaces
+ * (paths relative to the reference root).  The Python mirror of the reference interface
+ * (visreps_b200/rsa.py) binds these with ctypes; INTEGRATION.md shows the stub a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch / C++ types.
+ *   - Every function returns an int status (VR_OK == 0).  On failure a thread-local
+ *     message is available from vr_last_error_string().  Nothing throws, nothing
+ *     allocates device memory: scratch comes from the caller (`ws`, `ws_bytes`), sized
+ *     by the matching *_workspace_bytes() query.
+ *   - Pointers are DEVICE pointers unless the parameter says "host".
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and the
+ *     call returns without synchronising.
+ *   - Stimulus count n <= VR_MAX_STIMULI.  N = n(n-1)/2 is the strict upper-triangle
+ *     length, in the row-major order of torch.triu_indices(n, n, 1) (rsa.py:111).
+ */
+#ifndef VISREPS_B200_H
+#define VISREPS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VR_ABI_VERSION 1
+#define VR_MAX_STIMULI 32767
+
+enum {
+  VR_OK = 0,
+  VR_ERR_INVALID = 1,     /* bad argument (maps to ValueError on the Python side) */
+  VR_ERR_WORKSPACE = 2,   /* ws_bytes smaller than the *_workspace_bytes() answer  */
+  VR_ERR_CUDA = 3,        /* a CUDA runtime/driver call failed                     */
+  VR_ERR_UNSUPPORTED = 4  /* device is not sm_100, or a feature is not built       */
+};
+
+enum { VR_SPEARMAN = 0, VR_PEARSON = 1, VR_KENDALL = 2 };
+
+typedef void* vr_stream_t;
+
+int vr_abi_version(void);
+/* Host, thread-local, valid until the next failing call on this thread. */
+const char* vr_last_error_string(void);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+unsigned long long vr_launch_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * RDM construction: replaces compute_rdm(), visreps/analysis/rsa.py:59-93
+ *   x -= rowmean; std = sqrt(mean(x^2)+c); std[std<10c] = 1;
+ *   rdm = 1 - clamp((x x^T / d) / (std_i std_j + c), -1, 1); diag = 0.
+ * X is row-major (n, d) fp32 with leading dimension ldx (elements); it is not modified
+ * (rsa.py:76).  rdm is (n, n) fp32, contiguous, exactly symmetric, diagonal exactly 0.
+ * zero_var_rows (nullable) receives the number of rows whose std was replaced by 1
+ * (the reference logs a warning for them, rsa.py:84-87).
+ * ---------------------------------------------------------------------------------- */
+size_t vr_rdm_workspace_bytes(int n, int64_t d);
+int vr_rdm_pearson_f32(const float* X, int n, int64_t d, int64_t ldx, float correction,
+                       float* rdm, int* zero_var_rows,
+                       void* ws, size_t ws_bytes, vr_stream_t stream);
+
+/* Row-wise 0-based ordinal ranks: replaces _rank(), rsa.py:50-52 (double argsort; ties
+ * are split by position, lower index first).  out is (n, d) fp32, contiguous. */
+size_t vr_rank_rows_workspace_bytes(int n, int64_t d);
+int vr_rank_rows_ordinal_f32(const float* X, int n, int64_t d, int64_t ldx, float* out,
+                             void* ws, size_t ws_bytes, vr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Presort: replaces the per-call `triu_indices` gather + SciPy stable argsort inside
+ * compute_rdm_correlation(), rsa.py:111-113,122 (scipy.stats.spearmanr -> rankdata).
+ * The strict upper triangle of `rdm` (n x n fp32, leading dimension ld) is sorted ONCE
+ * by value; the result is an opaque blob of vr_presort_bytes(n) bytes that every
+ * subsample of the same RDM is ranked from without sorting again.
+ * -0.0 ties with +0.0; a NaN anywhere marks the blob so that every score computed from
+ * it is NaN (rsa.py:123-125).
+ * ---------------------------------------------------------------------------------- */
+size_t vr_presort_bytes(int n);
+size_t vr_presort_workspace_bytes(int n);
+int vr_presort_triu_f32(const float* rdm, int n, int64_t ld, void* presorted,
+                        void* ws, size_t ws_bytes, vr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Subsample masks: turns the HOST-drawn index sets of the reference bootstrap
+ * (`rng.choice(n_test, int(0.9 n_test), replace=False)`, evals.py:362-364, rsa.py:249-251)
+ * into one n-bit membership mask per replicate.  idx is a device copy, (R, m) int32
+ * row-major.  masks is (R, vr_mask_words(n)) uint32.  Index order inside a draw does not
+ * change the multiset of sub-RDM pairs, so it does not change any score.
+ * ---------------------------------------------------------------------------------- */
+int vr_mask_words(int n);
+int vr_build_masks(const int32_t* idx, int R, int m, int n, uint32_t* masks, vr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Tie-averaged ranks of a subsample: replaces `rdm[idx][:, idx]` + triu gather +
+ * scipy.stats.rankdata(method="average") (evals.py:365-366 + rsa.py:111-113 + SciPy).
+ * For replicate r and every pair p = (i<j) of the FULL upper triangle:
+ *     dev[r][p] = 2*rank - (N_r + 1)   if both i and j are in mask r, else 0
+ * where rank is the 1-based tie-averaged rank among the N_r kept pairs.  2*rank is an
+ * integer, so dev is exact (int32).  dev rows have stride vr_dev_stride(n) elements.
+ * ss[r] = sum_p dev^2 (fp64), nkept[r] = N_r.
+ * ---------------------------------------------------------------------------------- */
+int64_t vr_dev_stride(int n);
+size_t vr_subsample_rank_workspace_bytes(int n);
+int vr_subsample_rank(const void* presorted, int n, const uint32_t* masks, int R,
+                      int32_t* dev, double* ss, int64_t* nkept,
+                      void* ws, size_t ws_bytes, vr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Grouped bootstrap comparison: replaces the loop at evals.py:361-369 (and its copies at
+ * evals.py:512-520, rsa.py:248-256, run_reconstruction.py:148-154) for nA model RDMs x
+ * nB neural RDMs x R masks in one call.  A mask with all n bits set gives the point
+ * estimate (evals.py:347).  out is (nA, nB, R) fp64, replicate order = mask order.
+ *   Spearman: inputs are presorted blobs (host arrays of device pointers).
+ *   Pearson : inputs are the RDMs themselves (n x n fp32, leading dimension ld).
+ * Undefined correlations (constant vector, < 2 kept stimuli, NaN input) give NaN.
+ * ---------------------------------------------------------------------------------- */
+size_t vr_bootstrap_spearman_workspace_bytes(int n, int nA, int nB, int R);
+int vr_bootstrap_spearman(const void* const* presortedA_host, int nA,
+                          const void* const* presortedB_host, int nB,
+                          int n, const uint32_t* masks, int R, double* out,
+                          void* ws, size_t ws_bytes, vr_stream_t stream);
+
+size_t vr_bootstrap_pearson_workspace_bytes(int n, int nA, int nB, int R);
+int vr_bootstrap_pearson(const float* const* rdmA_host, int nA,
+                         const float* const* rdmB_host, int nB,
+                         int n, int64_t ld, const uint32_t* masks, int R, double* out,
+                         void* ws, size_t ws_bytes, vr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VISREPS_B200_H */

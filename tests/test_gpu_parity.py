@@ -1,0 +1,295 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the golden fixtures.
+
+Bars (BASELINE.json north_star): ranks bit-exact given the same RDM; RDM entries within 1e-5
+absolute; RSA scores and every bootstrap replicate within 1e-5.
+"""
+import json
+import logging
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import visreps_b200 as vb
+from visreps_b200 import rsa as vrsa
+from oracle import cases, rsa_oracle as orc
+
+pytestmark = pytest.mark.gpu
+RDM_TOL = 1e-5
+SCORE_TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda", 0)
+
+
+# ------------------------------------------------------------------ RDM
+@pytest.mark.parametrize("name", list(cases.RDM_CASES))
+def test_rdm_matches_oracle_and_fp64_truth(name, dev, golden_dir):
+    x = cases.rdm_input(name)
+    keep = x.clone()
+    got_cpu_in = vb.compute_rdm(x)                    # CPU tensor in -> CPU tensor out (rsa.py device rule)
+    assert got_cpu_in.device.type == "cpu" and got_cpu_in.dtype == torch.float32
+    assert torch.equal(x, keep), "input mutated"
+    xd = x.to(dev)
+    got = vb.compute_rdm(xd)
+    assert got.device == xd.device and torch.equal(got.cpu(), got_cpu_in)
+    g = got.cpu()
+    ref = orc.rdm(x)
+    assert float((g - ref).abs().max()) <= RDM_TOL
+    assert float(np.abs(g.numpy().astype(np.float64) - orc.rdm_truth_f64(x)).max()) <= RDM_TOL
+    assert torch.equal(g, g.T), "RDM must be exactly symmetric"
+    assert float(g.diagonal().abs().max()) == 0.0
+    assert float(g.min()) >= 0.0 and float(g.max()) <= 2.0
+    gold = np.load(os.path.join(golden_dir, "rdm.npz"))
+    if f"{name}/pearson" in gold:
+        assert float(np.abs(g.numpy() - gold[f"{name}/pearson"]).max()) <= RDM_TOL
+    else:
+        assert float(np.abs(orc.triu_vector(g)[::97] - gold[f"{name}/pearson_triu_stride97"]).max()) <= RDM_TOL
+
+
+def test_rdm_known_answers_and_edge_rows(dev, caplog):
+    simple = torch.tensor([[1., 2., 3.], [4., 5., 6.], [1., 2., 3.], [7., 8., 9.]])
+    r = vb.compute_rdm(simple.to(dev)).cpu()
+    assert float((r - orc.rdm(simple)).abs().max()) <= 1e-6
+    assert abs(float(r[0, 2])) < 1e-4
+    anti = torch.tensor([[1., 2., 3., 4.], [4., 3., 2., 1.], [1., 1., 1., 1.], [2., 4., 6., 9.]])
+    with caplog.at_level(logging.WARNING):
+        ra = vb.compute_rdm(anti.to(dev)).cpu()
+    assert any("zero variance" in m for m in caplog.messages)      # rsa.py:84-87
+    assert torch.isfinite(ra).all() and abs(float(ra[0, 1]) - 2.0) < 1e-4
+    assert float((ra - orc.rdm(anti)).abs().max()) <= 1e-6
+    # n = 1 and n = 0
+    one = vb.compute_rdm(torch.randn(1, 7).to(dev))
+    assert one.shape == (1, 1) and float(one[0, 0]) == 0.0
+    assert vb.compute_rdm(torch.empty(0, 5).to(dev)).shape == (0, 0)
+    # other float dtypes are accepted like the reference's .float()
+    x = cases.rdm_input("n64_d48")
+    r16 = vb.compute_rdm(x.half().to(dev)).cpu()
+    assert float((r16 - orc.rdm(x.half())).abs().max()) <= RDM_TOL
+    # strided rows (pitch > width) are read in place
+    wide = torch.zeros(64, 80, device=dev)
+    wide[:, :48] = x.to(dev)
+    assert torch.equal(vb.compute_rdm(wide[:, :48]).cpu(), vb.compute_rdm(x.to(dev)).cpu())
+    with pytest.raises(ValueError):
+        vb.compute_rdm(x.to(dev), correlation="cosine")
+
+
+def test_rank_rows_and_spearman_rdm(dev):
+    x = cases.rdm_input("n64_d48") + torch.from_numpy(np.random.RandomState(5).standard_normal((64, 48)).astype(np.float32))
+    assert torch.equal(vb._rank(x.to(dev)).cpu(), orc.ordinal_row_ranks(x))       # no ties: bit-exact
+    t = torch.tensor([[3., 1., 2.], [1., 3., 2.]])
+    assert torch.equal(vb._rank(t.to(dev)).cpu(), torch.tensor([[2., 0., 1.], [0., 2., 1.]]))
+    ties = torch.tensor([[1., 1., 3., 1., -0.0, 0.0]])
+    assert vb._rank(ties.to(dev)).cpu().tolist() == [[2., 3., 5., 4., 0., 1.]]     # ties split by position
+    big = torch.from_numpy(np.random.RandomState(6).standard_normal((3, 10000)).astype(np.float32))
+    assert torch.equal(vb._rank(big.to(dev)).cpu(), orc.ordinal_row_ranks(big))
+    rs = vb.compute_rdm(x.to(dev), correlation="Spearman").cpu()
+    assert float((rs - orc.rdm(x, correlation="Spearman")).abs().max()) <= RDM_TOL
+
+
+# ------------------------------------------------------------------ ranks (bit-exact)
+def _full_masks(n, dev):
+    return vrsa.build_masks(None, n, dev, with_full=True)
+
+
+@pytest.mark.parametrize("n,levels,seed", [(24, 7, 301), (90, 40, 302), (33, 3, 303), (300, 1000, 304), (65, 1, 305)])
+def test_tie_averaged_ranks_are_bit_exact(n, levels, seed, dev):
+    N = n * (n - 1) // 2
+    va, _ = cases.tied_vectors(N, levels, seed)
+    if levels == 1:
+        va[:] = 0.5                                  # one run spanning every 32-group
+    m = cases.vector_to_rdm(va, n)
+    devv, ss, nk = vrsa.subsample_rank(m.to(dev), _full_masks(n, dev))
+    got = devv[0].cpu().numpy().astype(np.int64) + (N + 1)
+    np.testing.assert_array_equal(got, orc.rank2x(va))
+    assert int(nk[0]) == N
+    assert float(ss[0]) == float(((got - (N + 1)) ** 2).sum())
+
+
+@pytest.mark.parametrize("name", ["p64", "p220", "p1000"])
+def test_subsample_ranks_are_bit_exact(name, dev):
+    x, y = cases.pair_inputs(name)
+    n = x.shape[0]
+    rdm = vb.compute_rdm(x.to(dev))
+    v = orc.triu_vector(rdm)
+    idx = vrsa.draw_index_sets(n, 3, 42)
+    masks = vrsa.build_masks(idx, n, dev, with_full=True)
+    devv, ss, nk = vrsa.subsample_rank(rdm, masks)
+    devv = devv.cpu().numpy().astype(np.int64)
+    iu = np.triu_indices(n, 1)
+    for r in range(4):
+        keep = np.ones(n, bool) if r == 0 else np.isin(np.arange(n), idx[r - 1])
+        kp = keep[iu[0]] & keep[iu[1]]
+        Ns = int(kp.sum())
+        assert int(nk[r]) == Ns
+        np.testing.assert_array_equal(devv[r][kp] + (Ns + 1), orc.rank2x(v[kp]))
+        assert not devv[r][~kp].any()
+        assert int(devv[r].sum()) == 0
+
+
+# ------------------------------------------------------------------ comparisons
+@pytest.mark.parametrize("name", list(cases.PAIR_CASES))
+def test_compare_matches_oracle_and_golden(name, dev, golden_dir):
+    gold = np.load(os.path.join(golden_dir, "compare.npz"))
+    x, y = cases.pair_inputs(name)
+    a_ref, b_ref = orc.rdm(x), orc.rdm(y)
+    for method in ("Spearman", "Pearson"):
+        # same RDMs in (reference-built), CPU tensors like the reference's callers pass
+        s = vb.compute_rdm_correlation(a_ref, b_ref, correlation=method)
+        assert isinstance(s, float)
+        assert abs(s - orc.rdm_compare(a_ref, b_ref, correlation=method)) <= SCORE_TOL
+        assert abs(s - float(gold[f"{name}/{method.lower()}"])) <= SCORE_TOL
+        # end to end: our RDMs -> our comparison, still within the score bar of the reference
+        a, b = vb.compute_rdm(x.to(dev)), vb.compute_rdm(y.to(dev))
+        assert abs(vb.compute_rdm_correlation(a, b, correlation=method) - float(gold[f"{name}/{method.lower()}"])) <= SCORE_TOL
+
+
+@pytest.mark.parametrize("tag,n,levels,seed", [("ties24", 24, 7, 301), ("ties90", 90, 40, 302)])
+def test_compare_with_heavy_ties(tag, n, levels, seed, dev, golden_dir):
+    gold = np.load(os.path.join(golden_dir, "compare.npz"))
+    va, vbv = cases.tied_vectors(n * (n - 1) // 2, levels, seed)
+    a, b = cases.vector_to_rdm(va, n), cases.vector_to_rdm(vbv, n)
+    for method in ("Spearman", "Pearson"):
+        s = vb.compute_rdm_correlation(a.to(dev), b.to(dev), correlation=method)
+        assert abs(s - float(gold[f"{tag}/{method.lower()}"])) <= SCORE_TOL
+
+
+def test_compare_edge_semantics(dev):
+    x = torch.randn(20, 10)
+    r = vb.compute_rdm(x.to(dev))
+    for method in ("Spearman", "Pearson"):
+        assert vb.compute_rdm_correlation(r, r, correlation=method) == pytest.approx(1.0, abs=1e-9)
+    r2 = 2.0 - r
+    r2.fill_diagonal_(0.0)
+    assert vb.compute_rdm_correlation(r, r2, correlation="Spearman") == pytest.approx(-1.0, abs=1e-9)
+    assert math.isnan(vb.compute_rdm_correlation(torch.zeros(1, 1), torch.zeros(1, 1), correlation="Spearman"))
+    assert math.isnan(vb.compute_rdm_correlation(torch.ones(6, 6).to(dev), r[:6, :6], correlation="Spearman"))  # constant
+    assert math.isnan(vb.compute_rdm_correlation(torch.ones(6, 6).to(dev), r[:6, :6], correlation="Pearson"))
+    two = torch.tensor([[0., 0.3], [0.3, 0.]])
+    assert math.isnan(vb.compute_rdm_correlation(two.to(dev), two.to(dev), correlation="Spearman"))       # one pair
+    nanm = r.clone()
+    nanm[2, 5] = float("nan")
+    nanm[5, 2] = float("nan")
+    assert math.isnan(vb.compute_rdm_correlation(nanm, r, correlation="Spearman"))                     # NaN propagates
+    with pytest.raises(ValueError):
+        vb.compute_rdm_correlation(torch.zeros(5, 5), torch.zeros(6, 6))
+    with pytest.raises(ValueError):
+        vb.compute_rdm_correlation(r, r, correlation="cosine")
+    with pytest.raises(NotImplementedError):
+        vb.compute_rdm_correlation(r, r)                                  # default is Kendall (rsa.py:97)
+    # negative values, -0.0 and wide dynamic range sort correctly
+    rs = np.random.RandomState(9)
+    n = 40
+    N = n * (n - 1) // 2
+    va = (rs.standard_normal(N) * 10 ** rs.uniform(-20, 20, N)).astype(np.float32)
+    vbv = (va * rs.choice([-1, 1], N) + rs.standard_normal(N)).astype(np.float32)
+    va[:5] = [-0.0, 0.0, -1e-38, 1e-38, 0.0]
+    a, b = cases.vector_to_rdm(va, n), cases.vector_to_rdm(vbv, n)
+    assert abs(vb.compute_rdm_correlation(a, b, correlation="Spearman") - orc.rdm_compare(a, b, correlation="Spearman")) <= SCORE_TOL
+
+
+# ------------------------------------------------------------------ bootstrap
+@pytest.mark.parametrize("name,method", [("p64", "spearman"), ("p64", "pearson"), ("p220", "spearman"),
+                                         ("p220", "pearson"), ("p1000", "spearman"), ("p1000", "pearson")])
+def test_bootstrap_matches_golden_replicates(name, method, dev, golden_dir):
+    gold = np.load(os.path.join(golden_dir, "compare.npz"))
+    x, y = cases.pair_inputs(name)
+    a_ref, b_ref = orc.rdm(x), orc.rdm(y)
+    nb = cases.N_GOLDEN_REPLICATES[name]
+    point, lo, hi, scores = vb.bootstrap_rdm_correlation(a_ref, b_ref, method, n_bootstrap=nb, seed=42)
+    scores = np.asarray(scores)
+    assert scores.shape == (nb,)
+    np.testing.assert_allclose(scores, gold[f"{name}/boot_{method}"], atol=SCORE_TOL, rtol=0)
+    assert abs(point - float(gold[f"{name}/{method}"])) <= SCORE_TOL
+    assert lo == float(np.percentile(scores, 2.5)) and hi == float(np.percentile(scores, 97.5))
+    # from our own RDMs too
+    a, b = vb.compute_rdm(x.to(dev)), vb.compute_rdm(y.to(dev))
+    _, _, _, s2 = vb.bootstrap_rdm_correlation(a, b, method, n_bootstrap=nb, seed=42)
+    np.testing.assert_allclose(np.asarray(s2), gold[f"{name}/boot_{method}"], atol=SCORE_TOL, rtol=0)
+
+
+def test_bootstrap_against_oracle_loop_and_grouping(dev):
+    x, y = cases.pair_inputs("p220")
+    n = x.shape[0]
+    rs = np.random.RandomState(11)
+    models = [orc.rdm(x), orc.rdm(x[:, :40]), orc.rdm(torch.from_numpy(rs.standard_normal((n, 30)).astype(np.float32)))]
+    neurals = [orc.rdm(y), orc.rdm(y[:, ::2])]
+    B = 12
+    idx = orc.draw_subsamples(n, B, 42)
+    for method in ("spearman", "pearson"):
+        res = vb.bootstrap_rdm_correlation_grouped(models, neurals, method, n_bootstrap=B, seed=42)
+        assert res["scores"].shape == (3, 2, B) and res["point"].shape == (3, 2)
+        for i, m in enumerate(models):
+            for j, q in enumerate(neurals):
+                want = orc.bootstrap_compare_with_indices(m, q, method, idx)
+                np.testing.assert_allclose(res["scores"][i, j], want, atol=SCORE_TOL, rtol=0)
+                assert abs(res["point"][i, j] - orc.rdm_compare(m, q, correlation=method.capitalize())) <= SCORE_TOL
+        # a replicate slice (multi-GPU shard) reproduces the same entries
+        part = vb.bootstrap_rdm_correlation_grouped(models, neurals, method, n_bootstrap=B, seed=42, replicate_range=(5, 9))
+        np.testing.assert_array_equal(part["scores"], res["scores"][:, :, 5:9])
+    # n_bootstrap = 1 works (reference tests :2058-2069)
+    p, lo, hi, s = vb.bootstrap_rdm_correlation(models[0], neurals[0], "spearman", n_bootstrap=1)
+    assert len(s) == 1 and lo == hi == s[0]
+
+
+def test_compute_rsa_matches_reference_fixture(dev, golden_dir):
+    with open(os.path.join(golden_dir, "compute_rsa.json")) as f:
+        gold = json.load(f)["results"]
+    tr, te = cases.alignment_case()
+    for tag, kw in {"all_train": dict(n_select=None), "subsample": dict(n_select=120)}.items():
+        want = gold[f"{tag}/spearman"]
+        got = vb.compute_rsa({"compare_method": "spearman"}, vb.AlignmentData(**tr), vb.AlignmentData(**te),
+                             bootstrap=True, n_bootstrap=25, seed=7, **kw)[0]
+        assert list(got.keys()) == list(want.keys())
+        assert got["layer"] == want["layer"] == "good" and got["analysis"] == "rsa" and got["compare_method"] == "spearman"
+        assert abs(got["score"] - want["score"]) <= SCORE_TOL
+        np.testing.assert_allclose(got["bootstrap_scores"], want["bootstrap_scores"], atol=SCORE_TOL, rtol=0)
+        assert abs(got["ci_low"] - want["ci_low"]) <= SCORE_TOL and abs(got["ci_high"] - want["ci_high"]) <= SCORE_TOL
+        for g, w in zip(got["layer_selection_scores"], want["layer_selection_scores"]):
+            assert g["layer"] == w["layer"] and abs(g["score"] - w["score"]) <= SCORE_TOL
+    # no bootstrap -> CI fields None, no bootstrap_scores key (rsa.py:229-279)
+    nb = vb.compute_rsa({"compare_method": "spearman"}, vb.AlignmentData(**tr), vb.AlignmentData(**te), bootstrap=False)[0]
+    assert nb["ci_low"] is None and nb["ci_high"] is None and "bootstrap_scores" not in nb
+    # re_extract_fn is used for the evaluation RDM of the chosen layer (rsa.py:212-215)
+    calls = []
+
+    def re_extract(layer, ids):
+        calls.append((layer, ids))
+        return te["activations"][layer], ids
+    r2 = vb.compute_rsa({"compare_method": "spearman"}, vb.AlignmentData(**tr), vb.AlignmentData(**te), bootstrap=False,
+                        re_extract_fn=re_extract)[0]
+    assert calls == [("good", te["stimulus_ids"])] and abs(r2["score"] - nb["score"]) <= 1e-12
+    with pytest.raises(NotImplementedError):
+        vb.compute_rsa({"compare_method": "kendall"}, vb.AlignmentData(**tr), vb.AlignmentData(**te), bootstrap=False)
+
+
+# ------------------------------------------------------------------ full-size properties (no oracle loop)
+def test_nsd_shape_properties(dev):
+    """BASELINE config 2/3 sizes: checks that do not need the 0.25 s/replicate CPU path."""
+    x, y = cases.pair_inputs("p1000")
+    n = 1000
+    a, b = vb.compute_rdm(x.to(dev)), vb.compute_rdm(y.to(dev))
+    B = 40
+    idx = vrsa.draw_index_sets(n, B, 42)
+    res = vb.bootstrap_rdm_correlation_grouped([a], [b], "spearman", index_sets=idx)
+    s = res["scores"][0, 0]
+    # (1) sub-index == direct: a replicate equals the full comparison of the gathered sub-RDMs (reference tests :1390-1412)
+    for r in (0, 17, 39):
+        t = torch.from_numpy(idx[r].astype(np.int64)).to(dev)
+        direct = vb.compute_rdm_correlation(a[t][:, t], b[t][:, t], correlation="Spearman")
+        assert abs(direct - s[r]) <= 1e-12
+    # (2) order inside a draw is irrelevant; (3) determinism
+    shuffled = np.stack([np.random.RandomState(r).permutation(row) for r, row in enumerate(idx)])
+    again = vb.bootstrap_rdm_correlation_grouped([a], [b], "spearman", index_sets=shuffled)["scores"][0, 0]
+    np.testing.assert_array_equal(s, again)
+    # (4) self-comparison is exactly 1 for every replicate; symmetry in the arguments
+    self_s = vb.bootstrap_rdm_correlation_grouped([a], [a], "spearman", index_sets=idx)
+    np.testing.assert_allclose(self_s["scores"], 1.0, atol=1e-12)
+    swapped = vb.bootstrap_rdm_correlation_grouped([b], [a], "spearman", index_sets=idx)["scores"][0, 0]
+    np.testing.assert_allclose(swapped, s, atol=1e-15)
+    # (5) scores are plausible and spread around the point estimate
+    assert abs(np.median(s) - res["point"][0, 0]) < 0.02 and s.std() > 0

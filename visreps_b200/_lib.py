@@ -1,0 +1,114 @@
+"""ctypes binding of the C-ABI library (include/visreps_b200.h).
+
+The product path has no CPU implementation: if the shared library is missing, or CUDA is
+not available, every entry point raises.  PyTorch is used only for device memory, streams
+and torch.distributed.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libvisreps_b200.so")
+
+VR_OK, VR_ERR_INVALID, VR_ERR_WORKSPACE, VR_ERR_CUDA, VR_ERR_UNSUPPORTED = range(5)
+ABI_VERSION = 1
+
+# name -> (restype, argtypes); mirrors include/visreps_b200.h one to one
+_vp, _i, _i64, _sz, _f = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_float
+SIGNATURES = {
+    "vr_abi_version": (_i, []),
+    "vr_last_error_string": (C.c_char_p, []),
+    "vr_launch_count": (C.c_ulonglong, []),
+    "vr_rdm_workspace_bytes": (_sz, [_i, _i64]),
+    "vr_rdm_pearson_f32": (_i, [_vp, _i, _i64, _i64, _f, _vp, _vp, _vp, _sz, _vp]),
+    "vr_rank_rows_workspace_bytes": (_sz, [_i, _i64]),
+    "vr_rank_rows_ordinal_f32": (_i, [_vp, _i, _i64, _i64, _vp, _vp, _sz, _vp]),
+    "vr_presort_bytes": (_sz, [_i]),
+    "vr_presort_workspace_bytes": (_sz, [_i]),
+    "vr_presort_triu_f32": (_i, [_vp, _i, _i64, _vp, _vp, _sz, _vp]),
+    "vr_mask_words": (_i, [_i]),
+    "vr_build_masks": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "vr_dev_stride": (_i64, [_i]),
+    "vr_subsample_rank_workspace_bytes": (_sz, [_i]),
+    "vr_subsample_rank": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "vr_bootstrap_spearman_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "vr_bootstrap_spearman": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _vp, _vp, _sz, _vp]),
+    "vr_bootstrap_pearson_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "vr_bootstrap_pearson": (_i, [_vp, _i, _vp, _i, _i, _i64, _vp, _i, _vp, _vp, _sz, _vp]),
+}
+
+
+class VisrepsB200Error(RuntimeError):
+    pass
+
+
+_lock = threading.Lock()
+_lib = None
+
+
+def load(path: str = LIB_PATH) -> C.CDLL:
+    """dlopen the library and type every exported symbol.  Fails loudly."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(path):
+            raise VisrepsB200Error(
+                f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C visreps_b200/csrc`). There is no CPU fallback for this path.")
+        lib = C.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the header and the .so diverge
+            fn.restype, fn.argtypes = res, args
+        if lib.vr_abi_version() != ABI_VERSION:
+            raise VisrepsB200Error(f"ABI version {lib.vr_abi_version()} != expected {ABI_VERSION}")
+        _lib = lib
+        return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc == VR_OK:
+        return
+    msg = load().vr_last_error_string().decode("utf-8", "replace")
+    if rc == VR_ERR_INVALID:
+        raise ValueError(f"{what}: {msg}")
+    raise VisrepsB200Error(f"{what}: status {rc}: {msg}")
+
+
+def require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise VisrepsB200Error("visreps_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+_workspaces = {}
+
+
+def workspace(nbytes: int, device: torch.device, slot: str = "main") -> torch.Tensor:
+    """Grow-only per-(device, slot) scratch buffer (uint8)."""
+    key = (device.index, slot)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        if buf is not None:
+            del _workspaces[key]
+            del buf
+        buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+def release_workspaces() -> None:
+    _workspaces.clear()
+
+
+def launch_count() -> int:
+    return int(load().vr_launch_count())

@@ -1,0 +1,154 @@
+// Shared host/device helpers for the visreps_b200 CUDA library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/visreps_b200.h"
+
+namespace vr {
+
+// ---- error plumbing ------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+void count_launch(unsigned n = 1);
+
+#define VR_CHECK_CUDA(expr)                                                              \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      vr::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,    \
+                    __LINE__);                                                           \
+      return VR_ERR_CUDA;                                                                \
+    }                                                                                    \
+  } while (0)
+
+#define VR_CHECK_LAUNCH()                                                                \
+  do {                                                                                   \
+    vr::count_launch();                                                                  \
+    VR_CHECK_CUDA(cudaGetLastError());                                                   \
+  } while (0)
+
+#define VR_REQUIRE(cond, ...)                                                            \
+  do {                                                                                   \
+    if (!(cond)) {                                                                       \
+      vr::set_error(__VA_ARGS__);                                                        \
+      return VR_ERR_INVALID;                                                             \
+    }                                                                                    \
+  } while (0)
+
+// ---- sizes ---------------------------------------------------------------------------
+__host__ __device__ inline int64_t triu_len(int64_t n) { return n * (n - 1) / 2; }
+__host__ __device__ inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+constexpr int kNumSMs = 148;  // B200
+
+// Bump allocator over the caller's workspace; every block is 256-byte aligned.
+struct Arena {
+  char* base;
+  size_t cap;
+  size_t off = 0;
+  bool ok = true;
+  Arena(void* p, size_t bytes) : base(static_cast<char*>(p)), cap(bytes) {}
+  template <typename T>
+  T* take(size_t count) {
+    size_t bytes = (count * sizeof(T) + 255) / 256 * 256;
+    if (off + bytes > cap) { ok = false; off += bytes; return nullptr; }
+    T* r = reinterpret_cast<T*>(base + off);
+    off += bytes;
+    return r;
+  }
+};
+inline size_t arena_bytes(size_t count, size_t elem) { return (count * elem + 255) / 256 * 256; }
+
+// ---- packed (i, j) pair word of the presorted stream -----------------------------------
+//  bits  0..14  column j
+//  bits 15..29  row    i   (i < j)
+//  bit  30      head: first element of a run of equal values in sorted order
+//  bit  31      pad : position >= N in the last 32-group (never kept, never written)
+constexpr uint32_t kHeadBit = 1u << 30;
+constexpr uint32_t kPadBit = 1u << 31;
+__host__ __device__ inline uint32_t pack_pair(uint32_t i, uint32_t j) { return (i << 15) | j; }
+__host__ __device__ inline uint32_t pair_i(uint32_t w) { return (w >> 15) & 0x7FFFu; }
+__host__ __device__ inline uint32_t pair_j(uint32_t w) { return w & 0x7FFFu; }
+// Row-major position of (i<j) in the strict upper triangle of an n x n matrix.
+__host__ __device__ inline uint32_t triu_pos(uint32_t i, uint32_t j, uint32_t n) {
+  return i * (2u * n - i - 1u) / 2u + (j - i - 1u);
+}
+
+// ---- presorted blob layout --------------------------------------------------------------
+//  [0, 256)          header
+//  stream            uint32[G*32]   packed pairs in ascending value order (+pad words)
+//  prev_head         uint32[G]      last head position <= 32g+31
+//  next_head         uint32[G+1]    first head position >= 32g   (N if none; [G] = N)
+struct PresortHeader {
+  uint32_t magic;
+  uint32_t n;
+  uint32_t N;        // n(n-1)/2
+  uint32_t G;        // ceil(N/32)
+  uint32_t has_nan;  // written on the device
+  uint32_t n_runs;   // number of distinct values (device)
+};
+constexpr uint32_t kPresortMagic = 0x56525053u;  // 'VRPS'
+struct PresortView {
+  PresortHeader* hdr;
+  uint32_t* stream;
+  uint32_t* prev_head;
+  uint32_t* next_head;
+};
+__host__ __device__ inline uint32_t presort_groups(int n) { return (uint32_t)((triu_len(n) + 31) / 32); }
+inline size_t presort_blob_bytes(int n) {
+  size_t G = presort_groups(n);
+  return 256 + arena_bytes(G * 32, 4) + arena_bytes(G, 4) + arena_bytes(G + 1, 4);
+}
+__host__ __device__ inline PresortView presort_view(void* blob, int n) {
+  size_t G = presort_groups(n);
+  char* p = static_cast<char*>(blob);
+  PresortView v;
+  v.hdr = reinterpret_cast<PresortHeader*>(p);
+  p += 256;
+  v.stream = reinterpret_cast<uint32_t*>(p);
+  p += (G * 32 * 4 + 255) / 256 * 256;
+  v.prev_head = reinterpret_cast<uint32_t*>(p);
+  p += (G * 4 + 255) / 256 * 256;
+  v.next_head = reinterpret_cast<uint32_t*>(p);
+  return v;
+}
+
+// ---- device helpers ------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ uint32_t lanemask_lt() {
+  uint32_t m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+__device__ __forceinline__ uint32_t lanemask_le() {
+  uint32_t m;
+  asm("mov.u32 %0, %%lanemask_le;" : "=r"(m));
+  return m;
+}
+__device__ __forceinline__ uint32_t lanemask_gt() {
+  uint32_t m;
+  asm("mov.u32 %0, %%lanemask_gt;" : "=r"(m));
+  return m;
+}
+// Order-preserving map fp32 -> uint32 (ascending), with -0.0 folded onto +0.0.
+__device__ __forceinline__ uint32_t float_key(float f) {
+  uint32_t u = __float_as_uint(f);
+  if (u == 0x80000000u) u = 0u;
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+#endif
+
+}  // namespace vr

@@ -1,0 +1,194 @@
+// Presort of an RDM's strict upper triangle, and row-wise ordinal ranks.
+//
+// vr_presort_triu_f32 replaces, for every later comparison of the same RDM, the
+// `triu_indices` gather (visreps/analysis/rsa.py:111-113) and the stable argsort inside
+// scipy.stats.rankdata that scipy.stats.spearmanr runs per call (rsa.py:122).
+// vr_rank_rows_ordinal_f32 replaces _rank (rsa.py:50-52).
+#include "common.cuh"
+#include "sort.cuh"
+
+namespace vr {
+
+// ---- upper triangle -> (sortable key, packed pair) ------------------------------------
+__global__ void __launch_bounds__(256)
+triu_keys_kernel(const float* __restrict__ rdm, int n, int64_t ld, uint32_t* __restrict__ keys,
+                 uint32_t* __restrict__ vals, PresortHeader* hdr) {
+  const uint32_t i = blockIdx.y;
+  const uint32_t j = blockIdx.x * 256u + threadIdx.x;
+  if (j >= (uint32_t)n || j <= i) return;
+  const float v = rdm[(int64_t)i * ld + j];
+  if (v != v) atomicOr(&hdr->has_nan, 1u);
+  const uint32_t p = triu_pos(i, j, (uint32_t)n);
+  keys[p] = float_key(v);
+  vals[p] = pack_pair(i, j);
+}
+
+__global__ void init_header_kernel(PresortHeader* hdr, uint32_t n, uint32_t N, uint32_t G) {
+  hdr->magic = kPresortMagic;
+  hdr->n = n;
+  hdr->N = N;
+  hdr->G = G;
+  hdr->has_nan = 0;
+  hdr->n_runs = 0;
+}
+
+// One warp per 32-group of the sorted order: head flags, packed stream, per-group
+// candidates for the prev/next head tables.
+__global__ void __launch_bounds__(256)
+heads_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint32_t N,
+             uint32_t G, PresortView out) {
+  const uint32_t g = blockIdx.x * 8u + (threadIdx.x >> 5);
+  if (g >= G) return;
+  const unsigned lane = lane_id();
+  const uint32_t k = g * 32u + lane;
+  const bool valid = k < N;
+  const uint32_t key = valid ? keys[k] : 0u;
+  const uint32_t prev = (valid && k > 0) ? keys[k - 1] : 0u;
+  const bool head = valid && (k == 0 || key != prev);
+  const bool pad_head = (k == N);  // sentinel that closes the last run
+  uint32_t word;
+  if (valid) word = vals[k] | (head ? kHeadBit : 0u);
+  else word = kPadBit | (pad_head ? kHeadBit : 0u);
+  out.stream[k] = word;
+  const uint32_t H = __ballot_sync(0xffffffffu, head);
+  const uint32_t Hn = __ballot_sync(0xffffffffu, head || pad_head);
+  if (lane == 0) {
+    out.prev_head[g] = H ? g * 32u + (31u - __clz(H)) : 0u;
+    out.next_head[g] = Hn ? g * 32u + (__ffs(Hn) - 1u) : 0xFFFFFFFFu;
+    if (H) atomicAdd(&out.hdr->n_runs, (uint32_t)__popc(H));
+  }
+}
+
+// prev_head: inclusive running max (forward).  next_head: inclusive running min (backward),
+// seeded with next_head[G] = N.  Single CTA, each thread owns a contiguous chunk.
+__global__ void __launch_bounds__(1024)
+head_tables_kernel(uint32_t* __restrict__ prev_head, uint32_t* __restrict__ next_head, uint32_t N,
+                   uint32_t G) {
+  __shared__ uint32_t part[1024];
+  const uint32_t chunk = (G + 1023u) / 1024u;
+  const uint32_t lo = threadIdx.x * chunk;
+  const uint32_t hi = lo + chunk < G ? lo + chunk : G;
+  // forward max
+  uint32_t m = 0;
+  for (uint32_t g = lo; g < hi; ++g) m = max(m, prev_head[g]);
+  part[threadIdx.x] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    for (int t = 0; t < 1024; ++t) { uint32_t v = part[t]; part[t] = run; run = max(run, v); }
+  }
+  __syncthreads();
+  m = part[threadIdx.x];
+  for (uint32_t g = lo; g < hi; ++g) { m = max(m, prev_head[g]); prev_head[g] = m; }
+  __syncthreads();
+  // backward min
+  m = 0xFFFFFFFFu;
+  for (uint32_t g = lo; g < hi; ++g) m = min(m, next_head[g]);
+  part[threadIdx.x] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t run = N;
+    for (int t = 1023; t >= 0; --t) { uint32_t v = part[t]; part[t] = run; run = min(run, v); }
+    next_head[G] = N;
+  }
+  __syncthreads();
+  m = part[threadIdx.x];
+  for (uint32_t g = hi; g > lo; --g) { m = min(m, next_head[g - 1]); next_head[g - 1] = m; }
+}
+
+// ---- row-wise ordinal ranks ------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+row_keys_kernel(const float* __restrict__ X, int64_t d, int64_t ldx, uint32_t* __restrict__ keys,
+                uint32_t* __restrict__ vals) {
+  const int64_t row = blockIdx.y;
+  for (int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x; c < d; c += (int64_t)gridDim.x * 256) {
+    keys[row * d + c] = float_key(X[row * ldx + c]);
+    vals[row * d + c] = (uint32_t)c;
+  }
+}
+__global__ void __launch_bounds__(256)
+row_rank_scatter_kernel(const uint32_t* __restrict__ vals, int64_t d, float* __restrict__ out) {
+  const int64_t row = blockIdx.y;
+  for (int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x; k < d; k += (int64_t)gridDim.x * 256)
+    out[row * d + vals[row * d + k]] = (float)k;
+}
+
+}  // namespace vr
+
+using namespace vr;
+
+extern "C" size_t vr_presort_bytes(int n) { return n >= 2 ? presort_blob_bytes(n) : 256; }
+
+extern "C" size_t vr_presort_workspace_bytes(int n) {
+  if (n < 2) return 256;
+  const int64_t N = triu_len(n);
+  return 4 * arena_bytes((size_t)round_up(N, 32), 4) + arena_bytes(sort_count_elems(N, 1), 4) + 256;
+}
+
+extern "C" int vr_presort_triu_f32(const float* rdm, int n, int64_t ld, void* presorted, void* ws,
+                                   size_t ws_bytes, vr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  VR_REQUIRE(rdm && presorted, "vr_presort_triu_f32: null pointer");
+  VR_REQUIRE(n >= 2 && n <= VR_MAX_STIMULI, "vr_presort_triu_f32: n=%d outside [2, %d]", n, VR_MAX_STIMULI);
+  VR_REQUIRE(ld >= n, "vr_presort_triu_f32: ld=%lld < n=%d", (long long)ld, n);
+  if (ws_bytes < vr_presort_workspace_bytes(n) || !ws) {
+    set_error("vr_presort_triu_f32: workspace %zu < %zu", ws_bytes, vr_presort_workspace_bytes(n));
+    return VR_ERR_WORKSPACE;
+  }
+  const int64_t N = triu_len(n);
+  const uint32_t G = presort_groups(n);
+  Arena a(ws, ws_bytes);
+  uint32_t* k0 = a.take<uint32_t>(round_up(N, 32));
+  uint32_t* v0 = a.take<uint32_t>(round_up(N, 32));
+  uint32_t* k1 = a.take<uint32_t>(round_up(N, 32));
+  uint32_t* v1 = a.take<uint32_t>(round_up(N, 32));
+  uint32_t* counts = a.take<uint32_t>(sort_count_elems(N, 1));
+  PresortView view = presort_view(presorted, n);
+
+  init_header_kernel<<<1, 1, 0, stream>>>(view.hdr, (uint32_t)n, (uint32_t)N, G);
+  VR_CHECK_LAUNCH();
+  dim3 grid((n + 255) / 256, n);
+  triu_keys_kernel<<<grid, 256, 0, stream>>>(rdm, n, ld, k0, v0, view.hdr);
+  VR_CHECK_LAUNCH();
+  int rc = radix_sort_pairs(k0, v0, k1, v1, N, 0, 1, counts, stream);
+  if (rc != VR_OK) return rc;
+  heads_kernel<<<(G + 7) / 8, 256, 0, stream>>>(k0, v0, (uint32_t)N, G, view);
+  VR_CHECK_LAUNCH();
+  head_tables_kernel<<<1, 1024, 0, stream>>>(view.prev_head, view.next_head, (uint32_t)N, G);
+  VR_CHECK_LAUNCH();
+  return VR_OK;
+}
+
+extern "C" size_t vr_rank_rows_workspace_bytes(int n, int64_t d) {
+  if (n < 1 || d < 1) return 256;
+  return 4 * arena_bytes((size_t)n * d, 4) + arena_bytes(sort_count_elems(d, n), 4) + 256;
+}
+
+extern "C" int vr_rank_rows_ordinal_f32(const float* X, int n, int64_t d, int64_t ldx, float* out,
+                                        void* ws, size_t ws_bytes, vr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  VR_REQUIRE(X && out, "vr_rank_rows_ordinal_f32: null pointer");
+  VR_REQUIRE(n >= 1 && n <= 65535 && d >= 1 && ldx >= d, "vr_rank_rows_ordinal_f32: bad shape n=%d d=%lld ldx=%lld",
+             n, (long long)d, (long long)ldx);
+  VR_REQUIRE((int64_t)n * d < (1ll << 40), "vr_rank_rows_ordinal_f32: too large");
+  if (ws_bytes < vr_rank_rows_workspace_bytes(n, d) || !ws) {
+    set_error("vr_rank_rows_ordinal_f32: workspace %zu < %zu", ws_bytes, vr_rank_rows_workspace_bytes(n, d));
+    return VR_ERR_WORKSPACE;
+  }
+  Arena a(ws, ws_bytes);
+  const size_t tot = (size_t)n * d;
+  uint32_t* k0 = a.take<uint32_t>(tot);
+  uint32_t* v0 = a.take<uint32_t>(tot);
+  uint32_t* k1 = a.take<uint32_t>(tot);
+  uint32_t* v1 = a.take<uint32_t>(tot);
+  uint32_t* counts = a.take<uint32_t>(sort_count_elems(d, n));
+  const int gx = (int)((d + 255) / 256 < 1024 ? (d + 255) / 256 : 1024);
+  dim3 grid(gx, n);
+  row_keys_kernel<<<grid, 256, 0, stream>>>(X, d, ldx, k0, v0);
+  VR_CHECK_LAUNCH();
+  int rc = radix_sort_pairs(k0, v0, k1, v1, d, d, n, counts, stream);
+  if (rc != VR_OK) return rc;
+  row_rank_scatter_kernel<<<grid, 256, 0, stream>>>(v0, d, out);
+  VR_CHECK_LAUNCH();
+  return VR_OK;
+}

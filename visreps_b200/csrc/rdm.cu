@@ -1,0 +1,196 @@
+// Pearson correlation-distance RDM: replaces compute_rdm(), visreps/analysis/rsa.py:59-93.
+//
+//   row_center_kernel   per-stimulus mean / std (fp64 accumulation) and the centred copy Z
+//                       (zero-padded to the SYRK tile grid)                  rsa.py:80-87
+//   syrk kernel         upper-triangular tiles of Z Z^T, split over K        rsa.py:89
+//   rdm_epilogue_kernel sum of K-splits, /d, /(std_i std_j + c), clamp, diag,
+//                       1 - corr, mirrored to the lower triangle              rsa.py:89-92
+//
+// The SYRK here is the fp32 CUDA-core version (exact fp32 products, fp32 accumulation per
+// K-split, fp64 across splits); it is the reference the tcgen05 kernel in syrk_tc.cu is
+// checked against and the path used for shapes below one tensor tile.
+#include "common.cuh"
+
+namespace vr {
+
+constexpr int kTileMN = 64;   // FFMA SYRK output tile
+constexpr int kTileK = 16;
+
+struct RdmPlan {
+  int n_pad;        // multiple of 128 (covers both the FFMA and the tensor tile grids)
+  int64_t d_pad;    // multiple of 32
+  int splits;       // K-splits
+  int64_t k_per_split;  // multiple of 32
+  int nb;           // 64-row blocks
+};
+
+inline RdmPlan rdm_plan(int n, int64_t d) {
+  RdmPlan p;
+  p.n_pad = (int)round_up(n, 128);
+  p.d_pad = round_up(d, 32);
+  p.nb = p.n_pad / kTileMN;
+  const int64_t tiles = (int64_t)p.nb * (p.nb + 1) / 2;
+  // aim for >= 4 waves of CTAs, K-splits of at least 512 and at most 4096 columns
+  int64_t want = (4 * kNumSMs * 4 + tiles - 1) / tiles;
+  int64_t max_splits = (p.d_pad + 511) / 512;
+  int64_t min_splits = (p.d_pad + 4095) / 4096;
+  int64_t s = want;
+  if (s > max_splits) s = max_splits;
+  if (s < min_splits) s = min_splits;
+  if (s < 1) s = 1;
+  p.k_per_split = round_up((p.d_pad + s - 1) / s, 32);
+  p.splits = (int)((p.d_pad + p.k_per_split - 1) / p.k_per_split);
+  return p;
+}
+
+// One CTA per (padded) row.  Rows >= n and columns >= d are written as zeros.
+__global__ void __launch_bounds__(256)
+row_center_kernel(const float* __restrict__ X, int n, int64_t d, int64_t ldx, float correction,
+                  float* __restrict__ Z, int64_t d_pad, float* __restrict__ stdv, int* __restrict__ zero_rows) {
+  __shared__ double s_red[8];
+  __shared__ float s_mean;
+  const int row = blockIdx.x;
+  float* z = Z + (int64_t)row * d_pad;
+  if (row >= n) {
+    for (int64_t c = threadIdx.x; c < d_pad; c += 256) z[c] = 0.f;
+    return;
+  }
+  const float* x = X + (int64_t)row * ldx;
+  double acc = 0.0;
+  for (int64_t c = threadIdx.x; c < d; c += 256) acc += (double)x[c];
+  acc = warp_sum(acc);
+  if (lane_id() == 0) s_red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += s_red[w];
+    s_mean = (float)(t / (double)d);
+  }
+  __syncthreads();
+  const float mean = s_mean;
+  acc = 0.0;
+  for (int64_t c = threadIdx.x; c < d_pad; c += 256) {
+    float v = 0.f;
+    if (c < d) { v = x[c] - mean; acc += (double)v * (double)v; }
+    z[c] = v;
+  }
+  acc = warp_sum(acc);
+  __syncthreads();
+  if (lane_id() == 0) s_red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += s_red[w];
+    float sd = (float)sqrt(t / (double)d + (double)correction);
+    if (sd < correction * 10.f) { sd = 1.f; if (zero_rows) atomicAdd(zero_rows, 1); }
+    stdv[row] = sd;
+  }
+}
+
+__device__ __forceinline__ void decode_tile(int t, int nb, int& bi, int& bj) {
+  bi = 0;
+  while (t >= nb - bi) { t -= nb - bi; ++bi; }
+  bj = bi + t;
+}
+
+// partial[split][i][j] for i-block <= j-block.  256 threads, each a 4x4 micro-tile.
+__global__ void __launch_bounds__(256)
+syrk_ffma_kernel(const float* __restrict__ Z, int64_t d_pad, int n_pad, int nb, int64_t k_per_split,
+                 float* __restrict__ partial) {
+  __shared__ float As[kTileK][kTileMN + 4];
+  __shared__ float Bs[kTileK][kTileMN + 4];
+  int bi, bj;
+  decode_tile(blockIdx.x, nb, bi, bj);
+  const int split = blockIdx.y;
+  const int64_t k0 = (int64_t)split * k_per_split;
+  const int64_t k1 = min(d_pad, k0 + k_per_split);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  // loader mapping: 64 rows x 16 cols = 1024 floats = 256 threads x float4
+  const int lrow = threadIdx.x >> 2, lcol = (threadIdx.x & 3) * 4;
+  const float* a_src = Z + (int64_t)(bi * kTileMN + lrow) * d_pad + lcol;
+  const float* b_src = Z + (int64_t)(bj * kTileMN + lrow) * d_pad + lcol;
+  float acc[4][4] = {};
+  for (int64_t k = k0; k < k1; k += kTileK) {
+    const float4 av = *reinterpret_cast<const float4*>(a_src + k);
+    const float4 bv = *reinterpret_cast<const float4*>(b_src + k);
+    __syncthreads();
+    As[lcol + 0][lrow] = av.x; As[lcol + 1][lrow] = av.y; As[lcol + 2][lrow] = av.z; As[lcol + 3][lrow] = av.w;
+    Bs[lcol + 0][lrow] = bv.x; Bs[lcol + 1][lrow] = bv.y; Bs[lcol + 2][lrow] = bv.z; Bs[lcol + 3][lrow] = bv.w;
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kTileK; ++kk) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(a[x], b[y], acc[x][y]);
+    }
+  }
+  float* out = partial + (int64_t)split * n_pad * n_pad;
+#pragma unroll
+  for (int x = 0; x < 4; ++x) {
+    const int i = bi * kTileMN + ty * 4 + x;
+    float4 v = make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]);
+    *reinterpret_cast<float4*>(out + (int64_t)i * n_pad + bj * kTileMN + tx * 4) = v;
+  }
+}
+
+// One thread per (i <= j).  Mirrors to (j, i).
+__global__ void __launch_bounds__(256)
+rdm_epilogue_kernel(const float* __restrict__ partial, int splits, int n_pad, int n, int64_t d,
+                    const float* __restrict__ stdv, float correction, float* __restrict__ rdm) {
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  const int i = blockIdx.y;
+  if (j >= n || j < i) return;
+  if (i == j) { rdm[(int64_t)i * n + i] = 0.f; return; }
+  double g = 0.0;
+  const int64_t plane = (int64_t)n_pad * n_pad;
+  for (int s = 0; s < splits; ++s) g += (double)partial[s * plane + (int64_t)i * n_pad + j];
+  const float cov = (float)(g / (double)d);
+  float corr = cov / (stdv[i] * stdv[j] + correction);
+  corr = fminf(fmaxf(corr, -1.f), 1.f);
+  const float v = 1.0f - corr;
+  rdm[(int64_t)i * n + j] = v;
+  rdm[(int64_t)j * n + i] = v;
+}
+
+}  // namespace vr
+
+using namespace vr;
+
+extern "C" size_t vr_rdm_workspace_bytes(int n, int64_t d) {
+  if (n < 1 || d < 1) return 256;
+  RdmPlan p = rdm_plan(n, d);
+  return arena_bytes((size_t)p.n_pad * p.d_pad, 4) + arena_bytes(p.n_pad, 4) +
+         arena_bytes((size_t)p.splits * p.n_pad * p.n_pad, 4) + 256;
+}
+
+extern "C" int vr_rdm_pearson_f32(const float* X, int n, int64_t d, int64_t ldx, float correction, float* rdm,
+                                  int* zero_var_rows, void* ws, size_t ws_bytes, vr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  VR_REQUIRE(X && rdm, "vr_rdm_pearson_f32: null pointer");
+  VR_REQUIRE(n >= 1 && n <= VR_MAX_STIMULI && d >= 1 && ldx >= d, "vr_rdm_pearson_f32: bad shape n=%d d=%lld ldx=%lld",
+             n, (long long)d, (long long)ldx);
+  if (!ws || ws_bytes < vr_rdm_workspace_bytes(n, d)) {
+    set_error("vr_rdm_pearson_f32: workspace %zu < %zu", ws_bytes, vr_rdm_workspace_bytes(n, d));
+    return VR_ERR_WORKSPACE;
+  }
+  RdmPlan p = rdm_plan(n, d);
+  Arena a(ws, ws_bytes);
+  float* Z = a.take<float>((size_t)p.n_pad * p.d_pad);
+  float* stdv = a.take<float>(p.n_pad);
+  float* partial = a.take<float>((size_t)p.splits * p.n_pad * p.n_pad);
+  if (zero_var_rows) VR_CHECK_CUDA(cudaMemsetAsync(zero_var_rows, 0, sizeof(int), stream));
+  row_center_kernel<<<p.n_pad, 256, 0, stream>>>(X, n, d, ldx, correction, Z, p.d_pad, stdv, zero_var_rows);
+  VR_CHECK_LAUNCH();
+  dim3 grid(p.nb * (p.nb + 1) / 2, p.splits);
+  syrk_ffma_kernel<<<grid, 256, 0, stream>>>(Z, p.d_pad, p.n_pad, p.nb, p.k_per_split, partial);
+  VR_CHECK_LAUNCH();
+  dim3 eg((n + 255) / 256, n);
+  rdm_epilogue_kernel<<<eg, 256, 0, stream>>>(partial, p.splits, p.n_pad, n, d, stdv, correction, rdm);
+  VR_CHECK_LAUNCH();
+  return VR_OK;
+}

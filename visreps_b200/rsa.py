@@ -1,0 +1,414 @@
+"""Host-side mirror of the reference RSA interface, backed by the sm_100a CUDA library.
+
+Same names, argument meaning, return types and error behaviour as
+/root/reference/visreps/analysis/rsa.py (compute_rdm :59-93, compute_rdm_correlation :96-129,
+compute_rsa :132-281, _rank :50-52, _concept_average_exact :284-305) plus the bootstrap helper
+the reference inlines three times (visreps/evals.py:355-373, :506-522) and spells out once
+(experiments/reconstruction_analysis/run_reconstruction.py:137-158).
+
+Division of labour: this module validates arguments, draws the bootstrap index sets on the host
+from numpy's RandomState exactly as the reference does, moves tensors, and calls the C ABI
+(include/visreps_b200.h).  All arithmetic on the path runs in the CUDA library.  There is no CPU
+fallback: without the library or without a CUDA device every function raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+from typing import Dict, List, Optional, Sequence, Tuple, TYPE_CHECKING
+
+import numpy as np
+import torch
+
+from . import _lib
+
+if TYPE_CHECKING:  # pragma: no cover
+    from .alignment import AlignmentData
+
+logger = logging.getLogger(__name__)
+
+SUBSAMPLE_FRACTION = 0.9  # rsa.py:234 / evals.py:358
+_METHODS = ("pearson", "spearman", "kendall")
+_MAX_GROUP = 32  # vectors per side in one grouped library call (library limit: 64 in total)
+
+
+# --------------------------------------------------------------------------- helpers
+def _as_cuda_f32_rows(t: torch.Tensor, dev: torch.device) -> torch.Tensor:
+    """fp32 CUDA view/copy whose rows are unit-stride (row pitch may exceed the width)."""
+    x = t.detach()
+    if x.device != dev:
+        x = x.to(dev, non_blocking=True)
+    if x.dtype != torch.float32:
+        x = x.float()
+    if x.dim() != 2:
+        raise ValueError("expected a 2-D tensor")
+    if x.size(1) > 1 and x.stride(1) != 1 or x.stride(0) < x.size(1):
+        x = x.contiguous()
+    return x
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class PresortedRDM:
+    """An RDM's strict upper triangle sorted once on the device (opaque library blob).
+
+    Every comparison / bootstrap replicate of this RDM is ranked from the blob without
+    sorting again.  Keeps the source RDM alive for the Pearson path.
+    """
+
+    def __init__(self, rdm: torch.Tensor):
+        lib = _lib.load()
+        dev = _lib.require_cuda()
+        self.rdm = _as_cuda_f32_rows(rdm, dev)
+        if self.rdm.size(0) != self.rdm.size(1):
+            raise ValueError("RDM must be square")
+        self.n = int(self.rdm.size(0))
+        self.blob = torch.empty(lib.vr_presort_bytes(self.n), dtype=torch.uint8, device=dev)
+        ws = _lib.workspace(lib.vr_presort_workspace_bytes(self.n), dev)
+        _lib.check(lib.vr_presort_triu_f32(self.rdm.data_ptr(), self.n, self.rdm.stride(0), self.blob.data_ptr(),
+                                           ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "vr_presort_triu_f32")
+
+
+def full_mask(n: int) -> np.ndarray:
+    """All-stimuli membership mask (uint32 words): gives the point estimate."""
+    w = (n + 31) // 32
+    m = np.full(w, 0xFFFFFFFF, dtype=np.uint32)
+    if n % 32:
+        m[-1] = (1 << (n % 32)) - 1
+    return m
+
+
+def build_masks(index_sets: Optional[np.ndarray], n: int, device: torch.device, with_full: bool = True) -> torch.Tensor:
+    """(R, W) int32 device tensor of membership bit masks; row 0 is the full mask if with_full.
+
+    index_sets: host (B, m) integer array, the reference's `rng.choice(n, m, replace=False)` draws.
+    """
+    lib = _lib.load()
+    w = lib.vr_mask_words(n)
+    b = 0 if index_sets is None else int(index_sets.shape[0])
+    masks = torch.empty((b + (1 if with_full else 0), w), dtype=torch.int32, device=device)
+    if with_full:
+        masks[0].copy_(torch.from_numpy(full_mask(n).view(np.int32)), non_blocking=False)
+    if b:
+        idx_host = torch.from_numpy(np.ascontiguousarray(index_sets, dtype=np.int32))
+        if idx_host.numel() and (int(idx_host.min()) < 0 or int(idx_host.max()) >= n):
+            raise ValueError("bootstrap index out of range")
+        idx = idx_host.pin_memory().to(device, non_blocking=True)
+        sub = masks[1:] if with_full else masks
+        _lib.check(lib.vr_build_masks(idx.data_ptr(), b, int(idx.shape[1]), n, sub.data_ptr(), _lib.stream_ptr()),
+                   "vr_build_masks")
+    return masks
+
+
+def draw_index_sets(n: int, n_bootstrap: int, seed: int = 42, rng: Optional[np.random.RandomState] = None) -> np.ndarray:
+    """Host RNG stream of the reference bootstrap: B x int(0.9 n) draws without replacement,
+    in draw order (evals.py:356-364; rsa.py:249-251)."""
+    rng = np.random.RandomState(seed) if rng is None else rng
+    m = int(n * SUBSAMPLE_FRACTION)
+    out = np.empty((n_bootstrap, m), dtype=np.int32)
+    for b in range(n_bootstrap):
+        out[b] = rng.choice(n, size=m, replace=False)
+    return out
+
+
+def _ptr_array(tensors: Sequence[torch.Tensor]):
+    arr = (C.c_void_p * len(tensors))()
+    for k, t in enumerate(tensors):
+        arr[k] = t.data_ptr()
+    return arr
+
+
+def compare_grouped(model: Sequence[PresortedRDM], neural: Sequence[PresortedRDM], method: str,
+                    masks: torch.Tensor) -> torch.Tensor:
+    """(nA, nB, R) fp64 device tensor: every model RDM x every neural RDM x every mask."""
+    lib = _lib.load()
+    method = method.lower()
+    if method not in _METHODS:
+        raise ValueError("correlation must be 'Pearson', 'Spearman', or 'Kendall'")
+    if method == "kendall":
+        raise NotImplementedError("Kendall tau-a is not built on the device yet (SURVEY.md section 8f-1); "
+                                  "there is deliberately no CPU fallback")
+    n = model[0].n
+    if any(p.n != n for p in list(model) + list(neural)):
+        raise ValueError("RDMs must share the same 2-D shape")
+    dev = masks.device
+    nA, nB, R = len(model), len(neural), int(masks.shape[0])
+    out = torch.empty((nA, nB, R), dtype=torch.float64, device=dev)
+    for a0 in range(0, nA, _MAX_GROUP):
+        for b0 in range(0, nB, _MAX_GROUP):
+            ma, mb = model[a0:a0 + _MAX_GROUP], neural[b0:b0 + _MAX_GROUP]
+            full = len(ma) == nA and len(mb) == nB
+            part = out if full else torch.empty((len(ma), len(mb), R), dtype=torch.float64, device=dev)
+            if method == "spearman":
+                pa, pb = _ptr_array([p.blob for p in ma]), _ptr_array([p.blob for p in mb])
+                ws = _lib.workspace(lib.vr_bootstrap_spearman_workspace_bytes(n, len(ma), len(mb), R), dev)
+                _lib.check(lib.vr_bootstrap_spearman(pa, len(ma), pb, len(mb), n, masks.data_ptr(), R, part.data_ptr(),
+                                                     ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "vr_bootstrap_spearman")
+            else:
+                ld = ma[0].rdm.stride(0)
+                rows = [p.rdm if p.rdm.stride(0) == ld else p.rdm.contiguous() for p in list(ma) + list(mb)]
+                if any(r.stride(0) != ld for r in rows):
+                    rows = [r.contiguous() for r in rows]
+                    ld = n
+                pa, pb = _ptr_array(rows[:len(ma)]), _ptr_array(rows[len(ma):])
+                for r0 in range(0, R, 65535):
+                    rc = min(65535, R - r0)
+                    sub = part if rc == R else torch.empty((len(ma), len(mb), rc), dtype=torch.float64, device=dev)
+                    _lib.check(lib.vr_bootstrap_pearson(pa, len(ma), pb, len(mb), n, ld, masks[r0:r0 + rc].data_ptr(), rc,
+                                                        sub.data_ptr(), None, 0, _lib.stream_ptr()), "vr_bootstrap_pearson")
+                    if sub is not part:
+                        part[:, :, r0:r0 + rc] = sub
+            if not full:
+                out[a0:a0 + len(ma), b0:b0 + len(mb)] = part
+    return out
+
+
+# --------------------------------------------------------------------------- public API
+def _rank(x: torch.Tensor) -> torch.Tensor:
+    """Row-wise 0-based ordinal ranks, fp32 (reference: rsa.py:50-52)."""
+    lib = _lib.load()
+    dev = _lib.require_cuda()
+    src = x.device
+    xs = _as_cuda_f32_rows(x, dev)
+    n, d = int(xs.size(0)), int(xs.size(1))
+    out = torch.empty((n, d), dtype=torch.float32, device=dev)
+    if n and d:
+        ws = _lib.workspace(lib.vr_rank_rows_workspace_bytes(n, d), dev)
+        _lib.check(lib.vr_rank_rows_ordinal_f32(xs.data_ptr(), n, d, xs.stride(0), out.data_ptr(), ws.data_ptr(),
+                                                ws.numel(), _lib.stream_ptr()), "vr_rank_rows_ordinal_f32")
+    return out.to(src)
+
+
+def compute_rdm(representations: torch.Tensor, *, correlation: str = "Pearson", correction: float = 1e-12) -> torch.Tensor:
+    """(n x n) fp32 RDM = 1 - correlation between rows (reference: rsa.py:59-93).
+
+    Diagonal exactly 0, off-diagonal in [0, 2], exactly symmetric.  The input is not modified.
+    The result lives on the input's device.
+    """
+    kind = correlation.lower()
+    if kind not in ("pearson", "spearman"):
+        raise ValueError("correlation must be 'Pearson' or 'Spearman'")
+    lib = _lib.load()
+    dev = _lib.require_cuda()
+    src = representations.device
+    x = _as_cuda_f32_rows(representations, dev)
+    if kind == "spearman":
+        x = _rank(x)
+    n, d = int(x.size(0)), int(x.size(1))
+    rdm = torch.empty((n, n), dtype=torch.float32, device=dev)
+    if n == 0:
+        return rdm.to(src)
+    if d == 0:
+        raise ValueError("representations need at least one feature")
+    flat = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws = _lib.workspace(lib.vr_rdm_workspace_bytes(n, d), dev)
+    _lib.check(lib.vr_rdm_pearson_f32(x.data_ptr(), n, d, x.stride(0), float(correction), rdm.data_ptr(), flat.data_ptr(),
+                                      ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "vr_rdm_pearson_f32")
+    if logger.isEnabledFor(logging.WARNING):
+        nz = int(flat.item())
+        if nz:
+            logger.warning("%d/%d rows have ~zero variance for %s RDM", nz, n, correlation)
+    return rdm.to(src)
+
+
+def compute_rdm_correlation(rdm1: torch.Tensor, rdm2: torch.Tensor, *, correlation: str = "Kendall") -> float:
+    """Correlation of two RDMs over the strict upper triangle (reference: rsa.py:96-129).
+
+    NaN (not an exception) when the correlation is undefined."""
+    if rdm1.shape != rdm2.shape or rdm1.ndim != 2:
+        raise ValueError("RDMs must share the same 2-D shape")
+    n = rdm1.size(0)
+    if n <= 1:
+        logger.warning("RDM dimension <= 1; correlation undefined")
+        return float("nan")
+    kind = correlation.lower()
+    if kind not in _METHODS:
+        raise ValueError("correlation must be 'Pearson', 'Spearman', or 'Kendall'")
+    dev = _lib.require_cuda()
+    a, b = PresortedRDM(rdm1) if kind == "spearman" else _RawRDM(rdm1), \
+        PresortedRDM(rdm2) if kind == "spearman" else _RawRDM(rdm2)
+    masks = build_masks(None, int(n), dev, with_full=True)
+    val = float(compare_grouped([a], [b], kind, masks)[0, 0, 0].item())
+    if np.isnan(val):
+        logger.warning("NaN returned for %s correlation", correlation)
+        return float("nan")
+    return val
+
+
+class _RawRDM:
+    """RDM on the device without a presort (Pearson comparisons need only the matrix)."""
+
+    def __init__(self, rdm: torch.Tensor):
+        dev = _lib.require_cuda()
+        self.rdm = _as_cuda_f32_rows(rdm, dev)
+        if self.rdm.size(0) != self.rdm.size(1):
+            raise ValueError("RDM must be square")
+        self.n = int(self.rdm.size(0))
+
+
+def _prepare(rdm, method: str):
+    if isinstance(rdm, (PresortedRDM, _RawRDM)):
+        return rdm
+    return PresortedRDM(rdm) if method == "spearman" else _RawRDM(rdm)
+
+
+def bootstrap_rdm_correlation_grouped(model_rdms: Sequence, neural_rdms: Sequence, method: str,
+                                      n_bootstrap: int = 1000, seed: int = 42,
+                                      index_sets: Optional[np.ndarray] = None,
+                                      rng: Optional[np.random.RandomState] = None,
+                                      replicate_range: Optional[Tuple[int, int]] = None) -> Dict[str, np.ndarray]:
+    """Point estimates and bootstrap scores for every (model RDM, neural RDM) pair in one pass.
+
+    Every pair sees the SAME index sets, which is what the reference does by re-seeding
+    RandomState(42) per (region, subject) (evals.py:356).  Returns host arrays
+    {"point": (nA, nB), "scores": (nA, nB, B)} with replicates in draw order.
+    replicate_range=(lo, hi) computes only that slice of the draws (multi-GPU sharding).
+    """
+    method = method.lower()
+    dev = _lib.require_cuda()
+    A = [_prepare(r, method) for r in model_rdms]
+    B = [_prepare(r, method) for r in neural_rdms]
+    n = A[0].n
+    if index_sets is None:
+        index_sets = draw_index_sets(n, n_bootstrap, seed, rng)
+    if replicate_range is not None:
+        index_sets = index_sets[replicate_range[0]:replicate_range[1]]
+    masks = build_masks(index_sets, n, dev, with_full=True)
+    out = compare_grouped(A, B, method, masks).cpu().numpy()
+    return {"point": out[:, :, 0].copy(), "scores": out[:, :, 1:].copy()}
+
+
+def bootstrap_rdm_correlation(model_rdm, neural_rdm, method: str, n_bootstrap: int = 1000, seed: int = 42):
+    """(score, ci_low, ci_high, scores) -- the reference's helper of the same name
+    (run_reconstruction.py:137-158) and its inlined twins (evals.py:355-373, :506-522)."""
+    res = bootstrap_rdm_correlation_grouped([model_rdm], [neural_rdm], method, n_bootstrap, seed)
+    scores = res["scores"][0, 0]
+    return (float(res["point"][0, 0]), float(np.percentile(scores, 2.5)), float(np.percentile(scores, 97.5)),
+            scores.tolist())
+
+
+def _flat(a: torch.Tensor) -> torch.Tensor:
+    return a.flatten(start_dim=1) if a.ndim > 2 else a
+
+
+def compute_rsa(cfg: Dict, selection: "AlignmentData", evaluation: "AlignmentData", n_select: Optional[int] = None,
+                bootstrap: bool = True, n_bootstrap: int = 1000, seed: int = 42, verbose: bool = False,
+                re_extract_fn=None) -> List[Dict]:
+    """Train/test RSA (reference: rsa.py:132-281): pick the best layer on `selection`,
+    score it on `evaluation`, optional 90 %-subsample bootstrap CI.
+
+    One RandomState(seed) feeds the optional selection subsample first and the bootstrap draws
+    afterwards, exactly as the reference consumes it (rsa.py:169,176,249).
+    """
+    method = cfg.get("compare_method", "spearman").lower()
+    rng = np.random.RandomState(seed)
+    n_train = selection.neural.size(0)
+    n_test = evaluation.neural.size(0)
+    if n_select is not None and n_select < n_train:
+        sel_idx = rng.choice(n_train, size=n_select, replace=False)
+    else:
+        sel_idx = np.arange(n_train)
+    if verbose:
+        print(f"Train/test RSA: {n_train} train, {n_test} test, {len(sel_idx)} for layer selection; "
+              f"Pearson RDMs, {method.capitalize()} comparison")
+
+    # 1. layer selection: all layers against the neural RDM in one grouped device call
+    if method not in _METHODS:
+        raise ValueError("correlation must be 'Pearson', 'Spearman', or 'Kendall'")
+    if method == "kendall":
+        raise NotImplementedError("compare_method=kendall is not built on the device yet (SURVEY.md section 8f-1); "
+                                  "there is deliberately no CPU fallback")
+    dev = _lib.require_cuda()
+    neural_sel = _prepare(compute_rdm(selection.neural[sel_idx].to(dev)), method)
+    names = list(selection.activations.keys())
+    layer_rdms = [_prepare(compute_rdm(_flat(selection.activations[k][sel_idx]).to(dev)), method) for k in names]
+    full = build_masks(None, len(sel_idx), dev, with_full=True)
+    sel = compare_grouped(layer_rdms, [neural_sel], method, full)[:, 0, 0].cpu().numpy()
+    selection_scores, best_layer, best_score = [], None, -float("inf")
+    for name, s in zip(names, sel):
+        s = float(s)
+        selection_scores.append({"layer": name, "score": s})
+        if verbose:
+            print(f"  [select] {name:<15} RSA = {s:.4f}")
+        if s > best_score:
+            best_score, best_layer = s, name
+    del layer_rdms
+
+    # 2. evaluation RDMs (exact re-extraction if a callback is supplied, rsa.py:212-218)
+    if re_extract_fn is not None:
+        exact_acts, _ = re_extract_fn(best_layer, evaluation.stimulus_ids)
+        test_acts = _flat(exact_acts)
+    else:
+        test_acts = _flat(evaluation.activations[best_layer])
+    neural_rdm = compute_rdm(evaluation.neural.to(dev))
+    model_rdm = compute_rdm(test_acts.to(dev))
+
+    # 3. point estimate + bootstrap in one grouped call (mask 0 = all stimuli)
+    idx = None
+    if bootstrap:
+        idx = draw_index_sets(n_test, n_bootstrap, rng=rng)
+    if n_test <= 1:
+        point, scores = float("nan"), np.full(n_bootstrap if bootstrap else 0, np.nan)
+    else:
+        masks = build_masks(idx, n_test, dev, with_full=True)
+        out = compare_grouped([_prepare(model_rdm, method)], [_prepare(neural_rdm, method)], method, masks)[0, 0].cpu().numpy()
+        point, scores = float(out[0]), out[1:]
+    ci_low = ci_high = None
+    result = {"layer": best_layer, "compare_method": method, "score": point, "ci_low": None, "ci_high": None,
+              "analysis": "rsa", "layer_selection_scores": selection_scores}
+    if bootstrap:
+        ci_low, ci_high = float(np.percentile(scores, 2.5)), float(np.percentile(scores, 97.5))
+        result["ci_low"], result["ci_high"] = ci_low, ci_high
+        result["bootstrap_scores"] = scores.tolist()
+    if verbose:
+        msg = f"  {method.capitalize():<10}| {best_layer} = {point:.4f}"
+        if bootstrap:
+            msg += f"  [95% CI: {ci_low:.4f}, {ci_high:.4f}]"
+        print(msg)
+    return [result]
+
+
+def _concept_average_exact(raw_acts: torch.Tensor, raw_ids, data) -> torch.Tensor:
+    """Per-concept mean of per-image activations, in data.stimulus_ids order (reference: rsa.py:284-305).
+
+    Producer-side glue: stays in PyTorch, one index_add instead of a Python loop."""
+    where = {str(k): i for i, k in enumerate(raw_ids)}
+    rows, owner = [], []
+    for c, concept in enumerate(data.stimulus_ids):
+        for sid in data.concept_image_ids[concept]:
+            if sid in where:
+                rows.append(where[sid])
+                owner.append(c)
+    n_c = len(data.stimulus_ids)
+    out = torch.zeros((n_c, raw_acts.size(1)), dtype=torch.float32, device=raw_acts.device)
+    if rows:
+        r = torch.as_tensor(rows, device=raw_acts.device)
+        o = torch.as_tensor(owner, device=raw_acts.device)
+        out.index_add_(0, o, raw_acts[r].float())
+        cnt = torch.bincount(o, minlength=n_c).clamp_(min=1).to(out.dtype)
+        out /= cnt[:, None]
+    return out.to(raw_acts.dtype)
+
+
+def subsample_rank(rdm, masks: torch.Tensor):
+    """Centred tie-averaged ranks of every masked subsample of one RDM's upper triangle.
+
+    Returns (dev, ss, nkept): dev is (R, N) int32 with dev = 2*rank - (N_r + 1) for kept pairs and
+    0 elsewhere (canonical triu order), ss = sum(dev**2) per replicate, nkept = N_r.
+    With the all-ones mask, dev + N + 1 is 2 * scipy.stats.rankdata(triu_vector, 'average').
+    """
+    lib = _lib.load()
+    p = rdm if isinstance(rdm, PresortedRDM) else PresortedRDM(rdm)
+    dev_ = masks.device
+    R = int(masks.shape[0])
+    stride = lib.vr_dev_stride(p.n)
+    out = torch.empty((R, stride), dtype=torch.int32, device=dev_)
+    ss = torch.empty(R, dtype=torch.float64, device=dev_)
+    nk = torch.empty(R, dtype=torch.int64, device=dev_)
+    ws = _lib.workspace(lib.vr_subsample_rank_workspace_bytes(p.n), dev_)
+    _lib.check(lib.vr_subsample_rank(p.blob.data_ptr(), p.n, masks.data_ptr(), R, out.data_ptr(), ss.data_ptr(),
+                                     nk.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "vr_subsample_rank")
+    N = p.n * (p.n - 1) // 2
+    return out[:, :N], ss, nk
