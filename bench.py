@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- bootstrap RSA replicates/s (and RDM TFLOP/s) on B200, next to the reference CPU path.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # reference CPU path (oracle port) on host cores
+
+Workload (BASELINE.json metric / north_star target): NSD shared-1000 shape --
+n = 1000 stimuli, one model = 8 AlexNet layers (conv1..fc8, 494,184 features in total) x 8 ROI
+response matrices, Pearson RDMs + Spearman comparison, 1000 bootstrap replicates per (layer, ROI) pair.
+One step = one whole pass of the hot path over that input: 16 RDMs, 16 presorts, 64 point estimates,
+64 x 1000 replicate comparisons, percentile CIs.  value = replicate comparisons per second.
+With N GPUs every rank scores its own model (same ROIs) -- the granularity-sweep sharding of
+BASELINE config 4 -- and the per-replicate score vectors are combined with one NCCL all-gather per
+step (weak scaling; value = all ranks' replicates / max-over-ranks time).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+METRIC = "bootstrap_rsa_replicates_per_s"
+UNIT = "replicates/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=1000, help="stimuli")
+    ap.add_argument("--n-bootstrap", type=int, default=1000)
+    ap.add_argument("--small", action="store_true", help="shrunken layer widths (smoke runs only; not a valid bench)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_dims(args):
+    from visreps_b200 import synth
+    layers, rois = dict(synth.ALEXNET_DIMS), dict(synth.NSD_ROIS)
+    if args.small:
+        layers = {k: max(64, v // 64) for k, v in layers.items()}
+        rois = {k: max(32, v // 8) for k, v in rois.items()}
+    return layers, rois
+
+
+def config_dict(args, layers, rois, world):
+    return {
+        "workload": f"NSD shared-1000 shape: n={args.n}, {len(layers)} AlexNet layers x {len(rois)} ROIs, "
+                    f"Pearson RDM + Spearman compare, {args.n_bootstrap} bootstrap replicates per pair"
+                    + (" [SMALL smoke variant]" if args.small else ""),
+        "n_stimuli": args.n, "layers": layers, "rois": rois, "n_bootstrap": args.n_bootstrap,
+        "pairs_per_gpu": len(layers) * len(rois), "sharding": f"one model per GPU x{world}, 1 all-gather of scores per step",
+        "l2_policy": "inputs (2.05 GB of features per model) exceed the 126 MB L2; no flush needed",
+    }
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm / cpu baseline (host cores; the only place bench.py executes oracle/)
+# ----------------------------------------------------------------------------------------------
+def reference_sampler(args, layers, rois):
+    from oracle import cpu_bench
+    return cpu_bench.ReferenceSampler(args.n, layers, rois, args.n_bootstrap)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    layers, rois = workload_dims(args)
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    smp = reference_sampler(args, layers, rois)
+    t_rdm = smp.time_rdms()                      # measured once (seconds-long); reused by every step
+    for _ in range(args.warmup):
+        smp.step(t_rdm)
+    vals, jobs = [], []
+    for _ in range(args.steps):
+        r = smp.step(t_rdm)
+        vals.append(r["value"])
+        jobs.append(r["job_seconds"])
+    smp.close()
+    v = float(np.mean(vals))
+    line = {
+        "metric": METRIC, "value": v, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": float(np.mean(jobs)) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 RDM (CPU sgemm) / f64 Spearman (SciPy)", "data": "synthetic",
+        "config": config_dict(args, layers, rois, world),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": smp.cores, "kind": "port", "sample": smp.sample_description(),
+                         "t_rdm_s": t_rdm},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "ms_per_step is the whole-job time scaled from the bounded sample; a CPU job does not speed up with --gpus",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(gpu_index), "-lms", "100"], stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, mx, reasons = [], [], set()
+        for ln in self.tmp.read().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.tmp.name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    layers, rois = workload_dims(args)
+
+    # CPU baseline first: it forks worker processes, which must happen before CUDA is initialised
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        smp = reference_sampler(args, layers, rois)
+        r = smp.step()
+        cpu_baseline = {"value": r["value"], "unit": UNIT, "cores": smp.cores, "kind": "port",
+                        "sample": smp.sample_description(), "t_rdm_s": r["t_rdm"],
+                        "s_per_replicate_per_core": r["per_compare_s_per_core"]}
+        smp.close()
+        torch.set_num_threads(max(1, min(8, smp.cores)))
+
+    import torch.distributed as dist
+    import visreps_b200 as vb
+    from visreps_b200 import _lib, synth
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    feats, neur = synth.nsd_workload(args.n, dev, seed=rank, layers=layers, rois=rois)
+    X = [x for _, x in feats]
+    Y = [y for _, y in neur]
+    nA, nB, B = len(X), len(Y), args.n_bootstrap
+    in_bytes = sum(t.numel() * 4 for t in X + Y)
+    gathered = torch.empty((world, nA, nB, B + 1), dtype=torch.float64, device=dev) if world > 1 else None
+
+    def step_device():
+        res = vb.rsa_grouped(X, Y, "spearman", bootstrap=True, n_bootstrap=B, seed=42)
+        if world > 1:   # the one exchange step of the path: per-replicate score vectors, replicate order kept
+            mine = torch.from_numpy(np.concatenate([res["point"][:, :, None], res["scores"]], axis=2)).to(dev)
+            dist.all_gather_into_tensor(gathered, mine)
+        return res
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, profile=False):
+        barrier()
+        if profile:
+            _lib.profile_start()
+        l0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        last = None
+        for _ in range(steps):
+            last = fn()
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = e0.elapsed_time(e1)
+        prof = _lib.profile_stop() if profile else None
+        launches = _lib.launch_count() - l0
+        t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1]), prof, launches, last
+
+    for _ in range(args.warmup):
+        step_device()
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    ms_dev, wall_dev, prof, launches, res = timed(step_device, args.steps, profile=True)
+    clock_info = clocks.stop() if clocks else None
+
+    # ---- end to end: host (pinned) inputs -> public API -> host results, copies inside the timed region
+    Xh = [x.cpu().pin_memory() for x in X]
+    Yh = [y.cpu().pin_memory() for y in Y]
+
+    def step_e2e():
+        return step_device_host(Xh, Yh)
+
+    def step_device_host(xh, yh):
+        r = vb.rsa_grouped(xh, yh, "spearman", bootstrap=True, n_bootstrap=B, seed=42)
+        if world > 1:
+            mine = torch.from_numpy(np.concatenate([r["point"][:, :, None], r["scores"]], axis=2)).to(dev)
+            dist.all_gather_into_tensor(gathered, mine)
+        return r
+
+    step_e2e()
+    ms_e2e, wall_e2e, _, _, res_e2e = timed(step_e2e, args.steps)
+    assert np.array_equal(res["scores"], res_e2e["scores"]), "host-input and device-input runs disagree"
+    assert np.isfinite(res["scores"]).all() and np.isfinite(res["point"]).all()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # a step's host work (index draws, percentiles) overlaps device work; the step time is the max
+    # of the device-event time and the wall time between the two synchronised barriers
+    t_step_ms = max(ms_dev, wall_dev) / args.steps
+    t_e2e_ms = max(ms_e2e, wall_e2e) / args.steps
+    units = world * nA * nB * B
+    value = units / (t_step_ms * 1e-3)
+    e2e_value = units / (t_e2e_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel family (device time from CUDA events inside the timed region)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    fam_ms = {k: v["ms"] for k, v in prof.items() if v["ms"] > 0}
+    dom = max(fam_ms, key=fam_ms.get)
+    n = args.n
+    N = n * (n - 1) // 2
+    m = int(n * 0.9)
+    N_sub = m * (m - 1) // 2
+    roofline = None
+    if dom in ("rank", "dot"):
+        per_launch_ms = prof[dom]["ms"] / max(1, prof[dom]["launches"])
+        rankings_per_launch = (nA + nB) * (B + 1)
+        # 8*N_sub bytes per replicate comparison = 4*N_sub per ranked vector (rank kernel);
+        # the dot kernel reads both rank vectors of all nA+nB vectors once: 4*N_sub per vector as well.
+        alg_bytes = rankings_per_launch * 4.0 * N_sub
+        achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": per_launch_ms,
+                    "definition": "4*N_sub bytes per ranked vector x (nA+nB)*(B+1) vectors per launch (SURVEY 8d: 8*N_sub per replicate compare)"}
+    elif dom == "rdm_syrk":
+        flops = sum(n * (n + 1) * t.shape[1] for t in X + Y)
+        tf_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        ach = flops * args.steps / (prof[dom]["ms"] * 1e-3) / 1e12
+        roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
+                    "traffic": None, "peak_source": "measured bf16_tflops_sustained"}
+    rdm_flops = sum(n * (n + 1) * t.shape[1] for t in X + Y) * args.steps
+    rdm_ms = prof["rdm_syrk"]["ms"] + prof["rdm_center"]["ms"] + prof["rdm_epilogue"]["ms"]
+    rdm_tflops = rdm_flops / (rdm_ms * 1e-3) / 1e12 if rdm_ms > 0 else None
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": t_step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 RDM / u32 ranks / i64+f64 Spearman", "data": "synthetic",
+        "config": config_dict(args, layers, rois, world),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(in_bytes + (B * m * 4) + (B + 1) * ((n + 31) // 32) * 4),
+                "d2h_bytes_per_step": int(nA * nB * (B + 1) * 8 + (nA + nB) * 4), "ms_per_step": t_e2e_ms},
+        "gpu_launches": int(launches),
+        "clocks": clock_info,
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "rdm_tflops": rdm_tflops,
+        "rdm_flops_definition": "n(n+1)d per RDM (upper triangle incl. diagonal, 2 flop/MAC), fp32-accurate",
+        "stage_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items() if v["ms"] > 0},
+        "stage_launches_per_step": {k: v["launches"] / args.steps for k, v in prof.items() if v["launches"] > 0},
+        "device_ms_per_step": ms_dev / args.steps, "wall_ms_per_step": wall_dev / args.steps,
+        "score_sample": {"point_00": float(res["point"][0, 0]), "ci_00": [float(res["ci_low"][0, 0]), float(res["ci_high"][0, 0])]},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

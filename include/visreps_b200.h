@@ -51,6 +51,16 @@ const char* vr_last_error_string(void);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 unsigned long long vr_launch_count(void);
 
+/* Built-in stage profiler (no reference counterpart; the reference has no tracing, SURVEY.md
+ * section 5).  Between start and stop every stage of the library brackets its launches with CUDA
+ * events on the caller's stream.  stop() synchronises those events and fills, per family
+ * (vr_profile_family_count() entries, names from vr_profile_family_name()): device milliseconds,
+ * number of bracketed scopes, number of kernel launches.  All three arrays are host, nullable. */
+int vr_profile_family_count(void);
+const char* vr_profile_family_name(int family);
+int vr_profile_start(void);
+int vr_profile_stop(double* ms, unsigned long long* scopes, unsigned long long* launches);
+
 /* ------------------------------------------------------------------------------------
  * RDM construction: replaces compute_rdm(), visreps/analysis/rsa.py:59-93
  *   x -= rowmean; std = sqrt(mean(x^2)+c); std[std<10c] = 1;

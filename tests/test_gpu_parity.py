@@ -51,15 +51,16 @@ def test_rdm_matches_oracle_and_fp64_truth(name, dev, golden_dir):
         assert float(np.abs(orc.triu_vector(g)[::97] - gold[f"{name}/pearson_triu_stride97"]).max()) <= RDM_TOL
 
 
-def test_rdm_known_answers_and_edge_rows(dev, caplog):
+def test_rdm_known_answers_and_edge_rows(dev):
     simple = torch.tensor([[1., 2., 3.], [4., 5., 6.], [1., 2., 3.], [7., 8., 9.]])
     r = vb.compute_rdm(simple.to(dev)).cpu()
     assert float((r - orc.rdm(simple)).abs().max()) <= 1e-6
     assert abs(float(r[0, 2])) < 1e-4
     anti = torch.tensor([[1., 2., 3., 4.], [4., 3., 2., 1.], [1., 1., 1., 1.], [2., 4., 6., 9.]])
-    with caplog.at_level(logging.WARNING):
-        ra = vb.compute_rdm(anti.to(dev)).cpu()
-    assert any("zero variance" in m for m in caplog.messages)      # rsa.py:84-87
+    # constant row: std = sqrt(0 + 1e-12) = 1e-6, which the reference's guard (std < 1e-11, rsa.py:84-87)
+    # does NOT catch; its correlations are 0/(..) = 0, so its distances are exactly 1.
+    ra = vb.compute_rdm(anti.to(dev)).cpu()
+    assert ra[2].tolist() == [1.0, 1.0, 0.0, 1.0]
     assert torch.isfinite(ra).all() and abs(float(ra[0, 1]) - 2.0) < 1e-4
     assert float((ra - orc.rdm(anti)).abs().max()) <= 1e-6
     # n = 1 and n = 0

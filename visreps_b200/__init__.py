@@ -12,6 +12,7 @@ from .rsa import (  # noqa: F401
     compute_rdm_correlation,
     compute_rsa,
     draw_index_sets,
+    rsa_grouped,
     _rank,
     _concept_average_exact,
 )
@@ -19,4 +20,4 @@ from .alignment import AlignmentData, compute_traintest_alignment, _align_stimul
 from .install import install, uninstall  # noqa: F401
 
 __all__ = ["compute_rdm", "compute_rdm_correlation", "compute_rsa", "bootstrap_rdm_correlation",
-           "bootstrap_rdm_correlation_grouped", "AlignmentData", "compute_traintest_alignment", "install", "uninstall"]
+           "bootstrap_rdm_correlation_grouped", "rsa_grouped", "AlignmentData", "compute_traintest_alignment", "install", "uninstall"]

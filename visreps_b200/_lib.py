@@ -24,6 +24,10 @@ SIGNATURES = {
     "vr_abi_version": (_i, []),
     "vr_last_error_string": (C.c_char_p, []),
     "vr_launch_count": (C.c_ulonglong, []),
+    "vr_profile_family_count": (_i, []),
+    "vr_profile_family_name": (C.c_char_p, [_i]),
+    "vr_profile_start": (_i, []),
+    "vr_profile_stop": (_i, [_vp, _vp, _vp]),
     "vr_rdm_workspace_bytes": (_sz, [_i, _i64]),
     "vr_rdm_pearson_f32": (_i, [_vp, _i, _i64, _i64, _f, _vp, _vp, _vp, _sz, _vp]),
     "vr_rank_rows_workspace_bytes": (_sz, [_i, _i64]),
@@ -112,3 +116,19 @@ def release_workspaces() -> None:
 
 def launch_count() -> int:
     return int(load().vr_launch_count())
+
+
+def profile_start() -> None:
+    check(load().vr_profile_start(), "vr_profile_start")
+
+
+def profile_stop() -> dict:
+    """{family: {"ms": device ms, "scopes": bracketed stages, "launches": kernel launches}}"""
+    lib = load()
+    k = lib.vr_profile_family_count()
+    ms = (C.c_double * k)()
+    sc = (C.c_ulonglong * k)()
+    la = (C.c_ulonglong * k)()
+    check(lib.vr_profile_stop(ms, sc, la), "vr_profile_stop")
+    return {lib.vr_profile_family_name(i).decode(): {"ms": ms[i], "scopes": int(sc[i]), "launches": int(la[i])}
+            for i in range(k)}

@@ -1,6 +1,8 @@
 // Library-level entry points: ABI version, thread-local error text, launch counter.
 #include "common.cuh"
 #include <atomic>
+#include <mutex>
+#include <vector>
 
 namespace vr {
 static thread_local char g_err[512] = "";
@@ -12,8 +14,87 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
-void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- stage profiler ---------------------------------------------------------------------
+static const char* kFamilyNames[F_COUNT] = {"masks", "presort", "rank", "dot", "pearson",
+                                            "rdm_center", "rdm_syrk", "rdm_epilogue", "row_rank"};
+struct ProfRec { int fam; cudaEvent_t a, b; };
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;        // records of the current session
+static std::vector<cudaEvent_t> g_pool;    // recycled events
+static unsigned long long g_fam_launches[F_COUNT];
+static thread_local int t_family = -1;
+
+void count_launch(unsigned n) {
+  g_launches.fetch_add(n, std::memory_order_relaxed);
+  if (g_prof_on && t_family >= 0) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_fam_launches[t_family] += n;
+  }
+}
+
+static cudaEvent_t take_event() {
+  if (!g_pool.empty()) { cudaEvent_t e = g_pool.back(); g_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+ProfScope::ProfScope(int family, cudaStream_t s) : fam(family), stream(s), slot(-1) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (g_prof.size() >= (1u << 20)) return;
+  ProfRec r{family, take_event(), take_event()};
+  if (!r.a || !r.b) return;
+  cudaEventRecord(r.a, stream);
+  g_prof.push_back(r);
+  slot = (int)g_prof.size() - 1;
+  t_family = family;
+}
+ProfScope::~ProfScope() {
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (slot < (int)g_prof.size()) cudaEventRecord(g_prof[slot].b, stream);
+  t_family = -1;
+}
 }  // namespace vr
+
+extern "C" int vr_profile_family_count(void) { return vr::F_COUNT; }
+extern "C" const char* vr_profile_family_name(int i) { return (i >= 0 && i < vr::F_COUNT) ? vr::kFamilyNames[i] : ""; }
+extern "C" int vr_profile_start(void) {
+  std::lock_guard<std::mutex> lk(vr::g_prof_mu);
+  for (auto& r : vr::g_prof) { vr::g_pool.push_back(r.a); vr::g_pool.push_back(r.b); }
+  vr::g_prof.clear();
+  for (int i = 0; i < vr::F_COUNT; ++i) vr::g_fam_launches[i] = 0;
+  vr::g_prof_on = true;
+  return VR_OK;
+}
+extern "C" int vr_profile_stop(double* ms, unsigned long long* scopes, unsigned long long* launches) {
+  std::lock_guard<std::mutex> lk(vr::g_prof_mu);
+  vr::g_prof_on = false;
+  for (int i = 0; i < vr::F_COUNT; ++i) {
+    if (ms) ms[i] = 0.0;
+    if (scopes) scopes[i] = 0;
+    if (launches) launches[i] = vr::g_fam_launches[i];
+  }
+  int rc = VR_OK;
+  for (auto& r : vr::g_prof) {
+    float t = 0.f;
+    if (cudaEventSynchronize(r.b) != cudaSuccess || cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) {
+      vr::set_error("vr_profile_stop: event query failed");
+      rc = VR_ERR_CUDA;
+      (void)cudaGetLastError();
+    } else {
+      if (ms) ms[r.fam] += (double)t;
+      if (scopes) scopes[r.fam] += 1;
+    }
+    vr::g_pool.push_back(r.a);
+    vr::g_pool.push_back(r.b);
+  }
+  vr::g_prof.clear();
+  return rc;
+}
 
 extern "C" int vr_abi_version(void) { return VR_ABI_VERSION; }
 extern "C" const char* vr_last_error_string(void) { return vr::g_err; }

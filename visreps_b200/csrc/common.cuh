@@ -14,6 +14,22 @@ namespace vr {
 void set_error(const char* fmt, ...);
 void count_launch(unsigned n = 1);
 
+// ---- built-in stage profiler (CUDA events on the launching stream) ---------------------
+// Off by default.  Between vr_profile_start() and vr_profile_stop() every ProfScope records a
+// start/stop event pair; stop() synchronises them and returns per-family device time and
+// kernel-launch counts.  bench.py uses it to time the dominant kernel inside the timed region.
+enum Family {
+  F_MASKS = 0, F_PRESORT, F_RANK, F_DOT, F_PEARSON, F_RDM_CENTER, F_RDM_SYRK, F_RDM_EPILOGUE, F_ROWRANK,
+  F_COUNT
+};
+struct ProfScope {
+  int fam;
+  cudaStream_t stream;
+  int slot;
+  ProfScope(int family, cudaStream_t s);
+  ~ProfScope();
+};
+
 #define VR_CHECK_CUDA(expr)                                                              \
   do {                                                                                   \
     cudaError_t _e = (expr);                                                             \
@@ -79,6 +95,9 @@ __host__ __device__ inline uint32_t triu_pos(uint32_t i, uint32_t j, uint32_t n)
 // ---- presorted blob layout --------------------------------------------------------------
 //  [0, 256)          header
 //  stream            uint32[G*32]   packed pairs in ascending value order (+pad words)
+//  pos               uint32[G*32]   inverse permutation: sorted position of canonical pair p
+//  head_bits         uint32[G]      bit l of word g: sorted position 32g+l starts a run
+//                                   (position N, if it falls inside the last group, is set too)
 //  prev_head         uint32[G]      last head position <= 32g+31
 //  next_head         uint32[G+1]    first head position >= 32g   (N if none; [G] = N)
 struct PresortHeader {
@@ -93,13 +112,15 @@ constexpr uint32_t kPresortMagic = 0x56525053u;  // 'VRPS'
 struct PresortView {
   PresortHeader* hdr;
   uint32_t* stream;
+  uint32_t* pos;
+  uint32_t* head_bits;
   uint32_t* prev_head;
   uint32_t* next_head;
 };
 __host__ __device__ inline uint32_t presort_groups(int n) { return (uint32_t)((triu_len(n) + 31) / 32); }
 inline size_t presort_blob_bytes(int n) {
   size_t G = presort_groups(n);
-  return 256 + arena_bytes(G * 32, 4) + arena_bytes(G, 4) + arena_bytes(G + 1, 4);
+  return 256 + 2 * arena_bytes(G * 32, 4) + 2 * arena_bytes(G, 4) + arena_bytes(G + 1, 4);
 }
 __host__ __device__ inline PresortView presort_view(void* blob, int n) {
   size_t G = presort_groups(n);
@@ -109,6 +130,10 @@ __host__ __device__ inline PresortView presort_view(void* blob, int n) {
   p += 256;
   v.stream = reinterpret_cast<uint32_t*>(p);
   p += (G * 32 * 4 + 255) / 256 * 256;
+  v.pos = reinterpret_cast<uint32_t*>(p);
+  p += (G * 32 * 4 + 255) / 256 * 256;
+  v.head_bits = reinterpret_cast<uint32_t*>(p);
+  p += (G * 4 + 255) / 256 * 256;
   v.prev_head = reinterpret_cast<uint32_t*>(p);
   p += (G * 4 + 255) / 256 * 256;
   v.next_head = reinterpret_cast<uint32_t*>(p);

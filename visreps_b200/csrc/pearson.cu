@@ -125,6 +125,7 @@ extern "C" int vr_bootstrap_pearson(const float* const* A, int nA, const float* 
   const int W = vr_mask_words(n);
   const int tiles = ((nA + kPearTile - 1) / kPearTile) * ((nB + kPearTile - 1) / kPearTile);
   dim3 grid(tiles, R);
+  ProfScope prof(F_PEARSON, stream);
   pearson_kernel<<<grid, kPearThreads, (size_t)W * 4, stream>>>(ml, nA, nB, n, ld, masks, W, R, out);
   VR_CHECK_LAUNCH();
   return VR_OK;

@@ -36,7 +36,7 @@ __global__ void init_header_kernel(PresortHeader* hdr, uint32_t n, uint32_t N, u
 // candidates for the prev/next head tables.
 __global__ void __launch_bounds__(256)
 heads_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint32_t N,
-             uint32_t G, PresortView out) {
+             uint32_t G, uint32_t n, PresortView out) {
   const uint32_t g = blockIdx.x * 8u + (threadIdx.x >> 5);
   if (g >= G) return;
   const unsigned lane = lane_id();
@@ -50,9 +50,12 @@ heads_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ val
   if (valid) word = vals[k] | (head ? kHeadBit : 0u);
   else word = kPadBit | (pad_head ? kHeadBit : 0u);
   out.stream[k] = word;
+  if (valid) out.pos[triu_pos(pair_i(word), pair_j(word), n)] = k;
+  else out.pos[k] = 0xFFFFFFFFu;  // positions >= N of the canonical array are padding too
   const uint32_t H = __ballot_sync(0xffffffffu, head);
   const uint32_t Hn = __ballot_sync(0xffffffffu, head || pad_head);
   if (lane == 0) {
+    out.head_bits[g] = Hn;
     out.prev_head[g] = H ? g * 32u + (31u - __clz(H)) : 0u;
     out.next_head[g] = Hn ? g * 32u + (__ffs(Hn) - 1u) : 0xFFFFFFFFu;
     if (H) atomicAdd(&out.hdr->n_runs, (uint32_t)__popc(H));
@@ -144,6 +147,7 @@ extern "C" int vr_presort_triu_f32(const float* rdm, int n, int64_t ld, void* pr
   uint32_t* v1 = a.take<uint32_t>(round_up(N, 32));
   uint32_t* counts = a.take<uint32_t>(sort_count_elems(N, 1));
   PresortView view = presort_view(presorted, n);
+  ProfScope prof(F_PRESORT, stream);
 
   init_header_kernel<<<1, 1, 0, stream>>>(view.hdr, (uint32_t)n, (uint32_t)N, G);
   VR_CHECK_LAUNCH();
@@ -152,7 +156,7 @@ extern "C" int vr_presort_triu_f32(const float* rdm, int n, int64_t ld, void* pr
   VR_CHECK_LAUNCH();
   int rc = radix_sort_pairs(k0, v0, k1, v1, N, 0, 1, counts, stream);
   if (rc != VR_OK) return rc;
-  heads_kernel<<<(G + 7) / 8, 256, 0, stream>>>(k0, v0, (uint32_t)N, G, view);
+  heads_kernel<<<(G + 7) / 8, 256, 0, stream>>>(k0, v0, (uint32_t)N, G, (uint32_t)n, view);
   VR_CHECK_LAUNCH();
   head_tables_kernel<<<1, 1024, 0, stream>>>(view.prev_head, view.next_head, (uint32_t)N, G);
   VR_CHECK_LAUNCH();
@@ -184,6 +188,7 @@ extern "C" int vr_rank_rows_ordinal_f32(const float* X, int n, int64_t d, int64_
   uint32_t* counts = a.take<uint32_t>(sort_count_elems(d, n));
   const int gx = (int)((d + 255) / 256 < 1024 ? (d + 255) / 256 : 1024);
   dim3 grid(gx, n);
+  ProfScope prof(F_ROWRANK, stream);
   row_keys_kernel<<<grid, 256, 0, stream>>>(X, d, ldx, k0, v0);
   VR_CHECK_LAUNCH();
   int rc = radix_sort_pairs(k0, v0, k1, v1, d, d, n, counts, stream);

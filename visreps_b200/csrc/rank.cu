@@ -12,21 +12,24 @@
 // and Spearman rho = sum(devA*devB) / sqrt(sum(devA^2) * sum(devB^2)).
 //
 // rank_kernel: one CTA per (vector, replicate) work item, persistent over items.
-//   pass 1  stream the packed (i,j) words (L2-resident), test membership against the
-//           replicate's n-bit mask in shared memory, ballot -> kept word per 32-group and
-//           running kept count per group (warp-autonomous, one warp scan per 1024 pairs);
-//   pass 2  stream again; run start / end are found with bit tricks on the ballot of head
-//           flags inside the 32-group, falling back to the precomputed prev/next-head tables
-//           only when a run crosses a group boundary; write dev at the pair's canonical
-//           position (every pair is written exactly once: kept -> dev, dropped -> 0).
+//   pass 1  (sorted order) stream the packed (i,j) words, test membership against the
+//           replicate's n-bit mask in shared memory, ballot -> one 32-bit kept word per
+//           32-group plus the running kept count: the table {kept, count} (8 B per group).
+//           The table lives in shared memory when it fits (N <= ~880k pairs), else in an
+//           L2-resident per-CTA scratch.  C(x) is then one table read + popc for ANY x.
+//   pass 2  (canonical order) for each kept pair read its sorted position, find the run
+//           bounds from the head-bit word of its 32-group (bit tricks; prev/next-head tables
+//           only when the run leaves the group), two table reads -> dev.  Reads and the dev
+//           write are fully coalesced; the only random accesses hit the small tables.
 // dot_kernel: per replicate, tiles of 4x4 (model, neural) vectors, exact int64 products.
 #include "common.cuh"
 
 namespace vr {
 
-constexpr int kRankThreads = 256;
+constexpr int kRankThreads = 1024;
 constexpr int kRankWarps = kRankThreads / 32;
 constexpr int kMaxVectors = 64;
+constexpr size_t kRankSmemTableMax = 200 * 1024;   // bytes of shared memory the table may take
 
 struct BlobList {
   const void* p[kMaxVectors];
@@ -43,13 +46,25 @@ __global__ void build_masks_kernel(const int32_t* __restrict__ idx, int R, int m
 
 __device__ __forceinline__ uint32_t low_mask(uint32_t bit) { return (1u << bit) - 1u; }  // bit in [0,31]
 
-// scratch per CTA: kept[Gs] | cnt[Gs]   (Gs = groups rounded up to a multiple of 32, + 32)
-__global__ void __launch_bounds__(kRankThreads, 4)
+// Row of canonical pair p: largest i with i(2n-i-1)/2 <= p.
+__device__ __forceinline__ uint32_t triu_row(uint32_t p, uint32_t n) {
+  const float b = (float)(2u * n - 1u);
+  float disc = b * b - 8.0f * (float)p;
+  int i = (int)((b - sqrtf(fmaxf(disc, 0.f))) * 0.5f);
+  i = max(0, min(i, (int)n - 2));
+  while (i > 0 && (uint32_t)i * (2u * n - (uint32_t)i - 1u) / 2u > p) --i;
+  while ((uint32_t)(i + 1) * (2u * n - (uint32_t)(i + 1) - 1u) / 2u <= p) ++i;
+  return (uint32_t)i;
+}
+
+// Dynamic shared memory: mask words [Wpad] | table uint2[Gs] (only when kSmemTable).
+template <bool kSmemTable>
+__global__ void __launch_bounds__(kRankThreads, 1)
 rank_kernel(const __grid_constant__ BlobList blobs, int n_vectors, int n, const uint32_t* __restrict__ masks,
             int W, int R, int32_t* __restrict__ dev, int64_t dev_stride, double* __restrict__ ss_out,
-            int64_t* __restrict__ nkept_out, uint32_t* __restrict__ scratch, uint32_t Gs) {
-  extern __shared__ uint32_t smem[];
-  uint32_t* s_mask = smem;                         // [W]
+            int64_t* __restrict__ nkept_out, uint2* __restrict__ scratch, uint32_t Gs) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  uint32_t* s_mask = smem;                                   // [round_up(W, 4)]
   __shared__ uint32_t s_segbase[kRankWarps + 1];
   __shared__ double s_red[kRankWarps];
 
@@ -61,8 +76,8 @@ rank_kernel(const __grid_constant__ BlobList blobs, int n_vectors, int n, const 
   const uint32_t sg_per_warp = (SG + kRankWarps - 1) / kRankWarps;
   const uint32_t sg_lo = warp * sg_per_warp;
   const uint32_t sg_hi = min(SG, sg_lo + sg_per_warp);
-  uint32_t* g_kept = scratch + (size_t)blockIdx.x * 2 * Gs;
-  uint32_t* g_cnt = g_kept + Gs;
+  uint2* table = kSmemTable ? reinterpret_cast<uint2*>(smem + ((W + 3) & ~3))
+                            : scratch + (size_t)blockIdx.x * Gs;
 
   const int64_t items = (int64_t)n_vectors * R;
   for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
@@ -72,7 +87,7 @@ rank_kernel(const __grid_constant__ BlobList blobs, int n_vectors, int n, const 
     for (int w = threadIdx.x; w < W; w += kRankThreads) s_mask[w] = masks[(int64_t)r * W + w];
     __syncthreads();
 
-    // ---------------- pass 1: kept words + running counts -----------------------------
+    // ---------------- pass 1: kept words + running counts (sorted order) ----------------
     uint32_t running = 0;
     for (uint32_t sg = sg_lo; sg < sg_hi; ++sg) {
       uint32_t myK = 0;
@@ -96,63 +111,76 @@ rank_kernel(const __grid_constant__ BlobList blobs, int n_vectors, int n, const 
         uint32_t x = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= (unsigned)o) incl += x;
       }
-      g_kept[gbase + lane] = myK;
-      g_cnt[gbase + lane] = running + incl - c;
+      table[gbase + lane] = make_uint2(myK, running + incl - c);
       running += __shfl_sync(0xffffffffu, incl, 31);
     }
     if (lane == 0) s_segbase[warp] = running;
     __syncthreads();
-    if (threadIdx.x == 0) {
-      uint32_t run = 0;
-      for (int w = 0; w < kRankWarps; ++w) { uint32_t t = s_segbase[w]; s_segbase[w] = run; run += t; }
-      s_segbase[kRankWarps] = run;
+    if (warp == 0) {
+      const uint32_t mine = s_segbase[lane];
+      uint32_t incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t x = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (unsigned)o) incl += x;
+      }
+      s_segbase[lane] = incl - mine;
+      if (lane == 31) s_segbase[kRankWarps] = incl;
     }
     __syncthreads();
     const uint32_t Ns = s_segbase[kRankWarps];
-    const uint32_t mybase = s_segbase[warp];
+    {  // make the counts global (add each warp's segment base)
+      const uint32_t mybase = s_segbase[warp];
+      if (mybase)
+        for (uint32_t g = sg_lo * 32u + lane; g < sg_hi * 32u; g += 32u) table[g].y += mybase;
+    }
+    __syncthreads();
 
-    // number of kept pairs at sorted positions < x, for any x in [0, N]
+    // kept pairs at sorted positions < x, x in [0, N]
     auto count_below = [&](uint32_t x) -> uint32_t {
       if (x >= N) return Ns;
-      const uint32_t g = x >> 5;
-      const uint32_t owner = (g >> 5) / sg_per_warp;
-      return s_segbase[owner] + g_cnt[g] + __popc(g_kept[g] & low_mask(x & 31u));
+      const uint2 e = table[x >> 5];
+      return e.y + __popc(e.x & low_mask(x & 31u));
     };
 
-    // ---------------- pass 2: run bounds -> dev, scatter to canonical position ----------
+    // ---------------- pass 2: canonical order, 4 pairs per thread per step ----------------
     int32_t* __restrict__ out = dev + ((int64_t)v * R + r) * dev_stride;
+    const uint32_t* __restrict__ posv = blob.pos;
+    const uint32_t* __restrict__ headw = blob.head_bits;
     double acc = 0.0;
-    for (uint32_t sg = sg_lo; sg < sg_hi; ++sg) {
-      const uint32_t gbase = sg * 32u;
-      const uint32_t myK = g_kept[gbase + lane];
-      const uint32_t myC = g_cnt[gbase + lane];
-#pragma unroll 4
-      for (uint32_t t = 0; t < 32u; ++t) {
-        const uint32_t g = gbase + t;
-        if (g >= G) break;
-        const uint32_t wd = __ldg(stream + (size_t)g * 32u + lane);
-        const uint32_t K = __shfl_sync(0xffffffffu, myK, t);
-        const uint32_t base = mybase + __shfl_sync(0xffffffffu, myC, t);
-        const uint32_t H = __ballot_sync(0xffffffffu, (wd & kHeadBit) != 0u);
-        if (!(wd & kPadBit)) {
-          int32_t d = 0;
-          if ((K >> lane) & 1u) {
-            uint32_t lo, hi;
-            const uint32_t below = H & lanemask_le();
-            if (below) lo = base + __popc(K & low_mask(31u - __clz(below)));
-            else lo = count_below(__ldg(blob.prev_head + g - 1));
-            const uint32_t above = H & lanemask_gt();
-            if (above) hi = base + __popc(K & low_mask(__ffs(above) - 1u));
-            else hi = count_below(__ldg(blob.next_head + g + 1));
-            d = (int32_t)(lo + hi) - (int32_t)Ns;
-            acc += (double)d * (double)d;
+    for (uint32_t p0 = threadIdx.x * 4u; p0 < (uint32_t)dev_stride; p0 += kRankThreads * 4u) {
+      int32_t d4[4] = {0, 0, 0, 0};
+      if (p0 < N) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(posv + p0));
+        const uint32_t xs[4] = {q.x, q.y, q.z, q.w};
+        uint32_t i = triu_row(p0, (uint32_t)n);
+        uint32_t j = p0 - i * (2u * n - i - 1u) / 2u + i + 1u;
+        bool ki = (s_mask[i >> 5] >> (i & 31u)) & 1u;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (p0 + e < N) {
+            if (ki && ((s_mask[j >> 5] >> (j & 31u)) & 1u)) {
+              const uint32_t x = xs[e];
+              const uint32_t g = x >> 5, l = x & 31u;
+              const uint2 te = table[g];
+              const uint32_t H = __ldg(headw + g);
+              uint32_t lo, hi;
+              const uint32_t below = H & (low_mask(l) | (1u << l));
+              if (below) lo = te.y + __popc(te.x & low_mask(31u - __clz(below)));
+              else lo = count_below(__ldg(blob.prev_head + g - 1));
+              const uint32_t above = l == 31u ? 0u : (H >> (l + 1u));
+              if (above) hi = te.y + __popc(te.x & low_mask(l + (uint32_t)__ffs(above)));
+              else hi = count_below(__ldg(blob.next_head + g + 1));
+              const int32_t d = (int32_t)(lo + hi) - (int32_t)Ns;
+              d4[e] = d;
+              acc += (double)d * (double)d;
+            }
+            if (++j == (uint32_t)n) { ++i; j = i + 1u; ki = (s_mask[i >> 5] >> (i & 31u)) & 1u; }
           }
-          out[triu_pos(pair_i(wd), pair_j(wd), (uint32_t)n)] = d;
         }
       }
+      *reinterpret_cast<int4*>(out + p0) = make_int4(d4[0], d4[1], d4[2], d4[3]);
     }
-    // zero the stride padding so the dot kernel can read whole int4s
-    for (int64_t p = (int64_t)N + threadIdx.x; p < dev_stride; p += kRankThreads) out[p] = 0;
 
     acc = warp_sum(acc);
     if (lane == 0) s_red[warp] = acc;
@@ -164,7 +192,7 @@ rank_kernel(const __grid_constant__ BlobList blobs, int n_vectors, int n, const 
       ss_out[(int64_t)v * R + r] = tot;
       nkept_out[(int64_t)v * R + r] = (int64_t)Ns;
     }
-    __syncthreads();  // scratch + s_mask are reused by the next item
+    __syncthreads();  // table + s_mask are reused by the next item
   }
 }
 
@@ -248,30 +276,37 @@ dot_kernel(const int32_t* __restrict__ dev, int64_t dev_stride, const double* __
   }
 }
 
-static int g_rank_ctas_per_sm = 0;
-static int rank_grid(int64_t items, size_t smem) {
-  if (!g_rank_ctas_per_sm) {
-    int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rank_kernel, kRankThreads, smem) != cudaSuccess || occ < 1)
-      occ = 1;
-    g_rank_ctas_per_sm = occ;
-  }
-  int64_t g = (int64_t)kNumSMs * g_rank_ctas_per_sm;
-  return (int)(items < g ? items : g);
+static inline uint32_t table_groups(int n) { return (uint32_t)round_up(presort_groups(n) + 1, 32) + 32u; }
+static inline size_t rank_smem_bytes(int n, bool smem_table) {
+  const size_t mask_bytes = (size_t)round_up(vr_mask_words(n), 4) * 4;
+  return mask_bytes + (smem_table ? (size_t)table_groups(n) * 8 : 0);
 }
-static inline uint32_t scratch_groups(int n) { return (uint32_t)round_up(presort_groups(n) + 1, 32) + 32u; }
+static inline bool rank_table_in_smem(int n) { return (size_t)table_groups(n) * 8 <= kRankSmemTableMax; }
 static inline size_t rank_scratch_bytes(int n) {
-  return arena_bytes((size_t)kNumSMs * 8 * 2 * scratch_groups(n), 4);
+  return rank_table_in_smem(n) ? 256 : arena_bytes((size_t)kNumSMs * table_groups(n), 8);
 }
 
 static int launch_rank(const BlobList& blobs, int nV, int n, const uint32_t* masks, int R, int32_t* dev,
-                       double* ss, int64_t* nkept, uint32_t* scratch, cudaStream_t stream) {
+                       double* ss, int64_t* nkept, void* scratch, cudaStream_t stream) {
   const int W = vr_mask_words(n);
-  const size_t smem = (size_t)W * 4;
-  const int grid = rank_grid((int64_t)nV * R, smem);
-  if (grid > kNumSMs * 8) { set_error("rank grid %d exceeds scratch provisioning", grid); return VR_ERR_CUDA; }
-  rank_kernel<<<grid, kRankThreads, smem, stream>>>(blobs, nV, n, masks, W, R, dev, vr_dev_stride(n), ss, nkept,
-                                                   scratch, scratch_groups(n));
+  const bool in_smem = rank_table_in_smem(n);
+  const size_t smem = rank_smem_bytes(n, in_smem);
+  const int64_t items = (int64_t)nV * R;
+  const int grid = (int)(items < kNumSMs ? items : kNumSMs);
+  ProfScope prof(F_RANK, stream);
+  if (in_smem) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      VR_CHECK_CUDA(cudaFuncSetAttribute(rank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(kRankSmemTableMax + 8192)));
+      attr_set = true;
+    }
+    rank_kernel<true><<<grid, kRankThreads, smem, stream>>>(blobs, nV, n, masks, W, R, dev, vr_dev_stride(n), ss,
+                                                           nkept, nullptr, table_groups(n));
+  } else {
+    rank_kernel<false><<<grid, kRankThreads, smem, stream>>>(blobs, nV, n, masks, W, R, dev, vr_dev_stride(n), ss,
+                                                            nkept, static_cast<uint2*>(scratch), table_groups(n));
+  }
   VR_CHECK_LAUNCH();
   return VR_OK;
 }
@@ -291,6 +326,7 @@ extern "C" int vr_build_masks(const int32_t* idx, int R, int m, int n, uint32_t*
   VR_CHECK_CUDA(cudaMemsetAsync(masks, 0, (size_t)R * W * 4, stream));
   const int64_t tot = (int64_t)R * m;
   if (tot > 0) {
+    ProfScope prof(F_MASKS, stream);
     build_masks_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(idx, R, m, n, W, masks);
     VR_CHECK_LAUNCH();
   }
@@ -312,7 +348,7 @@ extern "C" int vr_subsample_rank(const void* presorted, int n, const uint32_t* m
   }
   BlobList bl{};
   bl.p[0] = presorted;
-  return launch_rank(bl, 1, n, masks, R, dev, ss, nkept, static_cast<uint32_t*>(ws), stream);
+  return launch_rank(bl, 1, n, masks, R, dev, ss, nkept, ws, stream);
 }
 
 namespace {
@@ -360,7 +396,7 @@ extern "C" int vr_bootstrap_spearman(const void* const* A, int nA, const void* c
   if (chunk > R) chunk = R;
   if (chunk > 65535) chunk = 65535;  // grid.y limit of the dot kernel
   Arena a(ws, ws_bytes);
-  uint32_t* scratch = a.take<uint32_t>(rank_scratch_bytes(n) / 4);
+  void* scratch = a.take<char>(rank_scratch_bytes(n));
   double* ss = a.take<double>((size_t)nV * chunk);
   int64_t* nkept = a.take<int64_t>((size_t)nV * chunk);
   int32_t* dev = a.take<int32_t>((size_t)nV * chunk * vr_dev_stride(n));
@@ -372,6 +408,7 @@ extern "C" int vr_bootstrap_spearman(const void* const* A, int nA, const void* c
     int st = launch_rank(bl, nV, n, masks + (size_t)r0 * W, rc, dev, ss, nkept, scratch, stream);
     if (st != VR_OK) return st;
     dim3 grid(tiles, rc);
+    ProfScope prof(F_DOT, stream);
     dot_kernel<<<grid, kDotThreads, 0, stream>>>(dev, vr_dev_stride(n), ss, nA, nB, rc, (int)r0, R, out);
     VR_CHECK_LAUNCH();
   }

@@ -184,12 +184,15 @@ extern "C" int vr_rdm_pearson_f32(const float* X, int n, int64_t d, int64_t ldx,
   float* stdv = a.take<float>(p.n_pad);
   float* partial = a.take<float>((size_t)p.splits * p.n_pad * p.n_pad);
   if (zero_var_rows) VR_CHECK_CUDA(cudaMemsetAsync(zero_var_rows, 0, sizeof(int), stream));
+  { ProfScope prof(F_RDM_CENTER, stream);
   row_center_kernel<<<p.n_pad, 256, 0, stream>>>(X, n, d, ldx, correction, Z, p.d_pad, stdv, zero_var_rows);
-  VR_CHECK_LAUNCH();
+  VR_CHECK_LAUNCH(); }
   dim3 grid(p.nb * (p.nb + 1) / 2, p.splits);
+  { ProfScope prof(F_RDM_SYRK, stream);
   syrk_ffma_kernel<<<grid, 256, 0, stream>>>(Z, p.d_pad, p.n_pad, p.nb, p.k_per_split, partial);
-  VR_CHECK_LAUNCH();
+  VR_CHECK_LAUNCH(); }
   dim3 eg((n + 255) / 256, n);
+  ProfScope prof(F_RDM_EPILOGUE, stream);
   rdm_epilogue_kernel<<<eg, 256, 0, stream>>>(partial, p.splits, p.n_pad, n, d, stdv, correction, rdm);
   VR_CHECK_LAUNCH();
   return VR_OK;

@@ -412,3 +412,74 @@ def subsample_rank(rdm, masks: torch.Tensor):
                                      nk.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "vr_subsample_rank")
     N = p.n * (p.n - 1) // 2
     return out[:, :N], ss, nk
+
+
+def _rdm_device(x: torch.Tensor, dev: torch.device, correction: float, flags: torch.Tensor, slot: int) -> torch.Tensor:
+    """compute_rdm without the host round trip for the zero-variance count (collected in `flags`)."""
+    lib = _lib.load()
+    x = _as_cuda_f32_rows(_flat(x) if x.ndim > 2 else x, dev)
+    n, d = int(x.size(0)), int(x.size(1))
+    rdm = torch.empty((n, n), dtype=torch.float32, device=dev)
+    ws = _lib.workspace(lib.vr_rdm_workspace_bytes(n, d), dev)
+    _lib.check(lib.vr_rdm_pearson_f32(x.data_ptr(), n, d, x.stride(0), float(correction), rdm.data_ptr(),
+                                      flags[slot:slot + 1].data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr()),
+               "vr_rdm_pearson_f32")
+    return rdm
+
+
+def rsa_grouped(model_features: Sequence[torch.Tensor], neural_responses: Sequence[torch.Tensor],
+                method: str = "spearman", bootstrap: bool = True, n_bootstrap: int = 1000, seed: int = 42,
+                correction: float = 1e-12, replicate_range: Optional[Tuple[int, int]] = None,
+                index_sets: Optional[np.ndarray] = None) -> Dict[str, np.ndarray]:
+    """The scoring block of `_eval_rsa` (visreps/evals.py:333-398) for many layers and many
+    (region, subject) response matrices at once, with one host<->device round trip.
+
+    model_features: (n, d_l) activations per layer (host or device; >2-D inputs are flattened like
+    evals.py:321); neural_responses: (n, V_k) per ROI/subject.  For every (layer, ROI) pair:
+    Pearson RDMs -> point estimate (evals.py:347) -> `n_bootstrap` 90 %-subsample replicates with the
+    index sets of RandomState(seed), identical for every pair as in the reference (evals.py:356) ->
+    percentile CI (evals.py:371-372).
+    Returns host arrays: point (nA, nB), scores (nA, nB, B) in draw order, ci_low / ci_high (nA, nB).
+    """
+    method = method.lower()
+    if method not in _METHODS:
+        raise ValueError("correlation must be 'Pearson', 'Spearman', or 'Kendall'")
+    if method == "kendall":
+        raise NotImplementedError("compare_method=kendall is not built on the device yet (SURVEY.md section 8f-1)")
+    dev = _lib.require_cuda()
+    n = int(model_features[0].shape[0])
+    if any(int(t.shape[0]) != n for t in list(model_features) + list(neural_responses)):
+        raise ValueError("all inputs must have the same number of stimuli")
+    nA, nB = len(model_features), len(neural_responses)
+    flags = torch.zeros(nA + nB, dtype=torch.int32, device=dev)
+    # enqueue RDM + presort for every matrix (asynchronous) ...
+    prepared = []
+    for k, x in enumerate(list(model_features) + list(neural_responses)):
+        rdm = _rdm_device(x, dev, correction, flags, k)
+        prepared.append(_prepare(rdm, method))
+    # ... and draw the index sets on the host meanwhile
+    if bootstrap and index_sets is None:
+        index_sets = draw_index_sets(n, n_bootstrap, seed)
+    if not bootstrap:
+        index_sets = None
+    elif replicate_range is not None:
+        index_sets = index_sets[replicate_range[0]:replicate_range[1]]
+    if n <= 1:
+        b = 0 if index_sets is None else len(index_sets)
+        return {"point": np.full((nA, nB), np.nan), "scores": np.full((nA, nB, b), np.nan),
+                "ci_low": np.full((nA, nB), np.nan), "ci_high": np.full((nA, nB), np.nan)}
+    masks = build_masks(index_sets, n, dev, with_full=True)
+    out_dev = compare_grouped(prepared[:nA], prepared[nA:], method, masks)
+    host = torch.empty(out_dev.shape, dtype=torch.float64, pin_memory=True)
+    host.copy_(out_dev, non_blocking=True)
+    flags_host = flags.cpu()            # synchronises the stream: results are complete after this
+    torch.cuda.current_stream().synchronize()
+    nz = int(flags_host.sum())
+    if nz:
+        logger.warning("%d rows have ~zero variance across %d RDMs", nz, nA + nB)
+    out = host.numpy()
+    res = {"point": out[:, :, 0].copy(), "scores": out[:, :, 1:].copy()}
+    if bootstrap and res["scores"].shape[2] > 0:
+        res["ci_low"] = np.percentile(res["scores"], 2.5, axis=2)
+        res["ci_high"] = np.percentile(res["scores"], 97.5, axis=2)
+    return res
