@@ -115,7 +115,7 @@ int vr_build_masks(const int32_t* idx, int R, int m, int n, uint32_t* masks, vr_
  * ss[r] = sum_p dev^2 (fp64), nkept[r] = N_r.
  * ---------------------------------------------------------------------------------- */
 int64_t vr_dev_stride(int n);
-size_t vr_subsample_rank_workspace_bytes(int n);
+size_t vr_subsample_rank_workspace_bytes(int n, int R);
 int vr_subsample_rank(const void* presorted, int n, const uint32_t* masks, int R,
                       int32_t* dev, double* ss, int64_t* nkept,
                       void* ws, size_t ws_bytes, vr_stream_t stream);

@@ -38,7 +38,7 @@ SIGNATURES = {
     "vr_mask_words": (_i, [_i]),
     "vr_build_masks": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "vr_dev_stride": (_i64, [_i]),
-    "vr_subsample_rank_workspace_bytes": (_sz, [_i]),
+    "vr_subsample_rank_workspace_bytes": (_sz, [_i, _i]),
     "vr_subsample_rank": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "vr_bootstrap_spearman_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "vr_bootstrap_spearman": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _vp, _vp, _sz, _vp]),

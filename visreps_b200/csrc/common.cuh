@@ -95,7 +95,8 @@ __host__ __device__ inline uint32_t triu_pos(uint32_t i, uint32_t j, uint32_t n)
 // ---- presorted blob layout --------------------------------------------------------------
 //  [0, 256)          header
 //  stream            uint32[G*32]   packed pairs in ascending value order (+pad words)
-//  pos               uint32[G*32]   inverse permutation: sorted position of canonical pair p
+//  runs              uint32[G*32]   per canonical pair p: the run [s, e) of equal values holding it,
+//                                   packed as s | min(e-s-1, ESC) << sbits   (see run_sbits)
 //  head_bits         uint32[G]      bit l of word g: sorted position 32g+l starts a run
 //                                   (position N, if it falls inside the last group, is set too)
 //  prev_head         uint32[G]      last head position <= 32g+31
@@ -112,11 +113,19 @@ constexpr uint32_t kPresortMagic = 0x56525053u;  // 'VRPS'
 struct PresortView {
   PresortHeader* hdr;
   uint32_t* stream;
-  uint32_t* pos;
+  uint32_t* runs;
   uint32_t* head_bits;
   uint32_t* prev_head;
   uint32_t* next_head;
 };
+// Bits that hold a sorted position (< N); the remaining high bits of a `runs` word hold the run
+// length minus one, saturating at the escape code (all ones): longer runs are resolved from the
+// head tables.
+__host__ __device__ inline uint32_t run_sbits(uint32_t N) {
+  uint32_t b = 1;
+  while (b < 32 && (1ull << b) < (unsigned long long)N + 1ull) ++b;
+  return b;                 // n <= VR_MAX_STIMULI gives N < 2^29, so at least 3 length bits remain
+}
 __host__ __device__ inline uint32_t presort_groups(int n) { return (uint32_t)((triu_len(n) + 31) / 32); }
 inline size_t presort_blob_bytes(int n) {
   size_t G = presort_groups(n);
@@ -130,7 +139,7 @@ __host__ __device__ inline PresortView presort_view(void* blob, int n) {
   p += 256;
   v.stream = reinterpret_cast<uint32_t*>(p);
   p += (G * 32 * 4 + 255) / 256 * 256;
-  v.pos = reinterpret_cast<uint32_t*>(p);
+  v.runs = reinterpret_cast<uint32_t*>(p);
   p += (G * 32 * 4 + 255) / 256 * 256;
   v.head_bits = reinterpret_cast<uint32_t*>(p);
   p += (G * 4 + 255) / 256 * 256;

@@ -50,8 +50,6 @@ heads_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ val
   if (valid) word = vals[k] | (head ? kHeadBit : 0u);
   else word = kPadBit | (pad_head ? kHeadBit : 0u);
   out.stream[k] = word;
-  if (valid) out.pos[triu_pos(pair_i(word), pair_j(word), n)] = k;
-  else out.pos[k] = 0xFFFFFFFFu;  // positions >= N of the canonical array are padding too
   const uint32_t H = __ballot_sync(0xffffffffu, head);
   const uint32_t Hn = __ballot_sync(0xffffffffu, head || pad_head);
   if (lane == 0) {
@@ -97,6 +95,27 @@ head_tables_kernel(uint32_t* __restrict__ prev_head, uint32_t* __restrict__ next
   __syncthreads();
   m = part[threadIdx.x];
   for (uint32_t g = hi; g > lo; --g) { m = min(m, next_head[g - 1]); next_head[g - 1] = m; }
+}
+
+// One warp per 32-group of the sorted order, after the head tables are final: the run [s, e)
+// of every element, scattered to the element's canonical (row-major triu) position.
+__global__ void __launch_bounds__(256)
+runs_kernel(uint32_t N, uint32_t G, uint32_t n, PresortView blob) {
+  const uint32_t g = blockIdx.x * 8u + (threadIdx.x >> 5);
+  if (g >= G) return;
+  const unsigned lane = lane_id();
+  const uint32_t k = g * 32u + lane;
+  const uint32_t wd = blob.stream[k];
+  const uint32_t H = blob.head_bits[g];
+  if (k >= N) { blob.runs[k] = 0u; return; }        // canonical padding
+  const uint32_t below = H & lanemask_le();
+  const uint32_t s = below ? g * 32u + (31u - __clz(below)) : blob.prev_head[g - 1];
+  const uint32_t above = H & lanemask_gt();
+  const uint32_t e = above ? g * 32u + (__ffs(above) - 1u) : blob.next_head[g + 1];
+  const uint32_t sbits = run_sbits(N);
+  const uint32_t esc = (1u << (32u - sbits)) - 1u;
+  const uint32_t f = min(e - s - 1u, esc);
+  blob.runs[triu_pos(pair_i(wd), pair_j(wd), n)] = s | (f << sbits);
 }
 
 // ---- row-wise ordinal ranks ------------------------------------------------------------
@@ -159,6 +178,8 @@ extern "C" int vr_presort_triu_f32(const float* rdm, int n, int64_t ld, void* pr
   heads_kernel<<<(G + 7) / 8, 256, 0, stream>>>(k0, v0, (uint32_t)N, G, (uint32_t)n, view);
   VR_CHECK_LAUNCH();
   head_tables_kernel<<<1, 1024, 0, stream>>>(view.prev_head, view.next_head, (uint32_t)N, G);
+  VR_CHECK_LAUNCH();
+  runs_kernel<<<(G + 7) / 8, 256, 0, stream>>>((uint32_t)N, G, (uint32_t)n, view);
   VR_CHECK_LAUNCH();
   return VR_OK;
 }

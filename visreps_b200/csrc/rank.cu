@@ -11,16 +11,16 @@
 //     dev    = 2*rank - (N_r + 1) = C(s) + C(e) - N_r      (centred, integer)
 // and Spearman rho = sum(devA*devB) / sqrt(sum(devA^2) * sum(devB^2)).
 //
-// rank_kernel: one CTA per (vector, replicate) work item, persistent over items.
-//   pass 1  (sorted order) stream the packed (i,j) words, test membership against the
-//           replicate's n-bit mask in shared memory, ballot -> one 32-bit kept word per
-//           32-group plus the running kept count: the table {kept, count} (8 B per group).
-//           The table lives in shared memory when it fits (N <= ~880k pairs), else in an
-//           L2-resident per-CTA scratch.  C(x) is then one table read + popc for ANY x.
-//   pass 2  (canonical order) for each kept pair read its sorted position, find the run
-//           bounds from the head-bit word of its 32-group (bit tricks; prev/next-head tables
-//           only when the run leaves the group), two table reads -> dev.  Reads and the dev
-//           write are fully coalesced; the only random accesses hit the small tables.
+// count_kernel (sorted order, bit-sliced over 32 replicates): for one vector and a batch of 32
+//   replicates, lane l streams the packed (i,j) words; membership of the pair in ALL 32 replicates
+//   is one AND of two words of the transposed mask (bit r of maskT[i] = stimulus i kept in
+//   replicate r).  A 5-stage butterfly transposes the warp's 32x32 bit matrix so lane r holds the
+//   kept word of replicate r for the 32-group, keeps that replicate's running count in a register,
+//   and appends {kept word, count} to the replicate's table (8 B per 32 pairs).
+// rank_kernel (canonical order): one CTA per (vector, replicate).  The replicate's table is
+//   copied to shared memory (global when it does not fit); for every pair the precomputed run
+//   bounds (one packed word, coalesced) give C(s) and C(e) with two table reads + popc.
+//   Reads and the dev write are coalesced; the only random accesses hit the table.
 // dot_kernel: per replicate, tiles of 4x4 (model, neural) vectors, exact int64 products.
 #include "common.cuh"
 
@@ -28,6 +28,8 @@ namespace vr {
 
 constexpr int kRankThreads = 1024;
 constexpr int kRankWarps = kRankThreads / 32;
+constexpr int kCountThreads = 512;
+constexpr int kCountWarps = kCountThreads / 32;
 constexpr int kMaxVectors = 64;
 constexpr size_t kRankSmemTableMax = 200 * 1024;   // bytes of shared memory the table may take
 
@@ -44,6 +46,20 @@ __global__ void build_masks_kernel(const int32_t* __restrict__ idx, int R, int m
   if (i >= 0 && i < n) atomicOr(&masks[(int64_t)r * W + (i >> 5)], 1u << (i & 31));
 }
 
+// maskT[batch][i]: bit r = stimulus i is kept in replicate batch*32 + r (0 beyond R).
+__global__ void transpose_masks_kernel(const uint32_t* __restrict__ masks, int R, int n, int W,
+                                       uint32_t* __restrict__ maskT) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int batch = blockIdx.y;
+  if (i >= n) return;
+  uint32_t w = 0;
+  for (int r = 0; r < 32; ++r) {
+    const int rep = batch * 32 + r;
+    if (rep < R) w |= ((masks[(int64_t)rep * W + (i >> 5)] >> (i & 31)) & 1u) << r;
+  }
+  maskT[(int64_t)batch * n + i] = w;
+}
+
 __device__ __forceinline__ uint32_t low_mask(uint32_t bit) { return (1u << bit) - 1u; }  // bit in [0,31]
 
 // Row of canonical pair p: largest i with i(2n-i-1)/2 <= p.
@@ -57,140 +73,158 @@ __device__ __forceinline__ uint32_t triu_row(uint32_t p, uint32_t n) {
   return (uint32_t)i;
 }
 
-// Dynamic shared memory: mask words [Wpad] | table uint2[Gs] (only when kSmemTable).
+// Transpose a 32x32 bit matrix held one row per lane (row = lane, column = bit).
+__device__ __forceinline__ uint32_t warp_bit_transpose(uint32_t w, unsigned lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const uint32_t m = s == 16 ? 0x0000FFFFu : s == 8 ? 0x00FF00FFu : s == 4 ? 0x0F0F0F0Fu
+                     : s == 2 ? 0x33333333u : 0x55555555u;   // columns c with (c & s) == 0
+    const uint32_t x = __shfl_xor_sync(0xffffffffu, w, s);
+    w = (lane & s) ? ((w & ~m) | ((x >> s) & m)) : ((w & m) | ((x << s) & ~m));
+  }
+  return w;
+}
+
+// tables: [vector][replicate][Gs] of {kept word, kept count before the group}.
+// Dynamic shared memory: maskT of the batch, n words.
+__global__ void __launch_bounds__(kCountThreads)
+count_kernel(const __grid_constant__ BlobList blobs, int n, const uint32_t* __restrict__ maskT, int R,
+             uint2* __restrict__ tables, uint32_t Gs) {
+  extern __shared__ __align__(16) uint32_t s_maskT[];
+  __shared__ uint32_t s_tot[kCountWarps][32];
+  const unsigned lane = lane_id();
+  const int warp = threadIdx.x >> 5;
+  const int v = blockIdx.y, batch = blockIdx.x;
+  const uint32_t N = (uint32_t)triu_len(n);
+  const uint32_t G = (N + 31u) / 32u;
+  const uint32_t SG = (G + 31u) / 32u;
+  const uint32_t sg_per_warp = (SG + kCountWarps - 1) / kCountWarps;
+  const uint32_t g_lo = min(G, warp * sg_per_warp * 32u);
+  const uint32_t g_hi = min(G, g_lo + sg_per_warp * 32u);
+  PresortView blob = presort_view(const_cast<void*>(blobs.p[v]), n);
+  const uint32_t* __restrict__ stream = blob.stream;
+  for (int i = threadIdx.x; i < n; i += kCountThreads) s_maskT[i] = maskT[(int64_t)batch * n + i];
+  __syncthreads();
+
+  const int rep = batch * 32 + (int)lane;                 // the replicate this lane accumulates
+  uint2* __restrict__ my_table = tables + ((int64_t)v * R + min(rep, R - 1)) * Gs;
+  uint32_t running = 0;
+  for (uint32_t g0 = g_lo; g0 < g_hi; g0 += 4u) {          // g_lo is a multiple of 32: 4-group steps stay aligned
+    uint32_t wd[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) wd[q] = (g0 + q < G) ? __ldg(stream + (size_t)(g0 + q) * 32u + lane) : kPadBit;
+    uint32_t K[4], C[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t bits = (wd[q] & kPadBit) ? 0u : (s_maskT[pair_i(wd[q])] & s_maskT[pair_j(wd[q])]);
+      K[q] = warp_bit_transpose(bits, lane);                // lane r: kept word of replicate r
+      C[q] = running;
+      running += __popc(K[q]);
+    }
+    if (rep < R) {
+      uint4* dst = reinterpret_cast<uint4*>(my_table + g0);
+      dst[0] = make_uint4(K[0], C[0], K[1], C[1]);
+      dst[1] = make_uint4(K[2], C[2], K[3], C[3]);
+    }
+  }
+  // make the counts global: add the totals of the preceding warps' segments
+  s_tot[warp][lane] = running;
+  __syncthreads();
+  uint32_t base = 0;
+  for (int w = 0; w < warp; ++w) base += s_tot[w][lane];
+  if (rep < R) {
+    if (base)
+      for (uint32_t g = g_lo; g < g_hi; ++g) my_table[g].y += base;
+    if (warp == kCountWarps - 1) {                           // sentinel entry: C(N) = N_r
+      uint32_t tot = base + running;
+      for (uint32_t g = G; g < Gs; ++g) my_table[g] = make_uint2(0u, tot);
+    }
+  }
+}
+
+// Dynamic shared memory: mask words [round_up(W,4)] | table uint2[Gs] (only when kSmemTable).
 template <bool kSmemTable>
 __global__ void __launch_bounds__(kRankThreads, 1)
 rank_kernel(const __grid_constant__ BlobList blobs, int n_vectors, int n, const uint32_t* __restrict__ masks,
-            int W, int R, int32_t* __restrict__ dev, int64_t dev_stride, double* __restrict__ ss_out,
-            int64_t* __restrict__ nkept_out, uint2* __restrict__ scratch, uint32_t Gs) {
+            int W, int R, const uint2* __restrict__ tables, uint32_t Gs, int32_t* __restrict__ dev,
+            int64_t dev_stride, double* __restrict__ ss_out, int64_t* __restrict__ nkept_out) {
   extern __shared__ __align__(16) uint32_t smem[];
-  uint32_t* s_mask = smem;                                   // [round_up(W, 4)]
-  __shared__ uint32_t s_segbase[kRankWarps + 1];
+  uint32_t* s_mask = smem;
+  uint2* s_table = reinterpret_cast<uint2*>(smem + ((W + 3) & ~3));
   __shared__ double s_red[kRankWarps];
 
   const unsigned lane = lane_id();
   const int warp = threadIdx.x >> 5;
   const uint32_t N = (uint32_t)triu_len(n);
   const uint32_t G = (N + 31u) / 32u;
-  const uint32_t SG = (G + 31u) / 32u;                          // super-groups of 32 groups
-  const uint32_t sg_per_warp = (SG + kRankWarps - 1) / kRankWarps;
-  const uint32_t sg_lo = warp * sg_per_warp;
-  const uint32_t sg_hi = min(SG, sg_lo + sg_per_warp);
-  uint2* table = kSmemTable ? reinterpret_cast<uint2*>(smem + ((W + 3) & ~3))
-                            : scratch + (size_t)blockIdx.x * Gs;
+  const uint32_t sbits = run_sbits(N);
+  const uint32_t smask = (1u << sbits) - 1u;
+  const uint32_t esc = (1u << (32u - sbits)) - 1u;
 
   const int64_t items = (int64_t)n_vectors * R;
   for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
     const int v = (int)(item / R), r = (int)(item % R);
     PresortView blob = presort_view(const_cast<void*>(blobs.p[v]), n);
-    const uint32_t* __restrict__ stream = blob.stream;
+    const uint2* __restrict__ g_table = tables + item * Gs;
     for (int w = threadIdx.x; w < W; w += kRankThreads) s_mask[w] = masks[(int64_t)r * W + w];
-    __syncthreads();
-
-    // ---------------- pass 1: kept words + running counts (sorted order) ----------------
-    uint32_t running = 0;
-    for (uint32_t sg = sg_lo; sg < sg_hi; ++sg) {
-      uint32_t myK = 0;
-      const uint32_t gbase = sg * 32u;
-#pragma unroll 8
-      for (uint32_t t = 0; t < 32u; ++t) {
-        const uint32_t g = gbase + t;
-        bool kept = false;
-        if (g < G) {
-          const uint32_t wd = __ldg(stream + (size_t)g * 32u + lane);
-          const uint32_t i = pair_i(wd), j = pair_j(wd);
-          kept = !(wd & kPadBit) && ((s_mask[i >> 5] >> (i & 31u)) & (s_mask[j >> 5] >> (j & 31u)) & 1u);
-        }
-        const uint32_t K = __ballot_sync(0xffffffffu, kept);
-        if (lane == t) myK = K;
-      }
-      const uint32_t c = __popc(myK);
-      uint32_t incl = c;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        uint32_t x = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= (unsigned)o) incl += x;
-      }
-      table[gbase + lane] = make_uint2(myK, running + incl - c);
-      running += __shfl_sync(0xffffffffu, incl, 31);
-    }
-    if (lane == 0) s_segbase[warp] = running;
-    __syncthreads();
-    if (warp == 0) {
-      const uint32_t mine = s_segbase[lane];
-      uint32_t incl = mine;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        uint32_t x = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= (unsigned)o) incl += x;
-      }
-      s_segbase[lane] = incl - mine;
-      if (lane == 31) s_segbase[kRankWarps] = incl;
+    if (kSmemTable) {
+      const uint4* src = reinterpret_cast<const uint4*>(g_table);
+      uint4* dst = reinterpret_cast<uint4*>(s_table);
+      for (uint32_t q = threadIdx.x; q < Gs / 2; q += kRankThreads) dst[q] = src[q];
     }
     __syncthreads();
-    const uint32_t Ns = s_segbase[kRankWarps];
-    {  // make the counts global (add each warp's segment base)
-      const uint32_t mybase = s_segbase[warp];
-      if (mybase)
-        for (uint32_t g = sg_lo * 32u + lane; g < sg_hi * 32u; g += 32u) table[g].y += mybase;
-    }
-    __syncthreads();
+    const uint2* __restrict__ table = kSmemTable ? s_table : g_table;
+    const uint32_t Ns = table[G].y;
 
-    // kept pairs at sorted positions < x, x in [0, N]
-    auto count_below = [&](uint32_t x) -> uint32_t {
-      if (x >= N) return Ns;
-      const uint2 e = table[x >> 5];
-      return e.y + __popc(e.x & low_mask(x & 31u));
-    };
-
-    // ---------------- pass 2: canonical order, 4 pairs per thread per step ----------------
-    int32_t* __restrict__ out = dev + ((int64_t)v * R + r) * dev_stride;
-    const uint32_t* __restrict__ posv = blob.pos;
-    const uint32_t* __restrict__ headw = blob.head_bits;
-    double acc = 0.0;
+    int32_t* __restrict__ out = dev + item * dev_stride;
+    const uint32_t* __restrict__ runs = blob.runs;
+    long long acc = 0;
+    double accd = 0.0;
+    int since_flush = 0;
+    // |dev| <= N, so one step adds < 4 N^2; fold into fp64 before 2^62 can be reached
+    const int flush_every = (int)min(1024ull, (1ull << 62) / (4ull * (unsigned long long)N * N + 1ull) + 1ull);
     for (uint32_t p0 = threadIdx.x * 4u; p0 < (uint32_t)dev_stride; p0 += kRankThreads * 4u) {
       int32_t d4[4] = {0, 0, 0, 0};
       if (p0 < N) {
-        const uint4 q = __ldg(reinterpret_cast<const uint4*>(posv + p0));
-        const uint32_t xs[4] = {q.x, q.y, q.z, q.w};
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(runs + p0));
+        const uint32_t rw[4] = {q.x, q.y, q.z, q.w};
         uint32_t i = triu_row(p0, (uint32_t)n);
         uint32_t j = p0 - i * (2u * n - i - 1u) / 2u + i + 1u;
-        bool ki = (s_mask[i >> 5] >> (i & 31u)) & 1u;
+        uint32_t ki = (s_mask[i >> 5] >> (i & 31u)) & 1u;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          if (p0 + e < N) {
-            if (ki && ((s_mask[j >> 5] >> (j & 31u)) & 1u)) {
-              const uint32_t x = xs[e];
-              const uint32_t g = x >> 5, l = x & 31u;
-              const uint2 te = table[g];
-              const uint32_t H = __ldg(headw + g);
-              uint32_t lo, hi;
-              const uint32_t below = H & (low_mask(l) | (1u << l));
-              if (below) lo = te.y + __popc(te.x & low_mask(31u - __clz(below)));
-              else lo = count_below(__ldg(blob.prev_head + g - 1));
-              const uint32_t above = l == 31u ? 0u : (H >> (l + 1u));
-              if (above) hi = te.y + __popc(te.x & low_mask(l + (uint32_t)__ffs(above)));
-              else hi = count_below(__ldg(blob.next_head + g + 1));
-              const int32_t d = (int32_t)(lo + hi) - (int32_t)Ns;
-              d4[e] = d;
-              acc += (double)d * (double)d;
-            }
-            if (++j == (uint32_t)n) { ++i; j = i + 1u; ki = (s_mask[i >> 5] >> (i & 31u)) & 1u; }
+          const uint32_t s = rw[e] & smask;
+          const uint32_t f = rw[e] >> sbits;
+          uint32_t end = s + f + 1u;
+          if (f == esc) {                                   // long run: find its end from the head tables
+            const uint32_t g = s >> 5, l = s & 31u;
+            const uint32_t above = l == 31u ? 0u : (__ldg(blob.head_bits + g) >> (l + 1u));
+            end = above ? s + (uint32_t)__ffs(above) : __ldg(blob.next_head + g + 1);
           }
+          const uint2 ts = table[s >> 5];
+          const uint2 te = table[end >> 5];
+          const uint32_t lo = ts.y + __popc(ts.x & low_mask(s & 31u));
+          const uint32_t hi = te.y + __popc(te.x & low_mask(end & 31u));
+          const uint32_t kept = ki & (s_mask[j >> 5] >> (j & 31u)) & (p0 + e < N ? 1u : 0u);
+          const int32_t d = kept ? (int32_t)(lo + hi) - (int32_t)Ns : 0;
+          d4[e] = d;
+          acc += (long long)d * (long long)d;
+          if (++j == (uint32_t)n) { ++i; j = i + 1u; ki = (s_mask[min(i, (uint32_t)n - 1u) >> 5] >> (i & 31u)) & 1u; }
         }
+        if (++since_flush >= flush_every) { since_flush = 0; accd += (double)acc; acc = 0; }
       }
       *reinterpret_cast<int4*>(out + p0) = make_int4(d4[0], d4[1], d4[2], d4[3]);
     }
-
-    acc = warp_sum(acc);
-    if (lane == 0) s_red[warp] = acc;
+    accd += (double)acc;
+    accd = warp_sum(accd);
+    if (lane == 0) s_red[warp] = accd;
     __syncthreads();
     if (threadIdx.x == 0) {
       double tot = 0.0;
       for (int w = 0; w < kRankWarps; ++w) tot += s_red[w];
       if (blob.hdr->has_nan) tot = __longlong_as_double(0x7ff8000000000000LL);
-      ss_out[(int64_t)v * R + r] = tot;
-      nkept_out[(int64_t)v * R + r] = (int64_t)Ns;
+      ss_out[item] = tot;
+      nkept_out[item] = (int64_t)Ns;
     }
     __syncthreads();  // table + s_mask are reused by the next item
   }
@@ -225,6 +259,8 @@ dot_kernel(const int32_t* __restrict__ dev, int64_t dev_stride, const double* __
     for (int y = 0; y < kDotTile; ++y) { acc[x][y] = 0; accd[x][y] = 0.0; }
 
   int since_flush = 0;
+  // |dev| <= N (= dev_stride up to padding): one step adds < 4 N^2 per accumulator
+  const int flush_every = (int)min(256ull, (1ull << 62) / (4ull * (unsigned long long)dev_stride * dev_stride + 1ull) + 1ull);
   for (int64_t q = threadIdx.x; q < n4; q += kDotThreads) {
     int4 va[kDotTile], vb[kDotTile];
 #pragma unroll
@@ -236,8 +272,7 @@ dot_kernel(const int32_t* __restrict__ dev, int64_t dev_stride, const double* __
         acc[x][y] += (long long)va[x].x * vb[y].x + (long long)va[x].y * vb[y].y +
                      (long long)va[x].z * vb[y].z + (long long)va[x].w * vb[y].w;
       }
-    // |dev| < 2^26 -> each step adds < 2^54; flush to fp64 before 2^63 can be reached
-    if (++since_flush == 256) {
+    if (++since_flush >= flush_every) {
       since_flush = 0;
 #pragma unroll
       for (int x = 0; x < kDotTile; ++x)
@@ -277,23 +312,46 @@ dot_kernel(const int32_t* __restrict__ dev, int64_t dev_stride, const double* __
 }
 
 static inline uint32_t table_groups(int n) { return (uint32_t)round_up(presort_groups(n) + 1, 32) + 32u; }
+static inline bool rank_table_in_smem(int n) { return (size_t)table_groups(n) * 8 <= kRankSmemTableMax; }
 static inline size_t rank_smem_bytes(int n, bool smem_table) {
   const size_t mask_bytes = (size_t)round_up(vr_mask_words(n), 4) * 4;
   return mask_bytes + (smem_table ? (size_t)table_groups(n) * 8 : 0);
 }
-static inline bool rank_table_in_smem(int n) { return (size_t)table_groups(n) * 8 <= kRankSmemTableMax; }
-static inline size_t rank_scratch_bytes(int n) {
-  return rank_table_in_smem(n) ? 256 : arena_bytes((size_t)kNumSMs * table_groups(n), 8);
+// scratch of one launch over nV vectors x R replicates: transposed masks + count tables
+static inline size_t rank_scratch_bytes(int n, int nV, int64_t R) {
+  return arena_bytes((size_t)((R + 31) / 32) * n, 4) + arena_bytes((size_t)nV * R * table_groups(n), 8);
 }
 
 static int launch_rank(const BlobList& blobs, int nV, int n, const uint32_t* masks, int R, int32_t* dev,
-                       double* ss, int64_t* nkept, void* scratch, cudaStream_t stream) {
+                       double* ss, int64_t* nkept, void* scratch, size_t scratch_bytes, cudaStream_t stream) {
   const int W = vr_mask_words(n);
+  const uint32_t Gs = table_groups(n);
+  const int batches = (R + 31) / 32;
+  Arena a(scratch, scratch_bytes);
+  uint32_t* maskT = a.take<uint32_t>((size_t)batches * n);
+  uint2* tables = a.take<uint2>((size_t)nV * R * Gs);
+  if (!a.ok) { set_error("rank scratch too small"); return VR_ERR_WORKSPACE; }
+  ProfScope prof(F_RANK, stream);
+  {
+    dim3 grid((n + 255) / 256, batches);
+    transpose_masks_kernel<<<grid, 256, 0, stream>>>(masks, R, n, W, maskT);
+    VR_CHECK_LAUNCH();
+  }
+  {
+    static bool attr_set = false;
+    const size_t smem = (size_t)n * 4;
+    if (!attr_set && smem > 40 * 1024) {
+      VR_CHECK_CUDA(cudaFuncSetAttribute(count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      attr_set = true;
+    }
+    dim3 grid(batches, nV);
+    count_kernel<<<grid, kCountThreads, smem, stream>>>(blobs, n, maskT, R, tables, Gs);
+    VR_CHECK_LAUNCH();
+  }
   const bool in_smem = rank_table_in_smem(n);
   const size_t smem = rank_smem_bytes(n, in_smem);
   const int64_t items = (int64_t)nV * R;
   const int grid = (int)(items < kNumSMs ? items : kNumSMs);
-  ProfScope prof(F_RANK, stream);
   if (in_smem) {
     static bool attr_set = false;
     if (!attr_set) {
@@ -301,11 +359,11 @@ static int launch_rank(const BlobList& blobs, int nV, int n, const uint32_t* mas
                                          (int)(kRankSmemTableMax + 8192)));
       attr_set = true;
     }
-    rank_kernel<true><<<grid, kRankThreads, smem, stream>>>(blobs, nV, n, masks, W, R, dev, vr_dev_stride(n), ss,
-                                                           nkept, nullptr, table_groups(n));
+    rank_kernel<true><<<grid, kRankThreads, smem, stream>>>(blobs, nV, n, masks, W, R, tables, Gs, dev,
+                                                           vr_dev_stride(n), ss, nkept);
   } else {
-    rank_kernel<false><<<grid, kRankThreads, smem, stream>>>(blobs, nV, n, masks, W, R, dev, vr_dev_stride(n), ss,
-                                                            nkept, static_cast<uint2*>(scratch), table_groups(n));
+    rank_kernel<false><<<grid, kRankThreads, smem, stream>>>(blobs, nV, n, masks, W, R, tables, Gs, dev,
+                                                            vr_dev_stride(n), ss, nkept);
   }
   VR_CHECK_LAUNCH();
   return VR_OK;
@@ -335,20 +393,20 @@ extern "C" int vr_build_masks(const int32_t* idx, int R, int m, int n, uint32_t*
 
 extern "C" int64_t vr_dev_stride(int n) { return n >= 2 ? round_up(triu_len(n), 32) : 32; }
 
-extern "C" size_t vr_subsample_rank_workspace_bytes(int n) { return n >= 2 ? rank_scratch_bytes(n) + 256 : 256; }
+extern "C" size_t vr_subsample_rank_workspace_bytes(int n, int R) { return (n >= 2 && R >= 1) ? rank_scratch_bytes(n, 1, R) + 256 : 256; }
 
 extern "C" int vr_subsample_rank(const void* presorted, int n, const uint32_t* masks, int R, int32_t* dev,
                                  double* ss, int64_t* nkept, void* ws, size_t ws_bytes, vr_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   VR_REQUIRE(presorted && masks && dev && ss && nkept, "vr_subsample_rank: null pointer");
   VR_REQUIRE(n >= 2 && n <= VR_MAX_STIMULI && R >= 1, "vr_subsample_rank: bad sizes n=%d R=%d", n, R);
-  if (!ws || ws_bytes < vr_subsample_rank_workspace_bytes(n)) {
-    set_error("vr_subsample_rank: workspace %zu < %zu", ws_bytes, vr_subsample_rank_workspace_bytes(n));
+  if (!ws || ws_bytes < vr_subsample_rank_workspace_bytes(n, R)) {
+    set_error("vr_subsample_rank: workspace %zu < %zu", ws_bytes, vr_subsample_rank_workspace_bytes(n, R));
     return VR_ERR_WORKSPACE;
   }
   BlobList bl{};
   bl.p[0] = presorted;
-  return launch_rank(bl, 1, n, masks, R, dev, ss, nkept, ws, stream);
+  return launch_rank(bl, 1, n, masks, R, dev, ss, nkept, ws, ws_bytes, stream);
 }
 
 namespace {
@@ -358,8 +416,8 @@ struct SpearmanPlan {
 };
 SpearmanPlan spearman_plan(int n, int nV) {
   SpearmanPlan p;
-  p.fixed = rank_scratch_bytes(n) + 4096;
-  p.per_rep = (size_t)nV * ((size_t)vr_dev_stride(n) * 4 + 8 + 8);
+  p.fixed = arena_bytes((size_t)n * 2100, 4) + 8192;   // transposed masks of up to 65535 replicates + slack
+  p.per_rep = (size_t)nV * ((size_t)vr_dev_stride(n) * 4 + (size_t)table_groups(n) * 8 + 8 + 8);
   return p;
 }
 constexpr size_t kSoftCap = (size_t)40 << 30;  // default upper bound on one call's workspace
@@ -396,7 +454,8 @@ extern "C" int vr_bootstrap_spearman(const void* const* A, int nA, const void* c
   if (chunk > R) chunk = R;
   if (chunk > 65535) chunk = 65535;  // grid.y limit of the dot kernel
   Arena a(ws, ws_bytes);
-  void* scratch = a.take<char>(rank_scratch_bytes(n));
+  const size_t scratch_bytes = rank_scratch_bytes(n, nV, chunk) + 256;
+  void* scratch = a.take<char>(scratch_bytes);
   double* ss = a.take<double>((size_t)nV * chunk);
   int64_t* nkept = a.take<int64_t>((size_t)nV * chunk);
   int32_t* dev = a.take<int32_t>((size_t)nV * chunk * vr_dev_stride(n));
@@ -405,7 +464,7 @@ extern "C" int vr_bootstrap_spearman(const void* const* A, int nA, const void* c
   const int tiles = ((nA + kDotTile - 1) / kDotTile) * ((nB + kDotTile - 1) / kDotTile);
   for (int64_t r0 = 0; r0 < R; r0 += chunk) {
     const int rc = (int)(R - r0 < chunk ? R - r0 : chunk);
-    int st = launch_rank(bl, nV, n, masks + (size_t)r0 * W, rc, dev, ss, nkept, scratch, stream);
+    int st = launch_rank(bl, nV, n, masks + (size_t)r0 * W, rc, dev, ss, nkept, scratch, scratch_bytes, stream);
     if (st != VR_OK) return st;
     dim3 grid(tiles, rc);
     ProfScope prof(F_DOT, stream);

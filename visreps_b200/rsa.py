@@ -407,7 +407,7 @@ def subsample_rank(rdm, masks: torch.Tensor):
     out = torch.empty((R, stride), dtype=torch.int32, device=dev_)
     ss = torch.empty(R, dtype=torch.float64, device=dev_)
     nk = torch.empty(R, dtype=torch.int64, device=dev_)
-    ws = _lib.workspace(lib.vr_subsample_rank_workspace_bytes(p.n), dev_)
+    ws = _lib.workspace(lib.vr_subsample_rank_workspace_bytes(p.n, R), dev_)
     _lib.check(lib.vr_subsample_rank(p.blob.data_ptr(), p.n, masks.data_ptr(), R, out.data_ptr(), ss.data_ptr(),
                                      nk.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "vr_subsample_rank")
     N = p.n * (p.n - 1) // 2
