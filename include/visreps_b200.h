@@ -94,6 +94,11 @@ size_t vr_presort_bytes(int n);
 size_t vr_presort_workspace_bytes(int n);
 int vr_presort_triu_f32(const float* rdm, int n, int64_t ld, void* presorted,
                         void* ws, size_t ws_bytes, vr_stream_t stream);
+/* Same, for `count` (<= 64) RDMs of identical n and ld in one batched sort.  rdms_host and
+ * blobs_host are HOST arrays of device pointers. */
+size_t vr_presort_batch_workspace_bytes(int n, int count);
+int vr_presort_triu_batch_f32(const float* const* rdms_host, int count, int n, int64_t ld,
+                              void* const* blobs_host, void* ws, size_t ws_bytes, vr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Subsample masks: turns the HOST-drawn index sets of the reference bootstrap

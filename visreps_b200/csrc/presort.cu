@@ -9,36 +9,56 @@
 
 namespace vr {
 
+constexpr int kPresortBatch = 64;
+struct PresortBatch {
+  const float* rdm[kPresortBatch];
+  void* blob[kPresortBatch];
+};
+
 // ---- upper triangle -> (sortable key, packed pair) ------------------------------------
+// grid (ceil(n/256), n, batch); keys/vals of matrix b start at b * seg_stride.
 __global__ void __launch_bounds__(256)
-triu_keys_kernel(const float* __restrict__ rdm, int n, int64_t ld, uint32_t* __restrict__ keys,
-                 uint32_t* __restrict__ vals, PresortHeader* hdr) {
+triu_keys_kernel(const __grid_constant__ PresortBatch batch, int n, int64_t ld, uint32_t* __restrict__ keys,
+                 uint32_t* __restrict__ vals, int64_t seg_stride) {
   const uint32_t i = blockIdx.y;
   const uint32_t j = blockIdx.x * 256u + threadIdx.x;
+  const int b = blockIdx.z;
+  PresortHeader* hdr = reinterpret_cast<PresortHeader*>(batch.blob[b]);
+  if (i == 0 && j == 0) {
+    hdr->magic = kPresortMagic;
+    hdr->n = (uint32_t)n;
+    hdr->N = (uint32_t)triu_len(n);
+    hdr->G = presort_groups(n);
+  }
   if (j >= (uint32_t)n || j <= i) return;
-  const float v = rdm[(int64_t)i * ld + j];
+  const float v = batch.rdm[b][(int64_t)i * ld + j];
   if (v != v) atomicOr(&hdr->has_nan, 1u);
   const uint32_t p = triu_pos(i, j, (uint32_t)n);
-  keys[p] = float_key(v);
-  vals[p] = pack_pair(i, j);
+  keys[(int64_t)b * seg_stride + p] = float_key(v);
+  vals[(int64_t)b * seg_stride + p] = pack_pair(i, j);
 }
 
-__global__ void init_header_kernel(PresortHeader* hdr, uint32_t n, uint32_t N, uint32_t G) {
-  hdr->magic = kPresortMagic;
-  hdr->n = n;
-  hdr->N = N;
-  hdr->G = G;
-  hdr->has_nan = 0;
-  hdr->n_runs = 0;
+// Clears the device-written header fields (has_nan, n_runs) before triu_keys_kernel sets them.
+__global__ void clear_headers_kernel(const __grid_constant__ PresortBatch batch, int count) {
+  const int b = threadIdx.x;
+  if (b < count) {
+    PresortHeader* hdr = reinterpret_cast<PresortHeader*>(batch.blob[b]);
+    hdr->has_nan = 0;
+    hdr->n_runs = 0;
+  }
 }
 
 // One warp per 32-group of the sorted order: head flags, packed stream, per-group
-// candidates for the prev/next head tables.
+// candidates for the prev/next head tables.  grid (ceil(G/8), batch).
 __global__ void __launch_bounds__(256)
-heads_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint32_t N,
-             uint32_t G, uint32_t n, PresortView out) {
+heads_kernel(const uint32_t* __restrict__ keys_all, const uint32_t* __restrict__ vals_all, int64_t seg_stride,
+             uint32_t N, uint32_t G, uint32_t n, const __grid_constant__ PresortBatch batch) {
   const uint32_t g = blockIdx.x * 8u + (threadIdx.x >> 5);
   if (g >= G) return;
+  const int b = blockIdx.y;
+  const uint32_t* __restrict__ keys = keys_all + (int64_t)b * seg_stride;
+  const uint32_t* __restrict__ vals = vals_all + (int64_t)b * seg_stride;
+  PresortView out = presort_view(batch.blob[b], (int)n);
   const unsigned lane = lane_id();
   const uint32_t k = g * 32u + lane;
   const bool valid = k < N;
@@ -61,11 +81,13 @@ heads_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ val
 }
 
 // prev_head: inclusive running max (forward).  next_head: inclusive running min (backward),
-// seeded with next_head[G] = N.  Single CTA, each thread owns a contiguous chunk.
+// seeded with next_head[G] = N.  One CTA per matrix, each thread owns a contiguous chunk.
 __global__ void __launch_bounds__(1024)
-head_tables_kernel(uint32_t* __restrict__ prev_head, uint32_t* __restrict__ next_head, uint32_t N,
-                   uint32_t G) {
+head_tables_kernel(const __grid_constant__ PresortBatch batch, uint32_t N, uint32_t G, uint32_t n) {
   __shared__ uint32_t part[1024];
+  PresortView view = presort_view(batch.blob[blockIdx.x], (int)n);
+  uint32_t* __restrict__ prev_head = view.prev_head;
+  uint32_t* __restrict__ next_head = view.next_head;
   const uint32_t chunk = (G + 1023u) / 1024u;
   const uint32_t lo = threadIdx.x * chunk;
   const uint32_t hi = lo + chunk < G ? lo + chunk : G;
@@ -74,9 +96,14 @@ head_tables_kernel(uint32_t* __restrict__ prev_head, uint32_t* __restrict__ next
   for (uint32_t g = lo; g < hi; ++g) m = max(m, prev_head[g]);
   part[threadIdx.x] = m;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t run = 0;
-    for (int t = 0; t < 1024; ++t) { uint32_t v = part[t]; part[t] = run; run = max(run, v); }
+  if (threadIdx.x < 32) {   // exclusive max-scan of the 1024 chunk maxima, 32 per lane
+    uint32_t run = 0, loc[32];
+    for (int t = 0; t < 32; ++t) { loc[t] = part[threadIdx.x * 32 + t]; run = max(run, loc[t]); }
+    uint32_t incl = run;
+    for (int o = 1; o < 32; o <<= 1) { uint32_t x = __shfl_up_sync(0xffffffffu, incl, o); if (threadIdx.x >= (unsigned)o) incl = max(incl, x); }
+    uint32_t excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    run = threadIdx.x == 0 ? 0u : excl;
+    for (int t = 0; t < 32; ++t) { part[threadIdx.x * 32 + t] = run; run = max(run, loc[t]); }
   }
   __syncthreads();
   m = part[threadIdx.x];
@@ -87,10 +114,16 @@ head_tables_kernel(uint32_t* __restrict__ prev_head, uint32_t* __restrict__ next
   for (uint32_t g = lo; g < hi; ++g) m = min(m, next_head[g]);
   part[threadIdx.x] = m;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t run = N;
-    for (int t = 1023; t >= 0; --t) { uint32_t v = part[t]; part[t] = run; run = min(run, v); }
-    next_head[G] = N;
+  if (threadIdx.x < 32) {   // exclusive suffix-min-scan, seeded with N
+    const int L = 31 - (int)threadIdx.x;            // lane 0 owns the LAST 32 chunks
+    uint32_t run = 0xFFFFFFFFu, loc[32];
+    for (int t = 0; t < 32; ++t) { loc[t] = part[L * 32 + 31 - t]; run = min(run, loc[t]); }
+    uint32_t incl = run;
+    for (int o = 1; o < 32; o <<= 1) { uint32_t x = __shfl_up_sync(0xffffffffu, incl, o); if (threadIdx.x >= (unsigned)o) incl = min(incl, x); }
+    uint32_t excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    run = threadIdx.x == 0 ? N : min(N, excl);
+    for (int t = 0; t < 32; ++t) { part[L * 32 + 31 - t] = run; run = min(run, loc[t]); }
+    if (threadIdx.x == 0) next_head[G] = N;
   }
   __syncthreads();
   m = part[threadIdx.x];
@@ -100,9 +133,10 @@ head_tables_kernel(uint32_t* __restrict__ prev_head, uint32_t* __restrict__ next
 // One warp per 32-group of the sorted order, after the head tables are final: the run [s, e)
 // of every element, scattered to the element's canonical (row-major triu) position.
 __global__ void __launch_bounds__(256)
-runs_kernel(uint32_t N, uint32_t G, uint32_t n, PresortView blob) {
+runs_kernel(uint32_t N, uint32_t G, uint32_t n, const __grid_constant__ PresortBatch batch) {
   const uint32_t g = blockIdx.x * 8u + (threadIdx.x >> 5);
   if (g >= G) return;
+  PresortView blob = presort_view(batch.blob[blockIdx.y], (int)n);
   const unsigned lane = lane_id();
   const uint32_t k = g * 32u + lane;
   const uint32_t wd = blob.stream[k];
@@ -141,47 +175,65 @@ using namespace vr;
 
 extern "C" size_t vr_presort_bytes(int n) { return n >= 2 ? presort_blob_bytes(n) : 256; }
 
-extern "C" size_t vr_presort_workspace_bytes(int n) {
-  if (n < 2) return 256;
+static size_t presort_ws(int n, int count) {
+  if (n < 2 || count < 1) return 256;
   const int64_t N = triu_len(n);
-  return 4 * arena_bytes((size_t)round_up(N, 32), 4) + arena_bytes(sort_count_elems(N, 1), 4) + 256;
+  return 4 * arena_bytes((size_t)count * round_up(N, 32), 4) + arena_bytes(sort_count_elems(N, count), 4) + 256;
+}
+extern "C" size_t vr_presort_workspace_bytes(int n) { return presort_ws(n, 1); }
+extern "C" size_t vr_presort_batch_workspace_bytes(int n, int count) { return presort_ws(n, count); }
+
+extern "C" int vr_presort_triu_batch_f32(const float* const* rdms, int count, int n, int64_t ld, void* const* blobs,
+                                         void* ws, size_t ws_bytes, vr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  VR_REQUIRE(rdms && blobs, "vr_presort_triu_batch_f32: null pointer");
+  VR_REQUIRE(count >= 1 && count <= kPresortBatch, "vr_presort_triu_batch_f32: count=%d outside [1, %d]", count, kPresortBatch);
+  VR_REQUIRE(n >= 2 && n <= VR_MAX_STIMULI, "vr_presort_triu_f32: n=%d outside [2, %d]", n, VR_MAX_STIMULI);
+  VR_REQUIRE(ld >= n, "vr_presort_triu_f32: ld=%lld < n=%d", (long long)ld, n);
+  if (ws_bytes < presort_ws(n, count) || !ws) {
+    set_error("vr_presort_triu_f32: workspace %zu < %zu", ws_bytes, presort_ws(n, count));
+    return VR_ERR_WORKSPACE;
+  }
+  PresortBatch batch{};
+  for (int b = 0; b < count; ++b) {
+    VR_REQUIRE(rdms[b] && blobs[b], "vr_presort_triu_f32: null pointer in batch");
+    batch.rdm[b] = rdms[b];
+    batch.blob[b] = blobs[b];
+  }
+  const int64_t N = triu_len(n);
+  const int64_t Npad = round_up(N, 32);
+  const uint32_t G = presort_groups(n);
+  Arena a(ws, ws_bytes);
+  uint32_t* k0 = a.take<uint32_t>((size_t)count * Npad);
+  uint32_t* v0 = a.take<uint32_t>((size_t)count * Npad);
+  uint32_t* k1 = a.take<uint32_t>((size_t)count * Npad);
+  uint32_t* v1 = a.take<uint32_t>((size_t)count * Npad);
+  uint32_t* counts = a.take<uint32_t>(sort_count_elems(N, count));
+  ProfScope prof(F_PRESORT, stream);
+
+  clear_headers_kernel<<<1, kPresortBatch, 0, stream>>>(batch, count);
+  VR_CHECK_LAUNCH();
+  dim3 grid((n + 255) / 256, n, count);
+  triu_keys_kernel<<<grid, 256, 0, stream>>>(batch, n, ld, k0, v0, Npad);
+  VR_CHECK_LAUNCH();
+  int rc = radix_sort_pairs(k0, v0, k1, v1, N, Npad, count, counts, stream);
+  if (rc != VR_OK) return rc;
+  dim3 hg((G + 7) / 8, count);
+  heads_kernel<<<hg, 256, 0, stream>>>(k0, v0, Npad, (uint32_t)N, G, (uint32_t)n, batch);
+  VR_CHECK_LAUNCH();
+  head_tables_kernel<<<count, 1024, 0, stream>>>(batch, (uint32_t)N, G, (uint32_t)n);
+  VR_CHECK_LAUNCH();
+  runs_kernel<<<hg, 256, 0, stream>>>((uint32_t)N, G, (uint32_t)n, batch);
+  VR_CHECK_LAUNCH();
+  return VR_OK;
 }
 
 extern "C" int vr_presort_triu_f32(const float* rdm, int n, int64_t ld, void* presorted, void* ws,
                                    size_t ws_bytes, vr_stream_t stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   VR_REQUIRE(rdm && presorted, "vr_presort_triu_f32: null pointer");
-  VR_REQUIRE(n >= 2 && n <= VR_MAX_STIMULI, "vr_presort_triu_f32: n=%d outside [2, %d]", n, VR_MAX_STIMULI);
-  VR_REQUIRE(ld >= n, "vr_presort_triu_f32: ld=%lld < n=%d", (long long)ld, n);
-  if (ws_bytes < vr_presort_workspace_bytes(n) || !ws) {
-    set_error("vr_presort_triu_f32: workspace %zu < %zu", ws_bytes, vr_presort_workspace_bytes(n));
-    return VR_ERR_WORKSPACE;
-  }
-  const int64_t N = triu_len(n);
-  const uint32_t G = presort_groups(n);
-  Arena a(ws, ws_bytes);
-  uint32_t* k0 = a.take<uint32_t>(round_up(N, 32));
-  uint32_t* v0 = a.take<uint32_t>(round_up(N, 32));
-  uint32_t* k1 = a.take<uint32_t>(round_up(N, 32));
-  uint32_t* v1 = a.take<uint32_t>(round_up(N, 32));
-  uint32_t* counts = a.take<uint32_t>(sort_count_elems(N, 1));
-  PresortView view = presort_view(presorted, n);
-  ProfScope prof(F_PRESORT, stream);
-
-  init_header_kernel<<<1, 1, 0, stream>>>(view.hdr, (uint32_t)n, (uint32_t)N, G);
-  VR_CHECK_LAUNCH();
-  dim3 grid((n + 255) / 256, n);
-  triu_keys_kernel<<<grid, 256, 0, stream>>>(rdm, n, ld, k0, v0, view.hdr);
-  VR_CHECK_LAUNCH();
-  int rc = radix_sort_pairs(k0, v0, k1, v1, N, 0, 1, counts, stream);
-  if (rc != VR_OK) return rc;
-  heads_kernel<<<(G + 7) / 8, 256, 0, stream>>>(k0, v0, (uint32_t)N, G, (uint32_t)n, view);
-  VR_CHECK_LAUNCH();
-  head_tables_kernel<<<1, 1024, 0, stream>>>(view.prev_head, view.next_head, (uint32_t)N, G);
-  VR_CHECK_LAUNCH();
-  runs_kernel<<<(G + 7) / 8, 256, 0, stream>>>((uint32_t)N, G, (uint32_t)n, view);
-  VR_CHECK_LAUNCH();
-  return VR_OK;
+  const float* r[1] = {rdm};
+  void* b[1] = {presorted};
+  return vr_presort_triu_batch_f32(r, 1, n, ld, b, ws, ws_bytes, stream_);
 }
 
 extern "C" size_t vr_rank_rows_workspace_bytes(int n, int64_t d) {

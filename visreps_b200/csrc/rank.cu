@@ -89,9 +89,8 @@ __device__ __forceinline__ uint32_t warp_bit_transpose(uint32_t w, unsigned lane
 // Dynamic shared memory: maskT of the batch, n words.
 __global__ void __launch_bounds__(kCountThreads)
 count_kernel(const __grid_constant__ BlobList blobs, int n, const uint32_t* __restrict__ maskT, int R,
-             uint2* __restrict__ tables, uint32_t Gs) {
+             uint2* __restrict__ tables, uint32_t Gs, uint32_t* __restrict__ seg_tot) {
   extern __shared__ __align__(16) uint32_t s_maskT[];
-  __shared__ uint32_t s_tot[kCountWarps][32];
   const unsigned lane = lane_id();
   const int warp = threadIdx.x >> 5;
   const int v = blockIdx.y, batch = blockIdx.x;
@@ -127,36 +126,28 @@ count_kernel(const __grid_constant__ BlobList blobs, int n, const uint32_t* __re
       dst[1] = make_uint4(K[2], C[2], K[3], C[3]);
     }
   }
-  // make the counts global: add the totals of the preceding warps' segments
-  s_tot[warp][lane] = running;
-  __syncthreads();
-  uint32_t base = 0;
-  for (int w = 0; w < warp; ++w) base += s_tot[w][lane];
-  if (rep < R) {
-    if (base)
-      for (uint32_t g = g_lo; g < g_hi; ++g) my_table[g].y += base;
-    if (warp == kCountWarps - 1) {                           // sentinel entry: C(N) = N_r
-      uint32_t tot = base + running;
-      for (uint32_t g = G; g < Gs; ++g) my_table[g] = make_uint2(0u, tot);
-    }
-  }
+  // counts are relative to the warp's segment; rank_kernel adds the segment bases from seg_tot
+  if (rep < R) seg_tot[((int64_t)v * R + rep) * kCountWarps + warp] = running;
 }
 
 // Dynamic shared memory: mask words [round_up(W,4)] | table uint2[Gs] (only when kSmemTable).
 template <bool kSmemTable>
 __global__ void __launch_bounds__(kRankThreads, 1)
 rank_kernel(const __grid_constant__ BlobList blobs, int n_vectors, int n, const uint32_t* __restrict__ masks,
-            int W, int R, const uint2* __restrict__ tables, uint32_t Gs, int32_t* __restrict__ dev,
-            int64_t dev_stride, double* __restrict__ ss_out, int64_t* __restrict__ nkept_out) {
+            int W, int R, uint2* __restrict__ tables, uint32_t Gs, const uint32_t* __restrict__ seg_tot,
+            int32_t* __restrict__ dev, int64_t dev_stride, double* __restrict__ ss_out,
+            int64_t* __restrict__ nkept_out) {
   extern __shared__ __align__(16) uint32_t smem[];
   uint32_t* s_mask = smem;
   uint2* s_table = reinterpret_cast<uint2*>(smem + ((W + 3) & ~3));
   __shared__ double s_red[kRankWarps];
+  __shared__ uint32_t s_base[kCountWarps + 1];
 
   const unsigned lane = lane_id();
   const int warp = threadIdx.x >> 5;
   const uint32_t N = (uint32_t)triu_len(n);
   const uint32_t G = (N + 31u) / 32u;
+  const uint32_t seg_groups = ((((G + 31u) / 32u) + kCountWarps - 1) / kCountWarps) * 32u;  // count_kernel's segments
   const uint32_t sbits = run_sbits(N);
   const uint32_t smask = (1u << sbits) - 1u;
   const uint32_t esc = (1u << (32u - sbits)) - 1u;
@@ -165,16 +156,27 @@ rank_kernel(const __grid_constant__ BlobList blobs, int n_vectors, int n, const 
   for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
     const int v = (int)(item / R), r = (int)(item % R);
     PresortView blob = presort_view(const_cast<void*>(blobs.p[v]), n);
-    const uint2* __restrict__ g_table = tables + item * Gs;
+    uint2* __restrict__ g_table = tables + item * Gs;
     for (int w = threadIdx.x; w < W; w += kRankThreads) s_mask[w] = masks[(int64_t)r * W + w];
-    if (kSmemTable) {
-      const uint4* src = reinterpret_cast<const uint4*>(g_table);
-      uint4* dst = reinterpret_cast<uint4*>(s_table);
-      for (uint32_t q = threadIdx.x; q < Gs / 2; q += kRankThreads) dst[q] = src[q];
+    if (threadIdx.x == 0) {                                  // exclusive prefix of the segment totals
+      uint32_t run = 0;
+      for (int w = 0; w < kCountWarps; ++w) { s_base[w] = run; run += seg_tot[item * kCountWarps + w]; }
+      s_base[kCountWarps] = run;
+    }
+    __syncthreads();
+    const uint32_t Ns = s_base[kCountWarps];
+    // bring the table in (shared memory) or finish it in place (global), adding the segment bases;
+    // entries >= G become the sentinel {0, N_r} so that C(N) needs no special case
+    {
+      uint2* dst = kSmemTable ? s_table : g_table;
+      for (uint32_t g = threadIdx.x; g < Gs; g += kRankThreads) {
+        uint2 e = make_uint2(0u, Ns);
+        if (g < G) { e = g_table[g]; e.y += s_base[g / seg_groups]; }
+        dst[g] = e;
+      }
     }
     __syncthreads();
     const uint2* __restrict__ table = kSmemTable ? s_table : g_table;
-    const uint32_t Ns = table[G].y;
 
     int32_t* __restrict__ out = dev + item * dev_stride;
     const uint32_t* __restrict__ runs = blob.runs;
@@ -319,7 +321,8 @@ static inline size_t rank_smem_bytes(int n, bool smem_table) {
 }
 // scratch of one launch over nV vectors x R replicates: transposed masks + count tables
 static inline size_t rank_scratch_bytes(int n, int nV, int64_t R) {
-  return arena_bytes((size_t)((R + 31) / 32) * n, 4) + arena_bytes((size_t)nV * R * table_groups(n), 8);
+  return arena_bytes((size_t)((R + 31) / 32) * n, 4) + arena_bytes((size_t)nV * R * table_groups(n), 8) +
+         arena_bytes((size_t)nV * R * kCountWarps, 4);
 }
 
 static int launch_rank(const BlobList& blobs, int nV, int n, const uint32_t* masks, int R, int32_t* dev,
@@ -330,6 +333,7 @@ static int launch_rank(const BlobList& blobs, int nV, int n, const uint32_t* mas
   Arena a(scratch, scratch_bytes);
   uint32_t* maskT = a.take<uint32_t>((size_t)batches * n);
   uint2* tables = a.take<uint2>((size_t)nV * R * Gs);
+  uint32_t* seg_tot = a.take<uint32_t>((size_t)nV * R * kCountWarps);
   if (!a.ok) { set_error("rank scratch too small"); return VR_ERR_WORKSPACE; }
   ProfScope prof(F_RANK, stream);
   {
@@ -345,7 +349,7 @@ static int launch_rank(const BlobList& blobs, int nV, int n, const uint32_t* mas
       attr_set = true;
     }
     dim3 grid(batches, nV);
-    count_kernel<<<grid, kCountThreads, smem, stream>>>(blobs, n, maskT, R, tables, Gs);
+    count_kernel<<<grid, kCountThreads, smem, stream>>>(blobs, n, maskT, R, tables, Gs, seg_tot);
     VR_CHECK_LAUNCH();
   }
   const bool in_smem = rank_table_in_smem(n);
@@ -359,10 +363,10 @@ static int launch_rank(const BlobList& blobs, int nV, int n, const uint32_t* mas
                                          (int)(kRankSmemTableMax + 8192)));
       attr_set = true;
     }
-    rank_kernel<true><<<grid, kRankThreads, smem, stream>>>(blobs, nV, n, masks, W, R, tables, Gs, dev,
+    rank_kernel<true><<<grid, kRankThreads, smem, stream>>>(blobs, nV, n, masks, W, R, tables, Gs, seg_tot, dev,
                                                            vr_dev_stride(n), ss, nkept);
   } else {
-    rank_kernel<false><<<grid, kRankThreads, smem, stream>>>(blobs, nV, n, masks, W, R, tables, Gs, dev,
+    rank_kernel<false><<<grid, kRankThreads, smem, stream>>>(blobs, nV, n, masks, W, R, tables, Gs, seg_tot, dev,
                                                             vr_dev_stride(n), ss, nkept);
   }
   VR_CHECK_LAUNCH();
@@ -417,7 +421,7 @@ struct SpearmanPlan {
 SpearmanPlan spearman_plan(int n, int nV) {
   SpearmanPlan p;
   p.fixed = arena_bytes((size_t)n * 2100, 4) + 8192;   // transposed masks of up to 65535 replicates + slack
-  p.per_rep = (size_t)nV * ((size_t)vr_dev_stride(n) * 4 + (size_t)table_groups(n) * 8 + 8 + 8);
+  p.per_rep = (size_t)nV * ((size_t)vr_dev_stride(n) * 4 + (size_t)table_groups(n) * 8 + 8 + 8 + 4 * kCountWarps);
   return p;
 }
 constexpr size_t kSoftCap = (size_t)40 << 30;  // default upper bound on one call's workspace

@@ -58,7 +58,7 @@ class PresortedRDM:
     sorting again.  Keeps the source RDM alive for the Pearson path.
     """
 
-    def __init__(self, rdm: torch.Tensor):
+    def __init__(self, rdm: torch.Tensor, _defer: bool = False):
         lib = _lib.load()
         dev = _lib.require_cuda()
         self.rdm = _as_cuda_f32_rows(rdm, dev)
@@ -66,9 +66,37 @@ class PresortedRDM:
             raise ValueError("RDM must be square")
         self.n = int(self.rdm.size(0))
         self.blob = torch.empty(lib.vr_presort_bytes(self.n), dtype=torch.uint8, device=dev)
-        ws = _lib.workspace(lib.vr_presort_workspace_bytes(self.n), dev)
-        _lib.check(lib.vr_presort_triu_f32(self.rdm.data_ptr(), self.n, self.rdm.stride(0), self.blob.data_ptr(),
-                                           ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "vr_presort_triu_f32")
+        if not _defer:
+            PresortedRDM._sort_batch([self])
+
+    @staticmethod
+    def _sort_batch(items: "Sequence[PresortedRDM]") -> None:
+        lib = _lib.load()
+        dev = items[0].blob.device
+        n, ld = items[0].n, items[0].rdm.stride(0)
+        for k0 in range(0, len(items), 64):
+            part = items[k0:k0 + 64]
+            for it in part:
+                if it.rdm.stride(0) != ld:
+                    it.rdm = it.rdm.contiguous()
+            if any(it.rdm.stride(0) != ld for it in part):
+                for it in part:
+                    it.rdm = it.rdm.contiguous()
+                ld = n
+            ws = _lib.workspace(lib.vr_presort_batch_workspace_bytes(n, len(part)), dev)
+            _lib.check(lib.vr_presort_triu_batch_f32(_ptr_array([it.rdm for it in part]), len(part), n, ld,
+                                                     _ptr_array([it.blob for it in part]), ws.data_ptr(), ws.numel(),
+                                                     _lib.stream_ptr()), "vr_presort_triu_batch_f32")
+
+    @classmethod
+    def batch(cls, rdms: Sequence[torch.Tensor]) -> "List[PresortedRDM]":
+        """Presort several RDMs of the same size with one batched device sort."""
+        items = [cls(r, _defer=True) for r in rdms]
+        if items:
+            if any(it.n != items[0].n for it in items):
+                raise ValueError("RDMs must share the same 2-D shape")
+            cls._sort_batch(items)
+        return items
 
 
 def full_mask(n: int) -> np.ndarray:
@@ -254,6 +282,17 @@ def _prepare(rdm, method: str):
     return PresortedRDM(rdm) if method == "spearman" else _RawRDM(rdm)
 
 
+def _prepare_many(rdms: Sequence, method: str) -> list:
+    """Presort (Spearman) or wrap (Pearson) a list of RDMs; raw tensors are presorted in one batch."""
+    if method != "spearman":
+        return [_prepare(r, method) for r in rdms]
+    out = [r if isinstance(r, PresortedRDM) else None for r in rdms]
+    todo = [k for k, r in enumerate(out) if r is None]
+    for k, item in zip(todo, PresortedRDM.batch([rdms[k] for k in todo])):
+        out[k] = item
+    return out
+
+
 def bootstrap_rdm_correlation_grouped(model_rdms: Sequence, neural_rdms: Sequence, method: str,
                                       n_bootstrap: int = 1000, seed: int = 42,
                                       index_sets: Optional[np.ndarray] = None,
@@ -268,8 +307,8 @@ def bootstrap_rdm_correlation_grouped(model_rdms: Sequence, neural_rdms: Sequenc
     """
     method = method.lower()
     dev = _lib.require_cuda()
-    A = [_prepare(r, method) for r in model_rdms]
-    B = [_prepare(r, method) for r in neural_rdms]
+    both = _prepare_many(list(model_rdms) + list(neural_rdms), method)
+    A, B = both[:len(model_rdms)], both[len(model_rdms):]
     n = A[0].n
     if index_sets is None:
         index_sets = draw_index_sets(n, n_bootstrap, seed, rng)
@@ -323,7 +362,7 @@ def compute_rsa(cfg: Dict, selection: "AlignmentData", evaluation: "AlignmentDat
     dev = _lib.require_cuda()
     neural_sel = _prepare(compute_rdm(selection.neural[sel_idx].to(dev)), method)
     names = list(selection.activations.keys())
-    layer_rdms = [_prepare(compute_rdm(_flat(selection.activations[k][sel_idx]).to(dev)), method) for k in names]
+    layer_rdms = _prepare_many([compute_rdm(_flat(selection.activations[k][sel_idx]).to(dev)) for k in names], method)
     full = build_masks(None, len(sel_idx), dev, with_full=True)
     sel = compare_grouped(layer_rdms, [neural_sel], method, full)[:, 0, 0].cpu().numpy()
     selection_scores, best_layer, best_score = [], None, -float("inf")
@@ -453,10 +492,9 @@ def rsa_grouped(model_features: Sequence[torch.Tensor], neural_responses: Sequen
     nA, nB = len(model_features), len(neural_responses)
     flags = torch.zeros(nA + nB, dtype=torch.int32, device=dev)
     # enqueue RDM + presort for every matrix (asynchronous) ...
-    prepared = []
-    for k, x in enumerate(list(model_features) + list(neural_responses)):
-        rdm = _rdm_device(x, dev, correction, flags, k)
-        prepared.append(_prepare(rdm, method))
+    rdms = [_rdm_device(x, dev, correction, flags, k)
+            for k, x in enumerate(list(model_features) + list(neural_responses))]
+    prepared = _prepare_many(rdms, method)
     # ... and draw the index sets on the host meanwhile
     if bootstrap and index_sets is None:
         index_sets = draw_index_sets(n, n_bootstrap, seed)
