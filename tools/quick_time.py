@@ -31,7 +31,12 @@ def main():
     for d in dims + [193600]:
         x = torch.relu(z @ (torch.randn(64, d, device=dev, generator=g) / 8) + torch.randn(n, d, device=dev, generator=g))
         t = ev_time(lambda: vb.compute_rdm(x))
-        print(f"compute_rdm n={n} d={d}: {t:.3f} ms  -> {n*(n+1)*d/t/1e9:.2f} TFLOP/s (n(n+1)d)", flush=True)
+        r = vb.compute_rdm(x)
+        xd = x.double(); xd = xd - xd.mean(1, keepdim=True); sd = (xd.pow(2).mean(1) + 1e-12).sqrt()
+        truth = 1 - ((xd @ xd.T) / d / (sd[:, None] * sd[None, :] + 1e-12)).clamp(-1, 1); truth.fill_diagonal_(0)
+        err = float((r.double() - truth).abs().max())
+        del xd, truth
+        print(f"compute_rdm n={n} d={d}: {t:.3f} ms  -> {n*(n+1)*d/t/1e9:.2f} TFLOP/s (n(n+1)d)  max|err| vs fp64 = {err:.2e}", flush=True)
         del x
     models = [vb.compute_rdm(torch.relu(z @ (torch.randn(64, 512, device=dev, generator=g) / 8) + torch.randn(n, 512, device=dev, generator=g))) for _ in range(nA)]
     neurals = [vb.compute_rdm(z @ torch.randn(64, 300, device=dev, generator=g) + 0.5 * torch.randn(n, 300, device=dev, generator=g)) for _ in range(nA)]

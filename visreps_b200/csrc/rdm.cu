@@ -6,10 +6,11 @@
 //   rdm_epilogue_kernel sum of K-splits, /d, /(std_i std_j + c), clamp, diag,
 //                       1 - corr, mirrored to the lower triangle              rsa.py:89-92
 //
-// The SYRK here is the fp32 CUDA-core version (exact fp32 products, fp32 accumulation per
-// K-split, fp64 across splits); it is the reference the tcgen05 kernel in syrk_tc.cu is
-// checked against and the path used for shapes below one tensor tile.
+// The SYRK is the tcgen05 / TMEM / TMA kernel of syrk_tc.cuh (3xTF32, fp32-accurate).  An fp32
+// CUDA-core SYRK is kept only as a cross-check, selectable with VR_SYRK_IMPL=ffma.
+#include <cstdlib>
 #include "common.cuh"
+#include "syrk_tc.cuh"
 
 namespace vr {
 
@@ -22,6 +23,11 @@ struct RdmPlan {
   int splits;       // K-splits
   int64_t k_per_split;  // multiple of 32
   int nb;           // 64-row blocks
+  // tensor-core plan
+  int nb128;        // 128-row blocks
+  int kb_total;     // 32-column K blocks
+  int kb_per_split;
+  int tc_splits;
 };
 
 inline RdmPlan rdm_plan(int n, int64_t d) {
@@ -40,19 +46,34 @@ inline RdmPlan rdm_plan(int n, int64_t d) {
   if (s < 1) s = 1;
   p.k_per_split = round_up((p.d_pad + s - 1) / s, 32);
   p.splits = (int)((p.d_pad + p.k_per_split - 1) / p.k_per_split);
+  // tensor-core plan: <= 1024 columns per accumulation chain, >= 2 CTAs per SM worth of work if K allows
+  p.nb128 = p.n_pad / tc::kBM;
+  p.kb_total = (int)(p.d_pad / tc::kBK);
+  const int64_t tiles128 = (int64_t)p.nb128 * (p.nb128 + 1) / 2;
+  int64_t want_splits = (2 * kNumSMs + tiles128 - 1) / tiles128;
+  int64_t kbs = (p.kb_total + want_splits - 1) / want_splits;
+  if (kbs < 8) kbs = 8;
+  if (kbs > tc::kMaxKbPerSplit) kbs = tc::kMaxKbPerSplit;
+  if (kbs > p.kb_total) kbs = p.kb_total;
+  p.kb_per_split = (int)kbs;
+  p.tc_splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
   return p;
 }
 
 // One CTA per (padded) row.  Rows >= n and columns >= d are written as zeros.
 __global__ void __launch_bounds__(256)
 row_center_kernel(const float* __restrict__ X, int n, int64_t d, int64_t ldx, float correction,
-                  float* __restrict__ Z, int64_t d_pad, float* __restrict__ stdv, int* __restrict__ zero_rows) {
+                  float* __restrict__ Z, float* __restrict__ Zlo, int64_t d_pad, float* __restrict__ stdv,
+                  int* __restrict__ zero_rows) {
   __shared__ double s_red[8];
   __shared__ float s_mean;
   const int row = blockIdx.x;
+  // Zlo == nullptr: Z receives the centred fp32 row.  Otherwise Z / Zlo receive the tf32 split
+  // hi = rn_tf32(z), lo = rn_tf32(z - hi)  (z - hi is exact in fp32).
   float* z = Z + (int64_t)row * d_pad;
+  float* zl = Zlo ? Zlo + (int64_t)row * d_pad : nullptr;
   if (row >= n) {
-    for (int64_t c = threadIdx.x; c < d_pad; c += 256) z[c] = 0.f;
+    for (int64_t c = threadIdx.x; c < d_pad; c += 256) { z[c] = 0.f; if (zl) zl[c] = 0.f; }
     return;
   }
   const float* x = X + (int64_t)row * ldx;
@@ -72,7 +93,16 @@ row_center_kernel(const float* __restrict__ X, int n, int64_t d, int64_t ldx, fl
   for (int64_t c = threadIdx.x; c < d_pad; c += 256) {
     float v = 0.f;
     if (c < d) { v = x[c] - mean; acc += (double)v * (double)v; }
-    z[c] = v;
+    if (zl) {
+      uint32_t hb, lb;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+      const float hi = __uint_as_float(hb);
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(v - hi));
+      z[c] = hi;
+      zl[c] = __uint_as_float(lb);
+    } else {
+      z[c] = v;
+    }
   }
   acc = warp_sum(acc);
   __syncthreads();
@@ -164,8 +194,9 @@ using namespace vr;
 extern "C" size_t vr_rdm_workspace_bytes(int n, int64_t d) {
   if (n < 1 || d < 1) return 256;
   RdmPlan p = rdm_plan(n, d);
-  return arena_bytes((size_t)p.n_pad * p.d_pad, 4) + arena_bytes(p.n_pad, 4) +
-         arena_bytes((size_t)p.splits * p.n_pad * p.n_pad, 4) + 256;
+  const int splits = p.splits > p.tc_splits ? p.splits : p.tc_splits;
+  return 2 * arena_bytes((size_t)p.n_pad * p.d_pad, 4) + arena_bytes(p.n_pad, 4) +
+         arena_bytes((size_t)splits * p.n_pad * p.n_pad, 4) + 256;
 }
 
 extern "C" int vr_rdm_pearson_f32(const float* X, int n, int64_t d, int64_t ldx, float correction, float* rdm,
@@ -179,21 +210,45 @@ extern "C" int vr_rdm_pearson_f32(const float* X, int n, int64_t d, int64_t ldx,
     return VR_ERR_WORKSPACE;
   }
   RdmPlan p = rdm_plan(n, d);
+  static const bool use_ffma = [] { const char* e = getenv("VR_SYRK_IMPL"); return e && e[0] == 'f'; }();
   Arena a(ws, ws_bytes);
   float* Z = a.take<float>((size_t)p.n_pad * p.d_pad);
+  float* Zlo = a.take<float>((size_t)p.n_pad * p.d_pad);
   float* stdv = a.take<float>(p.n_pad);
-  float* partial = a.take<float>((size_t)p.splits * p.n_pad * p.n_pad);
+  const int splits = use_ffma ? p.splits : p.tc_splits;
+  float* partial = a.take<float>((size_t)(p.splits > p.tc_splits ? p.splits : p.tc_splits) * p.n_pad * p.n_pad);
   if (zero_var_rows) VR_CHECK_CUDA(cudaMemsetAsync(zero_var_rows, 0, sizeof(int), stream));
-  { ProfScope prof(F_RDM_CENTER, stream);
-  row_center_kernel<<<p.n_pad, 256, 0, stream>>>(X, n, d, ldx, correction, Z, p.d_pad, stdv, zero_var_rows);
-  VR_CHECK_LAUNCH(); }
-  dim3 grid(p.nb * (p.nb + 1) / 2, p.splits);
-  { ProfScope prof(F_RDM_SYRK, stream);
-  syrk_ffma_kernel<<<grid, 256, 0, stream>>>(Z, p.d_pad, p.n_pad, p.nb, p.k_per_split, partial);
-  VR_CHECK_LAUNCH(); }
+  {
+    ProfScope prof(F_RDM_CENTER, stream);
+    row_center_kernel<<<p.n_pad, 256, 0, stream>>>(X, n, d, ldx, correction, Z, use_ffma ? nullptr : Zlo, p.d_pad, stdv,
+                                                   zero_var_rows);
+    VR_CHECK_LAUNCH();
+  }
+  if (use_ffma) {
+    ProfScope prof(F_RDM_SYRK, stream);
+    dim3 grid(p.nb * (p.nb + 1) / 2, p.splits);
+    syrk_ffma_kernel<<<grid, 256, 0, stream>>>(Z, p.d_pad, p.n_pad, p.nb, p.k_per_split, partial);
+    VR_CHECK_LAUNCH();
+  } else {
+    CUtensorMap map_hi, map_lo;
+    int rc = tc::make_plane_map(&map_hi, Z, p.n_pad, p.d_pad);
+    if (rc != VR_OK) return rc;
+    rc = tc::make_plane_map(&map_lo, Zlo, p.n_pad, p.d_pad);
+    if (rc != VR_OK) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+      VR_CHECK_CUDA(cudaFuncSetAttribute(tc::syrk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes));
+      attr_set = true;
+    }
+    ProfScope prof(F_RDM_SYRK, stream);
+    dim3 grid(p.nb128 * (p.nb128 + 1) / 2, p.tc_splits);
+    tc::syrk_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, stream>>>(map_hi, map_lo, p.nb128, p.kb_total, p.kb_per_split,
+                                                                     partial, p.n_pad);
+    VR_CHECK_LAUNCH();
+  }
   dim3 eg((n + 255) / 256, n);
   ProfScope prof(F_RDM_EPILOGUE, stream);
-  rdm_epilogue_kernel<<<eg, 256, 0, stream>>>(partial, p.splits, p.n_pad, n, d, stdv, correction, rdm);
+  rdm_epilogue_kernel<<<eg, 256, 0, stream>>>(partial, splits, p.n_pad, n, d, stdv, correction, rdm);
   VR_CHECK_LAUNCH();
   return VR_OK;
 }
