@@ -274,17 +274,20 @@ def run_ours(args):
     m = int(n * 0.9)
     N_sub = m * (m - 1) // 2
     roofline = None
-    if dom in ("rank", "dot"):
-        per_launch_ms = prof[dom]["ms"] / max(1, prof[dom]["launches"])
-        rankings_per_launch = (nA + nB) * (B + 1)
-        # 8*N_sub bytes per replicate comparison = 4*N_sub per ranked vector (rank kernel);
-        # the dot kernel reads both rank vectors of all nA+nB vectors once: 4*N_sub per vector as well.
+    if dom in ("rank", "rank_fused", "kept"):
+        # one launch of this family ranks (or counts) a side's vectors for all B+1 masks
+        vectors = {"rank": min(nA, nB, 8), "rank_fused": max(nA, nB), "kept": nA + nB}[dom]
+        per_launch_ms = prof[dom]["ms"] / max(1, prof[dom]["scopes"])
+        rankings_per_launch = vectors * (B + 1)
+        # 8*N_sub bytes per replicate comparison = 4*N_sub per ranked vector
         alg_bytes = rankings_per_launch * 4.0 * N_sub
         achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
-        roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+        roofline = {"kernel": {"rank": "rank_kernel<materialise>", "rank_fused": "rank_kernel<fused dot>", "kept": "count_kernel"}[dom],
+                    "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                     "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": per_launch_ms,
-                    "definition": "4*N_sub bytes per ranked vector x (nA+nB)*(B+1) vectors per launch (SURVEY 8d: 8*N_sub per replicate compare)"}
+                    "definition": "4*N_sub bytes per ranked vector (SURVEY 8d: 8*N_sub per replicate comparison = two ranked vectors) "
+                                  "x vectors*(B+1) ranked per launch"}
     elif dom == "rdm_syrk":
         flops = sum(n * (n + 1) * t.shape[1] for t in X + Y)
         tf_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))

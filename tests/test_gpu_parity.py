@@ -237,6 +237,26 @@ def test_bootstrap_against_oracle_loop_and_grouping(dev):
     assert len(s) == 1 and lo == hi == s[0]
 
 
+def test_grouped_with_more_than_one_materialised_group(dev):
+    """10 model x 9 neural RDMs: the smaller side is materialised in groups of 8, so two groups."""
+    rs = np.random.RandomState(21)
+    n, B = 64, 5
+    base = rs.standard_normal((n, 12)).astype(np.float32)
+    mk = lambda k: orc.rdm(torch.from_numpy((base @ rs.standard_normal((12, 20 + k)) + rs.standard_normal((n, 20 + k))).astype(np.float32)))
+    models = [mk(k) for k in range(10)]
+    neurals = [mk(k + 3) for k in range(9)]
+    idx = orc.draw_subsamples(n, B, 42)
+    res = vb.bootstrap_rdm_correlation_grouped(models, neurals, "spearman", n_bootstrap=B, seed=42)
+    for i in (0, 7, 8, 9):
+        for j in (0, 4, 7, 8):
+            want = orc.bootstrap_compare_with_indices(models[i], neurals[j], "spearman", idx)
+            np.testing.assert_allclose(res["scores"][i, j], want, atol=SCORE_TOL, rtol=0)
+            assert abs(res["point"][i, j] - orc.rdm_compare(models[i], neurals[j], correlation="Spearman")) <= SCORE_TOL
+    # transposed roles (fewer models than neural RDMs) give the transposed result
+    res_t = vb.bootstrap_rdm_correlation_grouped(neurals, models, "spearman", n_bootstrap=B, seed=42)
+    np.testing.assert_allclose(res_t["scores"], np.transpose(res["scores"], (1, 0, 2)), atol=1e-15, rtol=0)
+
+
 def test_compute_rsa_matches_reference_fixture(dev, golden_dir):
     with open(os.path.join(golden_dir, "compute_rsa.json")) as f:
         gold = json.load(f)["results"]

@@ -16,14 +16,14 @@ void set_error(const char* fmt, ...) {
 }
 
 // ---- stage profiler ---------------------------------------------------------------------
-static const char* kFamilyNames[F_COUNT] = {"masks", "presort", "rank", "dot", "pearson",
+static const char* kFamilyNames[F_NUM_FAMILIES] = {"masks", "presort", "count", "rank", "rank_fused", "pearson",
                                             "rdm_center", "rdm_syrk", "rdm_epilogue", "row_rank"};
 struct ProfRec { int fam; cudaEvent_t a, b; };
 static std::mutex g_prof_mu;
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;        // records of the current session
 static std::vector<cudaEvent_t> g_pool;    // recycled events
-static unsigned long long g_fam_launches[F_COUNT];
+static unsigned long long g_fam_launches[F_NUM_FAMILIES];
 static thread_local int t_family = -1;
 
 void count_launch(unsigned n) {
@@ -60,20 +60,20 @@ ProfScope::~ProfScope() {
 }
 }  // namespace vr
 
-extern "C" int vr_profile_family_count(void) { return vr::F_COUNT; }
-extern "C" const char* vr_profile_family_name(int i) { return (i >= 0 && i < vr::F_COUNT) ? vr::kFamilyNames[i] : ""; }
+extern "C" int vr_profile_family_count(void) { return vr::F_NUM_FAMILIES; }
+extern "C" const char* vr_profile_family_name(int i) { return (i >= 0 && i < vr::F_NUM_FAMILIES) ? vr::kFamilyNames[i] : ""; }
 extern "C" int vr_profile_start(void) {
   std::lock_guard<std::mutex> lk(vr::g_prof_mu);
   for (auto& r : vr::g_prof) { vr::g_pool.push_back(r.a); vr::g_pool.push_back(r.b); }
   vr::g_prof.clear();
-  for (int i = 0; i < vr::F_COUNT; ++i) vr::g_fam_launches[i] = 0;
+  for (int i = 0; i < vr::F_NUM_FAMILIES; ++i) vr::g_fam_launches[i] = 0;
   vr::g_prof_on = true;
   return VR_OK;
 }
 extern "C" int vr_profile_stop(double* ms, unsigned long long* scopes, unsigned long long* launches) {
   std::lock_guard<std::mutex> lk(vr::g_prof_mu);
   vr::g_prof_on = false;
-  for (int i = 0; i < vr::F_COUNT; ++i) {
+  for (int i = 0; i < vr::F_NUM_FAMILIES; ++i) {
     if (ms) ms[i] = 0.0;
     if (scopes) scopes[i] = 0;
     if (launches) launches[i] = vr::g_fam_launches[i];

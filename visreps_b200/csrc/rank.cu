@@ -21,7 +21,9 @@
 //   copied to shared memory (global when it does not fit); for every pair the precomputed run
 //   bounds (one packed word, coalesced) give C(s) and C(e) with two table reads + popc.
 //   Reads and the dev write are coalesced; the only random accesses hit the table.
-// dot_kernel: per replicate, tiles of 4x4 (model, neural) vectors, exact int64 products.
+//   The side of the comparison with fewer vectors is materialised (dev vectors in HBM); the items of
+//   the other side multiply their dev values with those vectors on the fly (fused) and emit rho.
+#include <type_traits>
 #include "common.cuh"
 
 namespace vr {
@@ -130,37 +132,81 @@ count_kernel(const __grid_constant__ BlobList blobs, int n, const uint32_t* __re
   if (rep < R) seg_tot[((int64_t)v * R + rep) * kCountWarps + warp] = running;
 }
 
+// ---------------------------------------------------------------------------------------------
+// rank_kernel: one CTA per (vector, replicate) item, persistent over items.
+//   kFused == false ("materialise"): writes dev (int32, canonical order, 0 for dropped pairs) and ss.
+//   kFused == true : the item's dev values never leave registers; they are multiplied on the fly with
+//                    the <= kFuseMax materialised vectors of the same replicate (coalesced int4 reads)
+//                    and the finished Spearman coefficients are written.  Items are ordered
+//                    replicate-major so the CTAs sharing one replicate's materialised vectors run
+//                    together and hit L2.
+//   Acc = long long (exact) while N^3 fits 2^62, else double.
 // Dynamic shared memory: mask words [round_up(W,4)] | table uint2[Gs] (only when kSmemTable).
-template <bool kSmemTable>
+// ---------------------------------------------------------------------------------------------
+constexpr int kFuseMax = 8;
+
+struct RankArgs {
+  BlobList blobs;            // the vectors ranked by this launch
+  int n_vectors;
+  int n;
+  const uint32_t* masks;     // [R][W]
+  int W;
+  int R;
+  uint2* tables;             // [table_index(v)][R][Gs]
+  int table_base;            // index of vector 0 of this launch in the table / seg_tot arrays
+  uint32_t Gs;
+  const uint32_t* seg_tot;   // [table index][R][kCountWarps]
+  int64_t dev_stride;
+  // materialise
+  int32_t* dev;              // [n_vectors][R][dev_stride]
+  double* ss;                // [n_vectors][R]
+  int64_t* nkept;            // [n_vectors][R]  (nullable)
+  // fused
+  const int32_t* mat_dev;    // [n_mat][R][dev_stride]
+  const double* mat_ss;      // [n_mat][R]
+  int n_mat;
+  double* out;               // (nA, nB, Rtot)
+  int out_nB;
+  int64_t out_Rtot;
+  int out_r0;
+  int mat_is_A;              // 1: materialised vectors are the model side (rows of out)
+  int mat_off;               // index of materialised vector 0 on its side
+  int fused_off;             // index of fused vector 0 on its side
+};
+
+template <bool kSmemTable, bool kFused, typename Acc>
 __global__ void __launch_bounds__(kRankThreads, 1)
-rank_kernel(const __grid_constant__ BlobList blobs, int n_vectors, int n, const uint32_t* __restrict__ masks,
-            int W, int R, uint2* __restrict__ tables, uint32_t Gs, const uint32_t* __restrict__ seg_tot,
-            int32_t* __restrict__ dev, int64_t dev_stride, double* __restrict__ ss_out,
-            int64_t* __restrict__ nkept_out) {
+rank_kernel(const __grid_constant__ RankArgs A) {
   extern __shared__ __align__(16) uint32_t smem[];
   uint32_t* s_mask = smem;
-  uint2* s_table = reinterpret_cast<uint2*>(smem + ((W + 3) & ~3));
-  __shared__ double s_red[kRankWarps];
+  uint2* s_table = reinterpret_cast<uint2*>(smem + ((A.W + 3) & ~3));
+  __shared__ double s_red[kRankWarps][kFuseMax + 1];
   __shared__ uint32_t s_base[kCountWarps + 1];
 
   const unsigned lane = lane_id();
   const int warp = threadIdx.x >> 5;
+  const int n = A.n, R = A.R, W = A.W;
   const uint32_t N = (uint32_t)triu_len(n);
   const uint32_t G = (N + 31u) / 32u;
+  const uint32_t Gs = A.Gs;
   const uint32_t seg_groups = ((((G + 31u) / 32u) + kCountWarps - 1) / kCountWarps) * 32u;  // count_kernel's segments
   const uint32_t sbits = run_sbits(N);
   const uint32_t smask = (1u << sbits) - 1u;
   const uint32_t esc = (1u << (32u - sbits)) - 1u;
+  const int64_t dev_stride = A.dev_stride;
 
-  const int64_t items = (int64_t)n_vectors * R;
+  const int64_t items = (int64_t)A.n_vectors * R;
   for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
-    const int v = (int)(item / R), r = (int)(item % R);
-    PresortView blob = presort_view(const_cast<void*>(blobs.p[v]), n);
-    uint2* __restrict__ g_table = tables + item * Gs;
-    for (int w = threadIdx.x; w < W; w += kRankThreads) s_mask[w] = masks[(int64_t)r * W + w];
+    // materialise: vector-major (CTAs share the vector's `runs` stream); fused: replicate-major
+    const int v = kFused ? (int)(item % A.n_vectors) : (int)(item / R);
+    const int r = kFused ? (int)(item / A.n_vectors) : (int)(item % R);
+    PresortView blob = presort_view(const_cast<void*>(A.blobs.p[v]), n);
+    const int64_t tix = (int64_t)(A.table_base + v) * R + r;
+    uint2* __restrict__ g_table = A.tables + tix * Gs;
+    for (int w = threadIdx.x; w < W; w += kRankThreads) s_mask[w] = A.masks[(int64_t)r * W + w];
     if (threadIdx.x == 0) {                                  // exclusive prefix of the segment totals
       uint32_t run = 0;
-      for (int w = 0; w < kCountWarps; ++w) { s_base[w] = run; run += seg_tot[item * kCountWarps + w]; }
+      for (int w = 0; w < kCountWarps; ++w) { s_base[w] = run; run += A.seg_tot[tix * kCountWarps + w]; }
       s_base[kCountWarps] = run;
     }
     __syncthreads();
@@ -178,13 +224,15 @@ rank_kernel(const __grid_constant__ BlobList blobs, int n_vectors, int n, const 
     __syncthreads();
     const uint2* __restrict__ table = kSmemTable ? s_table : g_table;
 
-    int32_t* __restrict__ out = dev + item * dev_stride;
+    int32_t* __restrict__ out_dev = kFused ? nullptr : A.dev + ((int64_t)v * R + r) * dev_stride;
+    const int32_t* __restrict__ mat = kFused ? A.mat_dev + (int64_t)r * dev_stride : nullptr;
+    const int64_t mat_step = (int64_t)R * dev_stride;        // between materialised vectors
     const uint32_t* __restrict__ runs = blob.runs;
-    long long acc = 0;
-    double accd = 0.0;
-    int since_flush = 0;
-    // |dev| <= N, so one step adds < 4 N^2; fold into fp64 before 2^62 can be reached
-    const int flush_every = (int)min(1024ull, (1ull << 62) / (4ull * (unsigned long long)N * N + 1ull) + 1ull);
+    Acc acc_ss = 0;
+    Acc acc[kFuseMax];
+#pragma unroll
+    for (int a = 0; a < kFuseMax; ++a) acc[a] = 0;
+
     for (uint32_t p0 = threadIdx.x * 4u; p0 < (uint32_t)dev_stride; p0 += kRankThreads * 4u) {
       int32_t d4[4] = {0, 0, 0, 0};
       if (p0 < N) {
@@ -210,106 +258,67 @@ rank_kernel(const __grid_constant__ BlobList blobs, int n_vectors, int n, const 
           const uint32_t kept = ki & (s_mask[j >> 5] >> (j & 31u)) & (p0 + e < N ? 1u : 0u);
           const int32_t d = kept ? (int32_t)(lo + hi) - (int32_t)Ns : 0;
           d4[e] = d;
-          acc += (long long)d * (long long)d;
+          acc_ss += (Acc)d * (Acc)d;
           if (++j == (uint32_t)n) { ++i; j = i + 1u; ki = (s_mask[min(i, (uint32_t)n - 1u) >> 5] >> (i & 31u)) & 1u; }
         }
-        if (++since_flush >= flush_every) { since_flush = 0; accd += (double)acc; acc = 0; }
       }
-      *reinterpret_cast<int4*>(out + p0) = make_int4(d4[0], d4[1], d4[2], d4[3]);
+      if (kFused) {
+        if (p0 < N) {
+#pragma unroll
+          for (int a = 0; a < kFuseMax; ++a) {
+            if (a < A.n_mat) {
+              const int4 m4 = __ldg(reinterpret_cast<const int4*>(mat + a * mat_step + p0));
+              acc[a] += (Acc)d4[0] * (Acc)m4.x + (Acc)d4[1] * (Acc)m4.y + (Acc)d4[2] * (Acc)m4.z + (Acc)d4[3] * (Acc)m4.w;
+            }
+          }
+        }
+      } else {
+        *reinterpret_cast<int4*>(out_dev + p0) = make_int4(d4[0], d4[1], d4[2], d4[3]);
+      }
     }
-    accd += (double)acc;
-    accd = warp_sum(accd);
-    if (lane == 0) s_red[warp] = accd;
+
+    // block reduction: ss (slot kFuseMax) and, when fused, the n_mat dot products
+    {
+      double v_ss = warp_sum((double)acc_ss);
+      if (lane == 0) s_red[warp][kFuseMax] = v_ss;
+      if (kFused) {
+#pragma unroll
+        for (int a = 0; a < kFuseMax; ++a) {
+          if (a < A.n_mat) {
+            double t;
+            if constexpr (std::is_integral<Acc>::value) t = (double)warp_sum_ll((long long)acc[a]);   // exact
+            else t = warp_sum((double)acc[a]);
+            if (lane == 0) s_red[warp][a] = t;
+          }
+        }
+      }
+    }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x <= kFuseMax) {
+      const int slot = threadIdx.x;
       double tot = 0.0;
-      for (int w = 0; w < kRankWarps; ++w) tot += s_red[w];
-      if (blob.hdr->has_nan) tot = __longlong_as_double(0x7ff8000000000000LL);
-      ss_out[item] = tot;
-      nkept_out[item] = (int64_t)Ns;
-    }
-    __syncthreads();  // table + s_mask are reused by the next item
-  }
-}
-
-// out[a][b][r] = sum_p devA[a][r][p] * devB[b][r][p] / sqrt(ssA[a][r] * ssB[b][r])
-constexpr int kDotThreads = 256;
-constexpr int kDotTile = 4;
-__global__ void __launch_bounds__(kDotThreads)
-dot_kernel(const int32_t* __restrict__ dev, int64_t dev_stride, const double* __restrict__ ss, int nA, int nB,
-           int R, int r0, int Rtot, double* __restrict__ out) {
-  __shared__ long long s_part[kDotThreads / 32][kDotTile * kDotTile];
-  __shared__ double s_partd[kDotThreads / 32][kDotTile * kDotTile];
-  const int tilesB = (nB + kDotTile - 1) / kDotTile;
-  const int ta = blockIdx.x / tilesB, tb = blockIdx.x % tilesB;
-  const int r = blockIdx.y;
-  const int a0 = ta * kDotTile, b0 = tb * kDotTile;
-  const int4* pa[kDotTile];
-  const int4* pb[kDotTile];
-#pragma unroll
-  for (int k = 0; k < kDotTile; ++k) {
-    const int a = min(a0 + k, nA - 1), b = min(b0 + k, nB - 1);
-    pa[k] = reinterpret_cast<const int4*>(dev + ((int64_t)a * R + r) * dev_stride);
-    pb[k] = reinterpret_cast<const int4*>(dev + ((int64_t)(nA + b) * R + r) * dev_stride);
-  }
-  const int64_t n4 = dev_stride / 4;
-  long long acc[kDotTile][kDotTile];
-  double accd[kDotTile][kDotTile];
-#pragma unroll
-  for (int x = 0; x < kDotTile; ++x)
-#pragma unroll
-    for (int y = 0; y < kDotTile; ++y) { acc[x][y] = 0; accd[x][y] = 0.0; }
-
-  int since_flush = 0;
-  // |dev| <= N (= dev_stride up to padding): one step adds < 4 N^2 per accumulator
-  const int flush_every = (int)min(256ull, (1ull << 62) / (4ull * (unsigned long long)dev_stride * dev_stride + 1ull) + 1ull);
-  for (int64_t q = threadIdx.x; q < n4; q += kDotThreads) {
-    int4 va[kDotTile], vb[kDotTile];
-#pragma unroll
-    for (int k = 0; k < kDotTile; ++k) { va[k] = __ldg(pa[k] + q); vb[k] = __ldg(pb[k] + q); }
-#pragma unroll
-    for (int x = 0; x < kDotTile; ++x)
-#pragma unroll
-      for (int y = 0; y < kDotTile; ++y) {
-        acc[x][y] += (long long)va[x].x * vb[y].x + (long long)va[x].y * vb[y].y +
-                     (long long)va[x].z * vb[y].z + (long long)va[x].w * vb[y].w;
+      if (slot == kFuseMax || (kFused && slot < A.n_mat))
+        for (int w = 0; w < kRankWarps; ++w) tot += s_red[w][slot];
+      const double nan = __longlong_as_double(0x7ff8000000000000LL);
+      // every participating lane needs ss of this item: recompute it locally from slot kFuseMax
+      double ss_item = 0.0;
+      for (int w = 0; w < kRankWarps; ++w) ss_item += s_red[w][kFuseMax];
+      if (blob.hdr->has_nan) ss_item = nan;
+      if (!kFused) {
+        if (slot == kFuseMax) {
+          A.ss[(int64_t)v * R + r] = ss_item;
+          if (A.nkept) A.nkept[(int64_t)v * R + r] = (int64_t)Ns;
+        }
+      } else if (slot < A.n_mat) {
+        const double ss_m = A.mat_ss[(int64_t)slot * R + r];
+        double rho = tot / (sqrt(ss_m) * sqrt(ss_item));
+        if (!(ss_m > 0.0) || !(ss_item > 0.0)) rho = nan;
+        const int ia = A.mat_is_A ? A.mat_off + slot : A.fused_off + v;
+        const int ib = A.mat_is_A ? A.fused_off + v : A.mat_off + slot;
+        A.out[((int64_t)ia * A.out_nB + ib) * A.out_Rtot + A.out_r0 + r] = rho;
       }
-    if (++since_flush >= flush_every) {
-      since_flush = 0;
-#pragma unroll
-      for (int x = 0; x < kDotTile; ++x)
-#pragma unroll
-        for (int y = 0; y < kDotTile; ++y) { accd[x][y] += (double)acc[x][y]; acc[x][y] = 0; }
     }
-  }
-  const int warp = threadIdx.x >> 5;
-  const unsigned lane = lane_id();
-  // Up to 2^20 pairs the whole sum stays below 2^60 and is carried exactly in int64; beyond
-  // that the per-thread integers are folded into fp64 before any cross-thread addition.
-  const bool exact = dev_stride <= (1ll << 20);
-#pragma unroll
-  for (int x = 0; x < kDotTile; ++x)
-#pragma unroll
-    for (int y = 0; y < kDotTile; ++y) {
-      if (!exact) { accd[x][y] += (double)acc[x][y]; acc[x][y] = 0; }
-      long long s = warp_sum_ll(acc[x][y]);
-      double sd = warp_sum(accd[x][y]);
-      if (lane == 0) { s_part[warp][x * kDotTile + y] = s; s_partd[warp][x * kDotTile + y] = sd; }
-    }
-  __syncthreads();
-  if (threadIdx.x < kDotTile * kDotTile) {
-    const int x = threadIdx.x / kDotTile, y = threadIdx.x % kDotTile;
-    double tot = 0.0;
-    long long ti = 0;
-    for (int w = 0; w < kDotThreads / 32; ++w) { ti += s_part[w][threadIdx.x]; tot += s_partd[w][threadIdx.x]; }
-    tot += (double)ti;
-    const int a = a0 + x, b = b0 + y;
-    if (a < nA && b < nB) {
-      const double sa = ss[(int64_t)a * R + r], sb = ss[(int64_t)(nA + b) * R + r];
-      double rho = tot / (sqrt(sa) * sqrt(sb));
-      if (!(sa > 0.0) || !(sb > 0.0)) rho = __longlong_as_double(0x7ff8000000000000LL);
-      out[((int64_t)a * nB + b) * Rtot + r0 + r] = rho;
-    }
+    __syncthreads();  // table, s_mask and s_red are reused by the next item
   }
 }
 
@@ -319,58 +328,77 @@ static inline size_t rank_smem_bytes(int n, bool smem_table) {
   const size_t mask_bytes = (size_t)round_up(vr_mask_words(n), 4) * 4;
   return mask_bytes + (smem_table ? (size_t)table_groups(n) * 8 : 0);
 }
-// scratch of one launch over nV vectors x R replicates: transposed masks + count tables
-static inline size_t rank_scratch_bytes(int n, int nV, int64_t R) {
+// scratch shared by the launches of one replicate chunk: transposed masks + count tables + segment totals
+static inline size_t count_scratch_bytes(int n, int nV, int64_t R) {
   return arena_bytes((size_t)((R + 31) / 32) * n, 4) + arena_bytes((size_t)nV * R * table_groups(n), 8) +
          arena_bytes((size_t)nV * R * kCountWarps, 4);
 }
+struct CountScratch {
+  uint32_t* maskT;
+  uint2* tables;
+  uint32_t* seg_tot;
+};
 
-static int launch_rank(const BlobList& blobs, int nV, int n, const uint32_t* masks, int R, int32_t* dev,
-                       double* ss, int64_t* nkept, void* scratch, size_t scratch_bytes, cudaStream_t stream) {
+// kept words + counts of every (vector, replicate) of the chunk
+static int launch_count(const BlobList& blobs, int nV, int n, const uint32_t* masks, int R, void* scratch,
+                        size_t scratch_bytes, CountScratch* cs, cudaStream_t stream) {
   const int W = vr_mask_words(n);
   const uint32_t Gs = table_groups(n);
   const int batches = (R + 31) / 32;
   Arena a(scratch, scratch_bytes);
-  uint32_t* maskT = a.take<uint32_t>((size_t)batches * n);
-  uint2* tables = a.take<uint2>((size_t)nV * R * Gs);
-  uint32_t* seg_tot = a.take<uint32_t>((size_t)nV * R * kCountWarps);
+  cs->maskT = a.take<uint32_t>((size_t)batches * n);
+  cs->tables = a.take<uint2>((size_t)nV * R * Gs);
+  cs->seg_tot = a.take<uint32_t>((size_t)nV * R * kCountWarps);
   if (!a.ok) { set_error("rank scratch too small"); return VR_ERR_WORKSPACE; }
-  ProfScope prof(F_RANK, stream);
+  ProfScope prof(F_KEPT, stream);
   {
     dim3 grid((n + 255) / 256, batches);
-    transpose_masks_kernel<<<grid, 256, 0, stream>>>(masks, R, n, W, maskT);
+    transpose_masks_kernel<<<grid, 256, 0, stream>>>(masks, R, n, W, cs->maskT);
     VR_CHECK_LAUNCH();
   }
-  {
-    static bool attr_set = false;
-    const size_t smem = (size_t)n * 4;
-    if (!attr_set && smem > 40 * 1024) {
-      VR_CHECK_CUDA(cudaFuncSetAttribute(count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-      attr_set = true;
-    }
-    dim3 grid(batches, nV);
-    count_kernel<<<grid, kCountThreads, smem, stream>>>(blobs, n, maskT, R, tables, Gs, seg_tot);
-    VR_CHECK_LAUNCH();
+  static bool attr_set = false;
+  const size_t smem = (size_t)n * 4;
+  if (!attr_set && smem > 40 * 1024) {
+    VR_CHECK_CUDA(cudaFuncSetAttribute(count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set = true;
   }
-  const bool in_smem = rank_table_in_smem(n);
-  const size_t smem = rank_smem_bytes(n, in_smem);
-  const int64_t items = (int64_t)nV * R;
-  const int grid = (int)(items < kNumSMs ? items : kNumSMs);
-  if (in_smem) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      VR_CHECK_CUDA(cudaFuncSetAttribute(rank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(kRankSmemTableMax + 8192)));
-      attr_set = true;
-    }
-    rank_kernel<true><<<grid, kRankThreads, smem, stream>>>(blobs, nV, n, masks, W, R, tables, Gs, seg_tot, dev,
-                                                           vr_dev_stride(n), ss, nkept);
-  } else {
-    rank_kernel<false><<<grid, kRankThreads, smem, stream>>>(blobs, nV, n, masks, W, R, tables, Gs, seg_tot, dev,
-                                                            vr_dev_stride(n), ss, nkept);
-  }
+  dim3 grid(batches, nV);
+  count_kernel<<<grid, kCountThreads, smem, stream>>>(blobs, n, cs->maskT, R, cs->tables, Gs, cs->seg_tot);
   VR_CHECK_LAUNCH();
   return VR_OK;
+}
+
+template <bool kSmem, bool kFused, typename Acc>
+static int launch_rank_variant(const RankArgs& args, int grid, size_t smem, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (kSmem && !attr_set) {
+    VR_CHECK_CUDA(cudaFuncSetAttribute(rank_kernel<kSmem, kFused, Acc>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(kRankSmemTableMax + 8192)));
+    attr_set = true;
+  }
+  rank_kernel<kSmem, kFused, Acc><<<grid, kRankThreads, smem, stream>>>(args);
+  VR_CHECK_LAUNCH();
+  return VR_OK;
+}
+
+static int launch_rank(const RankArgs& args, bool fused, cudaStream_t stream) {
+  const int n = args.n;
+  const bool in_smem = rank_table_in_smem(n);
+  const size_t smem = rank_smem_bytes(n, in_smem);
+  const int64_t items = (int64_t)args.n_vectors * args.R;
+  const int grid = (int)(items < kNumSMs ? items : kNumSMs);
+  const bool exact = triu_len(n) <= (1ll << 20);            // N^3 < 2^60: integer accumulation cannot overflow
+  ProfScope prof(fused ? F_RANK_FUSED : F_RANK, stream);
+  if (in_smem) {
+    if (fused) return exact ? launch_rank_variant<true, true, long long>(args, grid, smem, stream)
+                            : launch_rank_variant<true, true, double>(args, grid, smem, stream);
+    return exact ? launch_rank_variant<true, false, long long>(args, grid, smem, stream)
+                 : launch_rank_variant<true, false, double>(args, grid, smem, stream);
+  }
+  if (fused) return exact ? launch_rank_variant<false, true, long long>(args, grid, smem, stream)
+                          : launch_rank_variant<false, true, double>(args, grid, smem, stream);
+  return exact ? launch_rank_variant<false, false, long long>(args, grid, smem, stream)
+               : launch_rank_variant<false, false, double>(args, grid, smem, stream);
 }
 
 }  // namespace vr
@@ -397,7 +425,9 @@ extern "C" int vr_build_masks(const int32_t* idx, int R, int m, int n, uint32_t*
 
 extern "C" int64_t vr_dev_stride(int n) { return n >= 2 ? round_up(triu_len(n), 32) : 32; }
 
-extern "C" size_t vr_subsample_rank_workspace_bytes(int n, int R) { return (n >= 2 && R >= 1) ? rank_scratch_bytes(n, 1, R) + 256 : 256; }
+extern "C" size_t vr_subsample_rank_workspace_bytes(int n, int R) {
+  return (n >= 2 && R >= 1) ? count_scratch_bytes(n, 1, R) + 256 : 256;
+}
 
 extern "C" int vr_subsample_rank(const void* presorted, int n, const uint32_t* masks, int R, int32_t* dev,
                                  double* ss, int64_t* nkept, void* ws, size_t ws_bytes, vr_stream_t stream_) {
@@ -408,33 +438,41 @@ extern "C" int vr_subsample_rank(const void* presorted, int n, const uint32_t* m
     set_error("vr_subsample_rank: workspace %zu < %zu", ws_bytes, vr_subsample_rank_workspace_bytes(n, R));
     return VR_ERR_WORKSPACE;
   }
-  BlobList bl{};
-  bl.p[0] = presorted;
-  return launch_rank(bl, 1, n, masks, R, dev, ss, nkept, ws, ws_bytes, stream);
+  RankArgs args{};
+  args.blobs.p[0] = presorted;
+  CountScratch cs;
+  int st = launch_count(args.blobs, 1, n, masks, R, ws, ws_bytes, &cs, stream);
+  if (st != VR_OK) return st;
+  args.n_vectors = 1; args.n = n; args.masks = masks; args.W = vr_mask_words(n); args.R = R;
+  args.tables = cs.tables; args.table_base = 0; args.Gs = table_groups(n); args.seg_tot = cs.seg_tot;
+  args.dev_stride = vr_dev_stride(n); args.dev = dev; args.ss = ss; args.nkept = nkept;
+  return launch_rank(args, false, stream);
 }
 
 namespace {
 struct SpearmanPlan {
-  size_t fixed;     // scratch
-  size_t per_rep;   // dev + ss + nkept for one replicate over all vectors
+  size_t fixed;     // transposed masks + slack
+  size_t per_rep;   // tables + segment totals of every vector, dev + ss of one materialised group
 };
-SpearmanPlan spearman_plan(int n, int nV) {
+SpearmanPlan spearman_plan(int n, int nV, int n_mat) {
   SpearmanPlan p;
   p.fixed = arena_bytes((size_t)n * 2100, 4) + 8192;   // transposed masks of up to 65535 replicates + slack
-  p.per_rep = (size_t)nV * ((size_t)vr_dev_stride(n) * 4 + (size_t)table_groups(n) * 8 + 8 + 8 + 4 * kCountWarps);
+  p.per_rep = (size_t)nV * ((size_t)table_groups(n) * 8 + 4 * kCountWarps) +
+              (size_t)n_mat * ((size_t)vr_dev_stride(n) * 4 + 8);
   return p;
 }
 constexpr size_t kSoftCap = (size_t)40 << 30;  // default upper bound on one call's workspace
+inline int mat_group(int nA, int nB) { int m = nA <= nB ? nA : nB; return m < kFuseMax ? m : kFuseMax; }
 }  // namespace
 
 extern "C" size_t vr_bootstrap_spearman_workspace_bytes(int n, int nA, int nB, int R) {
   if (n < 2 || nA < 1 || nB < 1 || R < 1) return 4096;
-  SpearmanPlan p = spearman_plan(n, nA + nB);
+  SpearmanPlan p = spearman_plan(n, nA + nB, mat_group(nA, nB));
   size_t reps = (size_t)R;
   size_t cap = kSoftCap / p.per_rep;
   if (cap < 1) cap = 1;
   if (reps > cap) reps = cap;
-  return p.fixed + reps * p.per_rep + 3 * 256;
+  return p.fixed + reps * p.per_rep + 8 * 256;
 }
 
 extern "C" int vr_bootstrap_spearman(const void* const* A, int nA, const void* const* B, int nB, int n,
@@ -446,34 +484,52 @@ extern "C" int vr_bootstrap_spearman(const void* const* A, int nA, const void* c
   VR_REQUIRE(nA >= 1 && nB >= 1 && nA + nB <= kMaxVectors, "vr_bootstrap_spearman: nA=%d nB=%d (max %d in total)", nA, nB, kMaxVectors);
   VR_REQUIRE(R >= 1, "vr_bootstrap_spearman: R=%d", R);
   const int nV = nA + nB;
-  SpearmanPlan plan = spearman_plan(n, nV);
-  if (!ws || ws_bytes < plan.fixed + plan.per_rep + 3 * 256) {
-    set_error("vr_bootstrap_spearman: workspace %zu < minimum %zu", ws_bytes, plan.fixed + plan.per_rep + 3 * 256);
+  // The side with fewer vectors is materialised (in groups of <= kFuseMax); the other side is fused.
+  const bool mat_is_A = nA <= nB;
+  const int nM = mat_is_A ? nA : nB, nF = mat_is_A ? nB : nA;
+  const int group = mat_group(nA, nB);
+  SpearmanPlan plan = spearman_plan(n, nV, group);
+  if (!ws || ws_bytes < plan.fixed + plan.per_rep + 8 * 256) {
+    set_error("vr_bootstrap_spearman: workspace %zu < minimum %zu", ws_bytes, plan.fixed + plan.per_rep + 8 * 256);
     return VR_ERR_WORKSPACE;
   }
-  BlobList bl{};
-  for (int i = 0; i < nA; ++i) { VR_REQUIRE(A[i], "null blob"); bl.p[i] = A[i]; }
-  for (int i = 0; i < nB; ++i) { VR_REQUIRE(B[i], "null blob"); bl.p[nA + i] = B[i]; }
-  int64_t chunk = (int64_t)((ws_bytes - plan.fixed - 3 * 256) / plan.per_rep);
+  BlobList all{};   // materialised side first, fused side after
+  for (int i = 0; i < nM; ++i) { const void* p = mat_is_A ? A[i] : B[i]; VR_REQUIRE(p, "null blob"); all.p[i] = p; }
+  for (int i = 0; i < nF; ++i) { const void* p = mat_is_A ? B[i] : A[i]; VR_REQUIRE(p, "null blob"); all.p[nM + i] = p; }
+  int64_t chunk = (int64_t)((ws_bytes - plan.fixed - 8 * 256) / plan.per_rep);
   if (chunk > R) chunk = R;
-  if (chunk > 65535) chunk = 65535;  // grid.y limit of the dot kernel
+  if (chunk > 65535) chunk = 65535;
   Arena a(ws, ws_bytes);
-  const size_t scratch_bytes = rank_scratch_bytes(n, nV, chunk) + 256;
+  const size_t scratch_bytes = count_scratch_bytes(n, nV, chunk) + 256;
   void* scratch = a.take<char>(scratch_bytes);
-  double* ss = a.take<double>((size_t)nV * chunk);
-  int64_t* nkept = a.take<int64_t>((size_t)nV * chunk);
-  int32_t* dev = a.take<int32_t>((size_t)nV * chunk * vr_dev_stride(n));
+  double* ss = a.take<double>((size_t)group * chunk);
+  int32_t* dev = a.take<int32_t>((size_t)group * chunk * vr_dev_stride(n));
   if (!a.ok) { set_error("vr_bootstrap_spearman: internal workspace plan overflow"); return VR_ERR_WORKSPACE; }
   const int W = vr_mask_words(n);
-  const int tiles = ((nA + kDotTile - 1) / kDotTile) * ((nB + kDotTile - 1) / kDotTile);
   for (int64_t r0 = 0; r0 < R; r0 += chunk) {
     const int rc = (int)(R - r0 < chunk ? R - r0 : chunk);
-    int st = launch_rank(bl, nV, n, masks + (size_t)r0 * W, rc, dev, ss, nkept, scratch, scratch_bytes, stream);
+    const uint32_t* mk = masks + (size_t)r0 * W;
+    CountScratch cs;
+    int st = launch_count(all, nV, n, mk, rc, scratch, scratch_bytes, &cs, stream);
     if (st != VR_OK) return st;
-    dim3 grid(tiles, rc);
-    ProfScope prof(F_DOT, stream);
-    dot_kernel<<<grid, kDotThreads, 0, stream>>>(dev, vr_dev_stride(n), ss, nA, nB, rc, (int)r0, R, out);
-    VR_CHECK_LAUNCH();
+    for (int m0 = 0; m0 < nM; m0 += group) {
+      const int mg = nM - m0 < group ? nM - m0 : group;
+      RankArgs base{};
+      base.n = n; base.masks = mk; base.W = W; base.R = rc; base.tables = cs.tables; base.Gs = table_groups(n);
+      base.seg_tot = cs.seg_tot; base.dev_stride = vr_dev_stride(n);
+      RankArgs mat = base;          // materialise vectors [m0, m0 + mg)
+      for (int i = 0; i < mg; ++i) mat.blobs.p[i] = all.p[m0 + i];
+      mat.n_vectors = mg; mat.table_base = m0; mat.dev = dev; mat.ss = ss; mat.nkept = nullptr;
+      st = launch_rank(mat, false, stream);
+      if (st != VR_OK) return st;
+      RankArgs fu = base;           // every fused vector against this group
+      for (int i = 0; i < nF; ++i) fu.blobs.p[i] = all.p[nM + i];
+      fu.n_vectors = nF; fu.table_base = nM; fu.mat_dev = dev; fu.mat_ss = ss; fu.n_mat = mg;
+      fu.out = out; fu.out_nB = nB; fu.out_Rtot = R; fu.out_r0 = (int)r0;
+      fu.mat_is_A = mat_is_A ? 1 : 0; fu.mat_off = m0; fu.fused_off = 0;
+      st = launch_rank(fu, true, stream);
+      if (st != VR_OK) return st;
+    }
   }
   return VR_OK;
 }
