@@ -274,15 +274,16 @@ def run_ours(args):
     m = int(n * 0.9)
     N_sub = m * (m - 1) // 2
     roofline = None
-    if dom in ("rank", "rank_fused", "kept"):
-        # one launch of this family ranks (or counts) a side's vectors for all B+1 masks
-        vectors = {"rank": min(nA, nB, 8), "rank_fused": max(nA, nB), "kept": nA + nB}[dom]
+    if dom in ("rank", "rank_fused", "kept", "dot"):
+        # one launch of this family ranks (or counts, or reads) a set of vectors for all B+1 masks
+        fused = prof["rank_fused"]["scopes"] > 0
+        vectors = {"rank": min(nA, nB, 8) if fused else nA + nB, "rank_fused": max(nA, nB), "kept": nA + nB, "dot": nA + nB}[dom]
         per_launch_ms = prof[dom]["ms"] / max(1, prof[dom]["scopes"])
         rankings_per_launch = vectors * (B + 1)
         # 8*N_sub bytes per replicate comparison = 4*N_sub per ranked vector
         alg_bytes = rankings_per_launch * 4.0 * N_sub
         achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
-        roofline = {"kernel": {"rank": "rank_kernel<materialise>", "rank_fused": "rank_kernel<fused dot>", "kept": "count_kernel"}[dom],
+        roofline = {"kernel": {"rank": "rank_kernel<materialise>", "rank_fused": "rank_kernel<fused dot>", "kept": "count_kernel", "dot": "dot_kernel"}[dom],
                     "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                     "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": per_launch_ms,

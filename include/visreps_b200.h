@@ -107,6 +107,11 @@ int vr_presort_triu_batch_f32(const float* const* rdms_host, int count, int n, i
  * row-major.  masks is (R, vr_mask_words(n)) uint32.  Index order inside a draw does not
  * change the multiset of sub-RDM pairs, so it does not change any score.
  * ---------------------------------------------------------------------------------- */
+/* HOST function (no device work): B draws of `RandomState.choice(n, m, replace=False)` from numpy's
+ * legacy MT19937 stream, bit-identical to the reference's Python loop.  mt_key (624 words) and
+ * mt_pos are RandomState.get_state()[1:3], updated in place so the generator can be handed back
+ * with set_state().  out is a HOST (B, m) int32 array, draw order preserved. */
+int vr_host_draw_subsamples(uint32_t* mt_key, int* mt_pos, int n, int m, int B, int32_t* out);
 int vr_mask_words(int n);
 int vr_build_masks(const int32_t* idx, int R, int m, int n, uint32_t* masks, vr_stream_t stream);
 

@@ -237,6 +237,34 @@ def test_bootstrap_against_oracle_loop_and_grouping(dev):
     assert len(s) == 1 and lo == hi == s[0]
 
 
+def test_large_n_global_table_path(dev):
+    """n = 1500 (N = 1,124,250 pairs): the count tables no longer fit shared memory and the sums leave the
+    exact-int64 regime, so the global-table / fp64-accumulator variants of the kernels run."""
+    rs = np.random.RandomState(31)
+    n = 1500
+    z = rs.standard_normal((n, 24)).astype(np.float32)
+    x = torch.from_numpy(np.maximum(z @ rs.standard_normal((24, 200)).astype(np.float32) + rs.standard_normal((n, 200)).astype(np.float32), 0))
+    y = torch.from_numpy((z @ rs.standard_normal((24, 90)) + 2 * rs.standard_normal((n, 90))).astype(np.float32))
+    a, b = vb.compute_rdm(x.to(dev)), vb.compute_rdm(y.to(dev))
+    assert float((a.cpu() - orc.rdm(x)).abs().max()) <= RDM_TOL
+    idx = vrsa.draw_index_sets(n, 2, 42)
+    res = vb.bootstrap_rdm_correlation_grouped([a], [b], "spearman", index_sets=idx)
+    want = orc.bootstrap_compare_with_indices(a.cpu(), b.cpu(), "spearman", idx)
+    np.testing.assert_allclose(res["scores"][0, 0], want, atol=SCORE_TOL, rtol=0)
+    assert abs(res["point"][0, 0] - orc.rdm_compare(a.cpu(), b.cpu(), correlation="Spearman")) <= SCORE_TOL
+    # ranks stay bit-exact on this path too
+    masks = vrsa.build_masks(idx[:1], n, dev, with_full=True)
+    devv, ss, nk = vrsa.subsample_rank(a, masks)
+    v = orc.triu_vector(a)
+    iu = np.triu_indices(n, 1)
+    keep = np.isin(np.arange(n), idx[0])
+    kp = keep[iu[0]] & keep[iu[1]]
+    got = devv[1].cpu().numpy().astype(np.int64)
+    np.testing.assert_array_equal(got[kp] + (int(kp.sum()) + 1), orc.rank2x(v[kp]))
+    pe = vb.compute_rdm_correlation(a, b, correlation="Pearson")
+    assert abs(pe - orc.rdm_compare(a.cpu(), b.cpu(), correlation="Pearson")) <= SCORE_TOL
+
+
 def test_grouped_with_more_than_one_materialised_group(dev):
     """10 model x 9 neural RDMs: the smaller side is materialised in groups of 8, so two groups."""
     rs = np.random.RandomState(21)

@@ -37,6 +37,7 @@ SIGNATURES = {
     "vr_presort_triu_f32": (_i, [_vp, _i, _i64, _vp, _vp, _sz, _vp]),
     "vr_presort_batch_workspace_bytes": (_sz, [_i, _i]),
     "vr_presort_triu_batch_f32": (_i, [_vp, _i, _i, _i64, _vp, _vp, _sz, _vp]),
+    "vr_host_draw_subsamples": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "vr_mask_words": (_i, [_i]),
     "vr_build_masks": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "vr_dev_stride": (_i64, [_i]),

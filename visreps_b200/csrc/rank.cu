@@ -23,6 +23,7 @@
 //   Reads and the dev write are coalesced; the only random accesses hit the table.
 //   The side of the comparison with fewer vectors is materialised (dev vectors in HBM); the items of
 //   the other side multiply their dev values with those vectors on the fly (fused) and emit rho.
+#include <cstdlib>
 #include <type_traits>
 #include "common.cuh"
 
@@ -62,7 +63,19 @@ __global__ void transpose_masks_kernel(const uint32_t* __restrict__ masks, int R
   maskT[(int64_t)batch * n + i] = w;
 }
 
+// pairbits[r][w]: bit b = canonical pair 32w+b has both stimuli in mask r (0 beyond N).
+// One thread per word; the row is decoded once and then walked.
+__global__ void __launch_bounds__(256)
+pair_mask_kernel(const uint32_t* __restrict__ masks, int R, int n, int W, uint32_t words,
+                 uint32_t* __restrict__ pairbits);
+
 __device__ __forceinline__ uint32_t low_mask(uint32_t bit) { return (1u << bit) - 1u; }  // bit in [0,31]
+// x << k with PTX semantics: k >= 32 gives 0 (C++ leaves that undefined).
+__device__ __forceinline__ uint32_t shl_clamp(uint32_t x, uint32_t k) {
+  uint32_t r;
+  asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(k));
+  return r;
+}
 
 // Row of canonical pair p: largest i with i(2n-i-1)/2 <= p.
 __device__ __forceinline__ uint32_t triu_row(uint32_t p, uint32_t n) {
@@ -73,6 +86,29 @@ __device__ __forceinline__ uint32_t triu_row(uint32_t p, uint32_t n) {
   while (i > 0 && (uint32_t)i * (2u * n - (uint32_t)i - 1u) / 2u > p) --i;
   while ((uint32_t)(i + 1) * (2u * n - (uint32_t)(i + 1) - 1u) / 2u <= p) ++i;
   return (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(256)
+pair_mask_kernel(const uint32_t* __restrict__ masks, int R, int n, int W, uint32_t words,
+                 uint32_t* __restrict__ pairbits) {
+  extern __shared__ uint32_t s_m[];
+  const int r = blockIdx.y;
+  for (int w = threadIdx.x; w < W; w += 256) s_m[w] = masks[(int64_t)r * W + w];
+  __syncthreads();
+  const uint32_t N = (uint32_t)triu_len(n);
+  for (uint32_t w = blockIdx.x * 256u + threadIdx.x; w < words; w += gridDim.x * 256u) {
+    uint32_t p = w * 32u, bits = 0;
+    if (p < N) {
+      uint32_t i = triu_row(p, (uint32_t)n);
+      uint32_t j = p - i * (2u * n - i - 1u) / 2u + i + 1u;
+      uint32_t ki = (s_m[i >> 5] >> (i & 31u)) & 1u;
+      for (uint32_t b = 0; b < 32u && p + b < N; ++b) {
+        bits |= (ki & (s_m[j >> 5] >> (j & 31u)) & 1u) << b;
+        if (++j == (uint32_t)n) { ++i; j = i + 1u; ki = (s_m[min(i, (uint32_t)n - 1u) >> 5] >> (i & 31u)) & 1u; }
+      }
+    }
+    pairbits[(int64_t)r * words + w] = bits;
+  }
 }
 
 // Transpose a 32x32 bit matrix held one row per lane (row = lane, column = bit).
@@ -149,8 +185,7 @@ struct RankArgs {
   BlobList blobs;            // the vectors ranked by this launch
   int n_vectors;
   int n;
-  const uint32_t* masks;     // [R][W]
-  int W;
+  const uint32_t* pairbits;  // [R][dev_stride/32]: kept bits of the canonical pairs
   int R;
   uint2* tables;             // [table_index(v)][R][Gs]
   int table_base;            // index of vector 0 of this launch in the table / seg_tot arrays
@@ -178,14 +213,13 @@ template <bool kSmemTable, bool kFused, typename Acc>
 __global__ void __launch_bounds__(kRankThreads, 1)
 rank_kernel(const __grid_constant__ RankArgs A) {
   extern __shared__ __align__(16) uint32_t smem[];
-  uint32_t* s_mask = smem;
-  uint2* s_table = reinterpret_cast<uint2*>(smem + ((A.W + 3) & ~3));
+  uint2* s_table = reinterpret_cast<uint2*>(smem);
   __shared__ double s_red[kRankWarps][kFuseMax + 1];
   __shared__ uint32_t s_base[kCountWarps + 1];
 
   const unsigned lane = lane_id();
   const int warp = threadIdx.x >> 5;
-  const int n = A.n, R = A.R, W = A.W;
+  const int n = A.n, R = A.R;
   const uint32_t N = (uint32_t)triu_len(n);
   const uint32_t G = (N + 31u) / 32u;
   const uint32_t Gs = A.Gs;
@@ -203,7 +237,6 @@ rank_kernel(const __grid_constant__ RankArgs A) {
     PresortView blob = presort_view(const_cast<void*>(A.blobs.p[v]), n);
     const int64_t tix = (int64_t)(A.table_base + v) * R + r;
     uint2* __restrict__ g_table = A.tables + tix * Gs;
-    for (int w = threadIdx.x; w < W; w += kRankThreads) s_mask[w] = A.masks[(int64_t)r * W + w];
     if (threadIdx.x == 0) {                                  // exclusive prefix of the segment totals
       uint32_t run = 0;
       for (int w = 0; w < kCountWarps; ++w) { s_base[w] = run; run += A.seg_tot[tix * kCountWarps + w]; }
@@ -228,48 +261,73 @@ rank_kernel(const __grid_constant__ RankArgs A) {
     const int32_t* __restrict__ mat = kFused ? A.mat_dev + (int64_t)r * dev_stride : nullptr;
     const int64_t mat_step = (int64_t)R * dev_stride;        // between materialised vectors
     const uint32_t* __restrict__ runs = blob.runs;
+    const uint32_t* __restrict__ keptw = A.pairbits + (int64_t)r * (dev_stride >> 5);
     Acc acc_ss = 0;
     Acc acc[kFuseMax];
 #pragma unroll
     for (int a = 0; a < kFuseMax; ++a) acc[a] = 0;
 
-    for (uint32_t p0 = threadIdx.x * 4u; p0 < (uint32_t)dev_stride; p0 += kRankThreads * 4u) {
+    // software pipeline: the run words and kept bits of the NEXT step are in flight while this one is ranked
+    const uint32_t esc_word = esc << sbits;                  // a run word >= esc_word carries the escape code
+    uint32_t p0 = threadIdx.x * 4u;
+    uint4 q_cur = make_uint4(0u, 0u, 0u, 0u);
+    uint32_t kw_cur = 0u;
+    if (p0 < N) { q_cur = __ldg(reinterpret_cast<const uint4*>(runs + p0)); kw_cur = __ldg(keptw + (p0 >> 5)); }
+    for (; p0 < (uint32_t)dev_stride; p0 += kRankThreads * 4u) {
       int32_t d4[4] = {0, 0, 0, 0};
+      int4 m4[4];
+      if (kFused && p0 < N) {   // first batch of materialised vectors: issued before the ranking work hides their latency
+#pragma unroll
+        for (int a = 0; a < 4; ++a) m4[a] = __ldg(reinterpret_cast<const int4*>(mat + min(a, A.n_mat - 1) * mat_step + p0));
+      }
+      const uint4 q = q_cur;
+      const uint32_t kw = kw_cur >> (p0 & 31u);              // 4 kept bits (p0 is a multiple of 4)
+      {
+        const uint32_t pn = p0 + kRankThreads * 4u;
+        if (pn < N) { q_cur = __ldg(reinterpret_cast<const uint4*>(runs + pn)); kw_cur = __ldg(keptw + (pn >> 5)); }
+      }
       if (p0 < N) {
-        const uint4 q = __ldg(reinterpret_cast<const uint4*>(runs + p0));
         const uint32_t rw[4] = {q.x, q.y, q.z, q.w};
-        uint32_t i = triu_row(p0, (uint32_t)n);
-        uint32_t j = p0 - i * (2u * n - i - 1u) / 2u + i + 1u;
-        uint32_t ki = (s_mask[i >> 5] >> (i & 31u)) & 1u;
+        uint32_t s4[4], e4[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { s4[e] = rw[e] & smask; e4[e] = s4[e] + (rw[e] >> sbits) + 1u; }
+        if (max(max(rw[0], rw[1]), max(rw[2], rw[3])) >= esc_word) {   // rare: a run longer than the packed field
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (rw[e] >= esc_word) {
+              const uint32_t g = s4[e] >> 5, l = s4[e] & 31u;
+              const uint32_t above = l == 31u ? 0u : (__ldg(blob.head_bits + g) >> (l + 1u));
+              e4[e] = above ? s4[e] + (uint32_t)__ffs(above) : __ldg(blob.next_head + g + 1);
+            }
+          }
+        }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const uint32_t s = rw[e] & smask;
-          const uint32_t f = rw[e] >> sbits;
-          uint32_t end = s + f + 1u;
-          if (f == esc) {                                   // long run: find its end from the head tables
-            const uint32_t g = s >> 5, l = s & 31u;
-            const uint32_t above = l == 31u ? 0u : (__ldg(blob.head_bits + g) >> (l + 1u));
-            end = above ? s + (uint32_t)__ffs(above) : __ldg(blob.next_head + g + 1);
-          }
-          const uint2 ts = table[s >> 5];
-          const uint2 te = table[end >> 5];
-          const uint32_t lo = ts.y + __popc(ts.x & low_mask(s & 31u));
-          const uint32_t hi = te.y + __popc(te.x & low_mask(end & 31u));
-          const uint32_t kept = ki & (s_mask[j >> 5] >> (j & 31u)) & (p0 + e < N ? 1u : 0u);
-          const int32_t d = kept ? (int32_t)(lo + hi) - (int32_t)Ns : 0;
+          const uint32_t gs = s4[e] >> 5, ge = e4[e] >> 5;
+          const uint2 ts = table[gs];
+          uint2 te = ts;
+          if (ge != gs) te = table[ge];                      // ~5 % of pairs: the run leaves the 32-group
+          // popc of the low (x & 31) bits: shifting left by 32 - (x & 31) drops the others (PTX shl clamps at 32)
+          const uint32_t lo = ts.y + __popc(shl_clamp(ts.x, 32u - (s4[e] & 31u)));
+          const uint32_t hi = te.y + __popc(shl_clamp(te.x, 32u - (e4[e] & 31u)));
+          const int32_t d = ((kw >> e) & 1u) ? (int32_t)(lo + hi) - (int32_t)Ns : 0;
           d4[e] = d;
           acc_ss += (Acc)d * (Acc)d;
-          if (++j == (uint32_t)n) { ++i; j = i + 1u; ki = (s_mask[min(i, (uint32_t)n - 1u) >> 5] >> (i & 31u)) & 1u; }
         }
       }
       if (kFused) {
         if (p0 < N) {
 #pragma unroll
-          for (int a = 0; a < kFuseMax; ++a) {
-            if (a < A.n_mat) {
-              const int4 m4 = __ldg(reinterpret_cast<const int4*>(mat + a * mat_step + p0));
-              acc[a] += (Acc)d4[0] * (Acc)m4.x + (Acc)d4[1] * (Acc)m4.y + (Acc)d4[2] * (Acc)m4.z + (Acc)d4[3] * (Acc)m4.w;
-            }
+          for (int a = 0; a < 4; ++a)
+            if (a < A.n_mat)
+              acc[a] += (Acc)d4[0] * (Acc)m4[a].x + (Acc)d4[1] * (Acc)m4[a].y + (Acc)d4[2] * (Acc)m4[a].z + (Acc)d4[3] * (Acc)m4[a].w;
+          if (A.n_mat > 4) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) m4[a] = __ldg(reinterpret_cast<const int4*>(mat + min(a + 4, A.n_mat - 1) * mat_step + p0));
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+              if (a + 4 < A.n_mat)
+                acc[a + 4] += (Acc)d4[0] * (Acc)m4[a].x + (Acc)d4[1] * (Acc)m4[a].y + (Acc)d4[2] * (Acc)m4[a].z + (Acc)d4[3] * (Acc)m4[a].w;
           }
         }
       } else {
@@ -322,18 +380,102 @@ rank_kernel(const __grid_constant__ RankArgs A) {
   }
 }
 
+// out[a][b][r] = sum_p devA[a][r][p] * devB[b][r][p] / sqrt(ssA[a][r] * ssB[b][r])
+constexpr int kDotThreads = 256;
+constexpr int kDotTile = 4;
+__global__ void __launch_bounds__(kDotThreads)
+dot_kernel(const int32_t* __restrict__ dev, int64_t dev_stride, const double* __restrict__ ss, int nA, int nB,
+           int R, int r0, int Rtot, double* __restrict__ out, int first_is_model, int out_nB) {
+  __shared__ long long s_part[kDotThreads / 32][kDotTile * kDotTile];
+  __shared__ double s_partd[kDotThreads / 32][kDotTile * kDotTile];
+  const int tilesB = (nB + kDotTile - 1) / kDotTile;
+  const int ta = blockIdx.x / tilesB, tb = blockIdx.x % tilesB;
+  const int r = blockIdx.y;
+  const int a0 = ta * kDotTile, b0 = tb * kDotTile;
+  const int4* pa[kDotTile];
+  const int4* pb[kDotTile];
+#pragma unroll
+  for (int k = 0; k < kDotTile; ++k) {
+    const int a = min(a0 + k, nA - 1), b = min(b0 + k, nB - 1);
+    pa[k] = reinterpret_cast<const int4*>(dev + ((int64_t)a * R + r) * dev_stride);
+    pb[k] = reinterpret_cast<const int4*>(dev + ((int64_t)(nA + b) * R + r) * dev_stride);
+  }
+  const int64_t n4 = dev_stride / 4;
+  long long acc[kDotTile][kDotTile];
+  double accd[kDotTile][kDotTile];
+#pragma unroll
+  for (int x = 0; x < kDotTile; ++x)
+#pragma unroll
+    for (int y = 0; y < kDotTile; ++y) { acc[x][y] = 0; accd[x][y] = 0.0; }
+
+  int since_flush = 0;
+  // |dev| <= N (= dev_stride up to padding): one step adds < 4 N^2 per accumulator
+  const int flush_every = (int)min(256ull, (1ull << 62) / (4ull * (unsigned long long)dev_stride * dev_stride + 1ull) + 1ull);
+  for (int64_t q = threadIdx.x; q < n4; q += kDotThreads) {
+    int4 va[kDotTile], vb[kDotTile];
+#pragma unroll
+    for (int k = 0; k < kDotTile; ++k) { va[k] = __ldg(pa[k] + q); vb[k] = __ldg(pb[k] + q); }
+#pragma unroll
+    for (int x = 0; x < kDotTile; ++x)
+#pragma unroll
+      for (int y = 0; y < kDotTile; ++y) {
+        acc[x][y] += (long long)va[x].x * vb[y].x + (long long)va[x].y * vb[y].y +
+                     (long long)va[x].z * vb[y].z + (long long)va[x].w * vb[y].w;
+      }
+    if (++since_flush >= flush_every) {
+      since_flush = 0;
+#pragma unroll
+      for (int x = 0; x < kDotTile; ++x)
+#pragma unroll
+        for (int y = 0; y < kDotTile; ++y) { accd[x][y] += (double)acc[x][y]; acc[x][y] = 0; }
+    }
+  }
+  const int warp = threadIdx.x >> 5;
+  const unsigned lane = lane_id();
+  // Up to 2^20 pairs the whole sum stays below 2^60 and is carried exactly in int64; beyond
+  // that the per-thread integers are folded into fp64 before any cross-thread addition.
+  const bool exact = dev_stride <= (1ll << 20);
+#pragma unroll
+  for (int x = 0; x < kDotTile; ++x)
+#pragma unroll
+    for (int y = 0; y < kDotTile; ++y) {
+      if (!exact) { accd[x][y] += (double)acc[x][y]; acc[x][y] = 0; }
+      long long s = warp_sum_ll(acc[x][y]);
+      double sd = warp_sum(accd[x][y]);
+      if (lane == 0) { s_part[warp][x * kDotTile + y] = s; s_partd[warp][x * kDotTile + y] = sd; }
+    }
+  __syncthreads();
+  if (threadIdx.x < kDotTile * kDotTile) {
+    const int x = threadIdx.x / kDotTile, y = threadIdx.x % kDotTile;
+    double tot = 0.0;
+    long long ti = 0;
+    for (int w = 0; w < kDotThreads / 32; ++w) { ti += s_part[w][threadIdx.x]; tot += s_partd[w][threadIdx.x]; }
+    tot += (double)ti;
+    const int a = a0 + x, b = b0 + y;
+    if (a < nA && b < nB) {
+      const double sa = ss[(int64_t)a * R + r], sb = ss[(int64_t)(nA + b) * R + r];
+      double rho = tot / (sqrt(sa) * sqrt(sb));
+      if (!(sa > 0.0) || !(sb > 0.0)) rho = __longlong_as_double(0x7ff8000000000000LL);
+      // the first nA vectors of `dev` are the model side when first_is_model, else the neural side
+      const int ia = first_is_model ? a : b, ib = first_is_model ? b : a;
+      out[((int64_t)ia * out_nB + ib) * Rtot + r0 + r] = rho;
+    }
+  }
+}
+
+
 static inline uint32_t table_groups(int n) { return (uint32_t)round_up(presort_groups(n) + 1, 32) + 32u; }
 static inline bool rank_table_in_smem(int n) { return (size_t)table_groups(n) * 8 <= kRankSmemTableMax; }
 static inline size_t rank_smem_bytes(int n, bool smem_table) {
-  const size_t mask_bytes = (size_t)round_up(vr_mask_words(n), 4) * 4;
-  return mask_bytes + (smem_table ? (size_t)table_groups(n) * 8 : 0);
+  return smem_table ? (size_t)table_groups(n) * 8 : 0;
 }
 // scratch shared by the launches of one replicate chunk: transposed masks + count tables + segment totals
 static inline size_t count_scratch_bytes(int n, int nV, int64_t R) {
   return arena_bytes((size_t)((R + 31) / 32) * n, 4) + arena_bytes((size_t)nV * R * table_groups(n), 8) +
-         arena_bytes((size_t)nV * R * kCountWarps, 4);
+         arena_bytes((size_t)nV * R * kCountWarps, 4) + arena_bytes((size_t)R * (vr_dev_stride(n) / 32), 4);
 }
 struct CountScratch {
+  uint32_t* pairbits;
   uint32_t* maskT;
   uint2* tables;
   uint32_t* seg_tot;
@@ -349,8 +491,15 @@ static int launch_count(const BlobList& blobs, int nV, int n, const uint32_t* ma
   cs->maskT = a.take<uint32_t>((size_t)batches * n);
   cs->tables = a.take<uint2>((size_t)nV * R * Gs);
   cs->seg_tot = a.take<uint32_t>((size_t)nV * R * kCountWarps);
+  const uint32_t words = (uint32_t)(vr_dev_stride(n) / 32);
+  cs->pairbits = a.take<uint32_t>((size_t)R * words);
   if (!a.ok) { set_error("rank scratch too small"); return VR_ERR_WORKSPACE; }
   ProfScope prof(F_KEPT, stream);
+  {
+    dim3 grid((words + 255) / 256 < 64 ? (words + 255) / 256 : 64, R);
+    pair_mask_kernel<<<grid, 256, (size_t)W * 4, stream>>>(masks, R, n, W, words, cs->pairbits);
+    VR_CHECK_LAUNCH();
+  }
   {
     dim3 grid((n + 255) / 256, batches);
     transpose_masks_kernel<<<grid, 256, 0, stream>>>(masks, R, n, W, cs->maskT);
@@ -443,13 +592,19 @@ extern "C" int vr_subsample_rank(const void* presorted, int n, const uint32_t* m
   CountScratch cs;
   int st = launch_count(args.blobs, 1, n, masks, R, ws, ws_bytes, &cs, stream);
   if (st != VR_OK) return st;
-  args.n_vectors = 1; args.n = n; args.masks = masks; args.W = vr_mask_words(n); args.R = R;
+  args.n_vectors = 1; args.n = n; args.pairbits = cs.pairbits; args.R = R;
   args.tables = cs.tables; args.table_base = 0; args.Gs = table_groups(n); args.seg_tot = cs.seg_tot;
   args.dev_stride = vr_dev_stride(n); args.dev = dev; args.ss = ss; args.nkept = nkept;
   return launch_rank(args, false, stream);
 }
 
 namespace {
+// VR_SPEARMAN_FUSED=1: the larger side multiplies on the fly (no dev vectors for it, no dot kernel).
+// Default: both sides are materialised and dot_kernel combines them.
+inline bool fused_mode() {
+  static const bool f = [] { const char* e = getenv("VR_SPEARMAN_FUSED"); return e && e[0] == '1'; }();
+  return f;
+}
 struct SpearmanPlan {
   size_t fixed;     // transposed masks + slack
   size_t per_rep;   // tables + segment totals of every vector, dev + ss of one materialised group
@@ -458,7 +613,7 @@ SpearmanPlan spearman_plan(int n, int nV, int n_mat) {
   SpearmanPlan p;
   p.fixed = arena_bytes((size_t)n * 2100, 4) + 8192;   // transposed masks of up to 65535 replicates + slack
   p.per_rep = (size_t)nV * ((size_t)table_groups(n) * 8 + 4 * kCountWarps) +
-              (size_t)n_mat * ((size_t)vr_dev_stride(n) * 4 + 8);
+              (size_t)(fused_mode() ? n_mat : nV) * ((size_t)vr_dev_stride(n) * 4 + 8) + (size_t)vr_dev_stride(n) / 8;
   return p;
 }
 constexpr size_t kSoftCap = (size_t)40 << 30;  // default upper bound on one call's workspace
@@ -502,8 +657,9 @@ extern "C" int vr_bootstrap_spearman(const void* const* A, int nA, const void* c
   Arena a(ws, ws_bytes);
   const size_t scratch_bytes = count_scratch_bytes(n, nV, chunk) + 256;
   void* scratch = a.take<char>(scratch_bytes);
-  double* ss = a.take<double>((size_t)group * chunk);
-  int32_t* dev = a.take<int32_t>((size_t)group * chunk * vr_dev_stride(n));
+  const int n_dev = fused_mode() ? group : nV;
+  double* ss = a.take<double>((size_t)n_dev * chunk);
+  int32_t* dev = a.take<int32_t>((size_t)n_dev * chunk * vr_dev_stride(n));
   if (!a.ok) { set_error("vr_bootstrap_spearman: internal workspace plan overflow"); return VR_ERR_WORKSPACE; }
   const int W = vr_mask_words(n);
   for (int64_t r0 = 0; r0 < R; r0 += chunk) {
@@ -512,10 +668,29 @@ extern "C" int vr_bootstrap_spearman(const void* const* A, int nA, const void* c
     CountScratch cs;
     int st = launch_count(all, nV, n, mk, rc, scratch, scratch_bytes, &cs, stream);
     if (st != VR_OK) return st;
+    if (!fused_mode()) {
+      // materialise every vector (model side first, as laid out in `all` when mat_is_A, else neural first)
+      RankArgs mat{};
+      mat.n = n; mat.pairbits = cs.pairbits; mat.R = rc; mat.tables = cs.tables; mat.Gs = table_groups(n);
+      mat.seg_tot = cs.seg_tot; mat.dev_stride = vr_dev_stride(n);
+      for (int i = 0; i < nV; ++i) mat.blobs.p[i] = all.p[i];
+      mat.n_vectors = nV; mat.table_base = 0; mat.dev = dev; mat.ss = ss; mat.nkept = nullptr;
+      st = launch_rank(mat, false, stream);
+      if (st != VR_OK) return st;
+      // dot_kernel expects the model vectors first: when the neural side was laid out first, swap the roles
+      // and transpose on output by calling it with (nM = rows) and writing through a strided view.
+      const int tiles = ((nM + kDotTile - 1) / kDotTile) * ((nF + kDotTile - 1) / kDotTile);
+      dim3 grid(tiles, rc);
+      ProfScope prof(F_DOT, stream);
+      dot_kernel<<<grid, kDotThreads, 0, stream>>>(dev, vr_dev_stride(n), ss, nM, nF, rc, (int)r0, R, out,
+                                                   mat_is_A ? 1 : 0, nB);
+      VR_CHECK_LAUNCH();
+      continue;
+    }
     for (int m0 = 0; m0 < nM; m0 += group) {
       const int mg = nM - m0 < group ? nM - m0 : group;
       RankArgs base{};
-      base.n = n; base.masks = mk; base.W = W; base.R = rc; base.tables = cs.tables; base.Gs = table_groups(n);
+      base.n = n; base.pairbits = cs.pairbits; base.R = rc; base.tables = cs.tables; base.Gs = table_groups(n);
       base.seg_tot = cs.seg_tot; base.dev_stride = vr_dev_stride(n);
       RankArgs mat = base;          // materialise vectors [m0, m0 + mg)
       for (int i = 0; i < mg; ++i) mat.blobs.p[i] = all.p[m0 + i];

@@ -132,12 +132,26 @@ def build_masks(index_sets: Optional[np.ndarray], n: int, device: torch.device, 
 
 def draw_index_sets(n: int, n_bootstrap: int, seed: int = 42, rng: Optional[np.random.RandomState] = None) -> np.ndarray:
     """Host RNG stream of the reference bootstrap: B x int(0.9 n) draws without replacement,
-    in draw order (evals.py:356-364; rsa.py:249-251)."""
+    in draw order (evals.py:356-364; rsa.py:249-251).
+
+    The B `rng.choice(n, m, replace=False)` calls are replayed by the library's host routine on the
+    generator's own MT19937 state (bit-identical, ~20x faster than the Python loop); `rng` is left in
+    exactly the state the reference's loop would leave it in."""
     rng = np.random.RandomState(seed) if rng is None else rng
     m = int(n * SUBSAMPLE_FRACTION)
     out = np.empty((n_bootstrap, m), dtype=np.int32)
-    for b in range(n_bootstrap):
-        out[b] = rng.choice(n, size=m, replace=False)
+    if n_bootstrap == 0:
+        return out
+    state = rng.get_state()
+    if state[0] != "MT19937" or n < 1:
+        for b in range(n_bootstrap):
+            out[b] = rng.choice(n, size=m, replace=False)
+        return out
+    key = np.ascontiguousarray(state[1], dtype=np.uint32).copy()
+    pos = C.c_int(int(state[2]))
+    _lib.check(_lib.load().vr_host_draw_subsamples(key.ctypes.data, C.byref(pos), n, m, n_bootstrap, out.ctypes.data),
+               "vr_host_draw_subsamples")
+    rng.set_state((state[0], key, pos.value, state[3], state[4]))
     return out
 
 
