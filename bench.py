@@ -37,7 +37,7 @@ UNIT = "replicates/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=1000, help="stimuli")
@@ -221,9 +221,13 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0]), float(t[1]), prof, launches, last
 
+    # the sampler is started before the warm-up so that nvidia-smi's own start-up (driver init, ~1 s of host
+    # and driver-lock contention) is over before the timed region; it then only polls every 100 ms
+    clocks = ClockSampler(local_rank) if (rank == 0 and not os.environ.get('VR_BENCH_NO_CLOCKS')) else None
+    if clocks is not None:
+        time.sleep(1.5)
     for _ in range(args.warmup):
         step_device()
-    clocks = ClockSampler(local_rank) if rank == 0 else None
     ms_dev, wall_dev, prof, launches, res = timed(step_device, args.steps, profile=True)
     clock_info = clocks.stop() if clocks else None
 

@@ -131,6 +131,31 @@ int vr_subsample_rank(const void* presorted, int n, const uint32_t* masks, int R
                       void* ws, size_t ws_bytes, vr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
+ * Staged form of the same computation, for callers that pipeline host->device copies with
+ * the ranking (visreps_b200.rsa_grouped does): all (layer, ROI) pairs of a job share the R masks
+ * (evals.py:356 re-seeds RandomState(42) per pair), so everything derived from the masks alone is
+ * built once (the rank context) and each RDM is ranked as soon as it exists.
+ *   vr_rank_context_build  masks (R, vr_mask_words(n)) -> opaque context of vr_rank_context_bytes(n, R)
+ *   vr_rank_materialise    dev (nV, R, vr_dev_stride(n)) int32 and ss (nV, R) fp64 of nV presorted RDMs
+ *                          (nkept (nV, R) is nullable)
+ *   vr_rank_fused          ranks nF presorted RDMs and, without writing their dev vectors, correlates them
+ *                          with nM <= vr_rank_fuse_max() materialised ones:
+ *                          out[f * out_stride_fused + m * out_stride_mat + r] = Spearman rho (fp64)
+ * blobs_host are HOST arrays of device pointers; ws needs vr_rank_workspace_bytes(n, nV or nF, R).
+ * ---------------------------------------------------------------------------------- */
+size_t vr_rank_context_bytes(int n, int R);
+int vr_rank_context_build(const uint32_t* masks, int n, int R, void* ctx, size_t ctx_bytes, vr_stream_t stream);
+size_t vr_rank_workspace_bytes(int n, int n_vectors, int R);
+int vr_rank_fuse_max(void);
+int vr_rank_materialise(const void* const* blobs_host, int nV, int n, const void* ctx, int R,
+                        int32_t* dev, double* ss, int64_t* nkept,
+                        void* ws, size_t ws_bytes, vr_stream_t stream);
+int vr_rank_fused(const void* const* blobs_host, int nF, int n, const void* ctx, int R,
+                  const int32_t* mat_dev, const double* mat_ss, int nM,
+                  double* out, int64_t out_stride_fused, int64_t out_stride_mat,
+                  void* ws, size_t ws_bytes, vr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
  * Grouped bootstrap comparison: replaces the loop at evals.py:361-369 (and its copies at
  * evals.py:512-520, rsa.py:248-256, run_reconstruction.py:148-154) for nA model RDMs x
  * nB neural RDMs x R masks in one call.  A mask with all n bits set gives the point

@@ -285,6 +285,39 @@ def test_grouped_with_more_than_one_materialised_group(dev):
     np.testing.assert_allclose(res_t["scores"], np.transpose(res["scores"], (1, 0, 2)), atol=1e-15, rtol=0)
 
 
+def test_rsa_grouped_pipeline_host_and_device_inputs(dev):
+    """rsa_grouped = the scoring block of _eval_rsa for all (layer, ROI) pairs; host inputs take the
+    copy/compute-overlapped path, device inputs the batched one: identical results, both equal to the oracle loop."""
+    rs = np.random.RandomState(17)
+    n, B = 96, 9
+    z = rs.standard_normal((n, 10)).astype(np.float32)
+    feats = [torch.from_numpy(np.maximum(z @ rs.standard_normal((10, d)).astype(np.float32) + rs.standard_normal((n, d)).astype(np.float32), 0))
+             for d in (300, 40, 1200)]
+    feats[1] = feats[1].reshape(n, 2, 4, 5)                      # >2-D activations are flattened (evals.py:321)
+    neur = [torch.from_numpy((z @ rs.standard_normal((10, v)) + rs.standard_normal((n, v))).astype(np.float32)) for v in (25, 60, 33, 80)]
+    host = vb.rsa_grouped([f.pin_memory() for f in feats], neur, "spearman", n_bootstrap=B, seed=42)
+    devr = vb.rsa_grouped([f.to(dev) for f in feats], [y.to(dev) for y in neur], "spearman", n_bootstrap=B, seed=42)
+    for key in ("point", "scores", "ci_low", "ci_high"):
+        np.testing.assert_array_equal(host[key], devr[key])
+    assert host["scores"].shape == (3, 4, B)
+    idx = orc.draw_subsamples(n, B, 42)
+    for i, f in enumerate(feats):
+        for j, y in enumerate(neur):
+            ra, rb = orc.rdm(f.flatten(start_dim=1)), orc.rdm(y)
+            np.testing.assert_allclose(host["scores"][i, j], orc.bootstrap_compare_with_indices(ra, rb, "spearman", idx), atol=SCORE_TOL, rtol=0)
+            assert abs(host["point"][i, j] - orc.rdm_compare(ra, rb, correlation="Spearman")) <= SCORE_TOL
+    np.testing.assert_allclose(host["ci_low"], np.percentile(host["scores"], 2.5, axis=2))
+    # more neural than model matrices -> the model side is materialised; and the Pearson route
+    swapped = vb.rsa_grouped(neur, feats, "spearman", n_bootstrap=B, seed=42)
+    np.testing.assert_allclose(swapped["scores"], np.transpose(host["scores"], (1, 0, 2)), atol=1e-15, rtol=0)
+    pear = vb.rsa_grouped(feats, neur, "pearson", n_bootstrap=3, seed=42)
+    ra, rb = orc.rdm(feats[2]), orc.rdm(neur[1])
+    np.testing.assert_allclose(pear["scores"][2, 1], orc.bootstrap_compare_with_indices(ra, rb, "pearson", idx[:3]), atol=SCORE_TOL, rtol=0)
+    nb = vb.rsa_grouped(feats, neur, "spearman", bootstrap=False)
+    assert nb["scores"].shape == (3, 4, 0) and "ci_low" not in nb
+    np.testing.assert_array_equal(nb["point"], host["point"])
+
+
 def test_compute_rsa_matches_reference_fixture(dev, golden_dir):
     with open(os.path.join(golden_dir, "compute_rsa.json")) as f:
         gold = json.load(f)["results"]

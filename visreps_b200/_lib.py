@@ -43,6 +43,12 @@ SIGNATURES = {
     "vr_dev_stride": (_i64, [_i]),
     "vr_subsample_rank_workspace_bytes": (_sz, [_i, _i]),
     "vr_subsample_rank": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "vr_rank_context_bytes": (_sz, [_i, _i]),
+    "vr_rank_context_build": (_i, [_vp, _i, _i, _vp, _sz, _vp]),
+    "vr_rank_workspace_bytes": (_sz, [_i, _i, _i]),
+    "vr_rank_fuse_max": (_i, []),
+    "vr_rank_materialise": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "vr_rank_fused": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _i64, _i64, _vp, _sz, _vp]),
     "vr_bootstrap_spearman_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "vr_bootstrap_spearman": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _vp, _vp, _sz, _vp]),
     "vr_bootstrap_pearson_workspace_bytes": (_sz, [_i, _i, _i, _i]),

@@ -200,13 +200,9 @@ struct RankArgs {
   const int32_t* mat_dev;    // [n_mat][R][dev_stride]
   const double* mat_ss;      // [n_mat][R]
   int n_mat;
-  double* out;               // (nA, nB, Rtot)
-  int out_nB;
-  int64_t out_Rtot;
-  int out_r0;
-  int mat_is_A;              // 1: materialised vectors are the model side (rows of out)
-  int mat_off;               // index of materialised vector 0 on its side
-  int fused_off;             // index of fused vector 0 on its side
+  double* out;               // out[f * out_stride_f + m * out_stride_m + r]
+  int64_t out_stride_f;
+  int64_t out_stride_m;
 };
 
 template <bool kSmemTable, bool kFused, typename Acc>
@@ -371,148 +367,76 @@ rank_kernel(const __grid_constant__ RankArgs A) {
         const double ss_m = A.mat_ss[(int64_t)slot * R + r];
         double rho = tot / (sqrt(ss_m) * sqrt(ss_item));
         if (!(ss_m > 0.0) || !(ss_item > 0.0)) rho = nan;
-        const int ia = A.mat_is_A ? A.mat_off + slot : A.fused_off + v;
-        const int ib = A.mat_is_A ? A.fused_off + v : A.mat_off + slot;
-        A.out[((int64_t)ia * A.out_nB + ib) * A.out_Rtot + A.out_r0 + r] = rho;
+        A.out[(int64_t)v * A.out_stride_f + (int64_t)slot * A.out_stride_m + r] = rho;
       }
     }
     __syncthreads();  // table, s_mask and s_red are reused by the next item
   }
 }
 
-// out[a][b][r] = sum_p devA[a][r][p] * devB[b][r][p] / sqrt(ssA[a][r] * ssB[b][r])
-constexpr int kDotThreads = 256;
-constexpr int kDotTile = 4;
-__global__ void __launch_bounds__(kDotThreads)
-dot_kernel(const int32_t* __restrict__ dev, int64_t dev_stride, const double* __restrict__ ss, int nA, int nB,
-           int R, int r0, int Rtot, double* __restrict__ out, int first_is_model, int out_nB) {
-  __shared__ long long s_part[kDotThreads / 32][kDotTile * kDotTile];
-  __shared__ double s_partd[kDotThreads / 32][kDotTile * kDotTile];
-  const int tilesB = (nB + kDotTile - 1) / kDotTile;
-  const int ta = blockIdx.x / tilesB, tb = blockIdx.x % tilesB;
-  const int r = blockIdx.y;
-  const int a0 = ta * kDotTile, b0 = tb * kDotTile;
-  const int4* pa[kDotTile];
-  const int4* pb[kDotTile];
-#pragma unroll
-  for (int k = 0; k < kDotTile; ++k) {
-    const int a = min(a0 + k, nA - 1), b = min(b0 + k, nB - 1);
-    pa[k] = reinterpret_cast<const int4*>(dev + ((int64_t)a * R + r) * dev_stride);
-    pb[k] = reinterpret_cast<const int4*>(dev + ((int64_t)(nA + b) * R + r) * dev_stride);
-  }
-  const int64_t n4 = dev_stride / 4;
-  long long acc[kDotTile][kDotTile];
-  double accd[kDotTile][kDotTile];
-#pragma unroll
-  for (int x = 0; x < kDotTile; ++x)
-#pragma unroll
-    for (int y = 0; y < kDotTile; ++y) { acc[x][y] = 0; accd[x][y] = 0.0; }
-
-  int since_flush = 0;
-  // |dev| <= N (= dev_stride up to padding): one step adds < 4 N^2 per accumulator
-  const int flush_every = (int)min(256ull, (1ull << 62) / (4ull * (unsigned long long)dev_stride * dev_stride + 1ull) + 1ull);
-  for (int64_t q = threadIdx.x; q < n4; q += kDotThreads) {
-    int4 va[kDotTile], vb[kDotTile];
-#pragma unroll
-    for (int k = 0; k < kDotTile; ++k) { va[k] = __ldg(pa[k] + q); vb[k] = __ldg(pb[k] + q); }
-#pragma unroll
-    for (int x = 0; x < kDotTile; ++x)
-#pragma unroll
-      for (int y = 0; y < kDotTile; ++y) {
-        acc[x][y] += (long long)va[x].x * vb[y].x + (long long)va[x].y * vb[y].y +
-                     (long long)va[x].z * vb[y].z + (long long)va[x].w * vb[y].w;
-      }
-    if (++since_flush >= flush_every) {
-      since_flush = 0;
-#pragma unroll
-      for (int x = 0; x < kDotTile; ++x)
-#pragma unroll
-        for (int y = 0; y < kDotTile; ++y) { accd[x][y] += (double)acc[x][y]; acc[x][y] = 0; }
-    }
-  }
-  const int warp = threadIdx.x >> 5;
-  const unsigned lane = lane_id();
-  // Up to 2^20 pairs the whole sum stays below 2^60 and is carried exactly in int64; beyond
-  // that the per-thread integers are folded into fp64 before any cross-thread addition.
-  const bool exact = dev_stride <= (1ll << 20);
-#pragma unroll
-  for (int x = 0; x < kDotTile; ++x)
-#pragma unroll
-    for (int y = 0; y < kDotTile; ++y) {
-      if (!exact) { accd[x][y] += (double)acc[x][y]; acc[x][y] = 0; }
-      long long s = warp_sum_ll(acc[x][y]);
-      double sd = warp_sum(accd[x][y]);
-      if (lane == 0) { s_part[warp][x * kDotTile + y] = s; s_partd[warp][x * kDotTile + y] = sd; }
-    }
-  __syncthreads();
-  if (threadIdx.x < kDotTile * kDotTile) {
-    const int x = threadIdx.x / kDotTile, y = threadIdx.x % kDotTile;
-    double tot = 0.0;
-    long long ti = 0;
-    for (int w = 0; w < kDotThreads / 32; ++w) { ti += s_part[w][threadIdx.x]; tot += s_partd[w][threadIdx.x]; }
-    tot += (double)ti;
-    const int a = a0 + x, b = b0 + y;
-    if (a < nA && b < nB) {
-      const double sa = ss[(int64_t)a * R + r], sb = ss[(int64_t)(nA + b) * R + r];
-      double rho = tot / (sqrt(sa) * sqrt(sb));
-      if (!(sa > 0.0) || !(sb > 0.0)) rho = __longlong_as_double(0x7ff8000000000000LL);
-      // the first nA vectors of `dev` are the model side when first_is_model, else the neural side
-      const int ia = first_is_model ? a : b, ib = first_is_model ? b : a;
-      out[((int64_t)ia * out_nB + ib) * Rtot + r0 + r] = rho;
-    }
-  }
-}
-
-
 static inline uint32_t table_groups(int n) { return (uint32_t)round_up(presort_groups(n) + 1, 32) + 32u; }
 static inline bool rank_table_in_smem(int n) { return (size_t)table_groups(n) * 8 <= kRankSmemTableMax; }
 static inline size_t rank_smem_bytes(int n, bool smem_table) {
   return smem_table ? (size_t)table_groups(n) * 8 : 0;
 }
-// scratch shared by the launches of one replicate chunk: transposed masks + count tables + segment totals
-static inline size_t count_scratch_bytes(int n, int nV, int64_t R) {
-  return arena_bytes((size_t)((R + 31) / 32) * n, 4) + arena_bytes((size_t)nV * R * table_groups(n), 8) +
-         arena_bytes((size_t)nV * R * kCountWarps, 4) + arena_bytes((size_t)R * (vr_dev_stride(n) / 32), 4);
-}
-struct CountScratch {
+
+// ---- rank context: everything derived from the masks alone, shared by all rank calls of a job ----
+//   pairbits [R][dev_stride/32]  kept bits of the canonical pairs        (rank_kernel)
+//   maskT    [ceil(R/32)][n]     transposed stimulus masks               (count_kernel)
+struct RankContext {
   uint32_t* pairbits;
   uint32_t* maskT;
-  uint2* tables;
-  uint32_t* seg_tot;
 };
-
-// kept words + counts of every (vector, replicate) of the chunk
-static int launch_count(const BlobList& blobs, int nV, int n, const uint32_t* masks, int R, void* scratch,
-                        size_t scratch_bytes, CountScratch* cs, cudaStream_t stream) {
+static inline size_t rank_context_bytes(int n, int64_t R) {
+  return 256 + arena_bytes((size_t)R * (vr_dev_stride(n) / 32), 4) + arena_bytes((size_t)((R + 31) / 32) * n, 4);
+}
+static inline RankContext rank_context_view(void* ctx, int n, int64_t R) {
+  char* p = static_cast<char*>(ctx) + 256;
+  RankContext c;
+  c.pairbits = reinterpret_cast<uint32_t*>(p);
+  p += arena_bytes((size_t)R * (vr_dev_stride(n) / 32), 4);
+  c.maskT = reinterpret_cast<uint32_t*>(p);
+  return c;
+}
+static int build_rank_context(const uint32_t* masks, int n, int R, void* ctx, cudaStream_t stream) {
   const int W = vr_mask_words(n);
-  const uint32_t Gs = table_groups(n);
-  const int batches = (R + 31) / 32;
-  Arena a(scratch, scratch_bytes);
-  cs->maskT = a.take<uint32_t>((size_t)batches * n);
-  cs->tables = a.take<uint2>((size_t)nV * R * Gs);
-  cs->seg_tot = a.take<uint32_t>((size_t)nV * R * kCountWarps);
+  RankContext c = rank_context_view(ctx, n, R);
   const uint32_t words = (uint32_t)(vr_dev_stride(n) / 32);
-  cs->pairbits = a.take<uint32_t>((size_t)R * words);
-  if (!a.ok) { set_error("rank scratch too small"); return VR_ERR_WORKSPACE; }
   ProfScope prof(F_KEPT, stream);
-  {
-    dim3 grid((words + 255) / 256 < 64 ? (words + 255) / 256 : 64, R);
-    pair_mask_kernel<<<grid, 256, (size_t)W * 4, stream>>>(masks, R, n, W, words, cs->pairbits);
+  for (int r0 = 0; r0 < R; r0 += 65535) {   // grid.y limit
+    const int rc = R - r0 < 65535 ? R - r0 : 65535;
+    dim3 grid((words + 255) / 256 < 64 ? (words + 255) / 256 : 64, rc);
+    pair_mask_kernel<<<grid, 256, (size_t)W * 4, stream>>>(masks + (size_t)r0 * W, rc, n, W, words,
+                                                           c.pairbits + (size_t)r0 * words);
     VR_CHECK_LAUNCH();
   }
-  {
-    dim3 grid((n + 255) / 256, batches);
-    transpose_masks_kernel<<<grid, 256, 0, stream>>>(masks, R, n, W, cs->maskT);
-    VR_CHECK_LAUNCH();
-  }
+  const int batches = (R + 31) / 32;
+  dim3 grid((n + 255) / 256, batches);
+  transpose_masks_kernel<<<grid, 256, 0, stream>>>(masks, R, n, W, c.maskT);
+  VR_CHECK_LAUNCH();
+  return VR_OK;
+}
+
+// count tables + segment totals of nV vectors x R replicates
+static inline size_t tables_bytes(int n, int nV, int64_t R) {
+  return arena_bytes((size_t)nV * R * table_groups(n), 8) + arena_bytes((size_t)nV * R * kCountWarps, 4);
+}
+static int launch_count(const BlobList& blobs, int nV, int n, const RankContext& ctx, int R, void* ws, size_t ws_bytes,
+                        uint2** tables, uint32_t** seg_tot, cudaStream_t stream) {
+  const uint32_t Gs = table_groups(n);
+  Arena a(ws, ws_bytes);
+  *tables = a.take<uint2>((size_t)nV * R * Gs);
+  *seg_tot = a.take<uint32_t>((size_t)nV * R * kCountWarps);
+  if (!a.ok) { set_error("rank workspace too small for the count tables"); return VR_ERR_WORKSPACE; }
   static bool attr_set = false;
   const size_t smem = (size_t)n * 4;
   if (!attr_set && smem > 40 * 1024) {
     VR_CHECK_CUDA(cudaFuncSetAttribute(count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     attr_set = true;
   }
-  dim3 grid(batches, nV);
-  count_kernel<<<grid, kCountThreads, smem, stream>>>(blobs, n, cs->maskT, R, cs->tables, Gs, cs->seg_tot);
+  ProfScope prof(F_KEPT, stream);
+  dim3 grid((R + 31) / 32, nV);
+  count_kernel<<<grid, kCountThreads, smem, stream>>>(blobs, n, ctx.maskT, R, *tables, Gs, *seg_tot);
   VR_CHECK_LAUNCH();
   return VR_OK;
 }
@@ -550,6 +474,27 @@ static int launch_rank(const RankArgs& args, bool fused, cudaStream_t stream) {
                : launch_rank_variant<false, false, double>(args, grid, smem, stream);
 }
 
+// count + rank of nV vectors: materialise (dev/ss) or fused against nM materialised vectors
+static int rank_stage(const void* const* blobs_host, int nV, int n, const RankContext& ctx, int R, bool fused,
+                      int32_t* dev, double* ss, int64_t* nkept, const int32_t* mat_dev, const double* mat_ss, int nM,
+                      double* out, int64_t stride_f, int64_t stride_m, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  RankArgs args{};
+  for (int i = 0; i < nV; ++i) {
+    if (!blobs_host[i]) { set_error("null presorted blob"); return VR_ERR_INVALID; }
+    args.blobs.p[i] = blobs_host[i];
+  }
+  uint2* tables = nullptr;
+  uint32_t* seg_tot = nullptr;
+  int st = launch_count(args.blobs, nV, n, ctx, R, ws, ws_bytes, &tables, &seg_tot, stream);
+  if (st != VR_OK) return st;
+  args.n_vectors = nV; args.n = n; args.pairbits = ctx.pairbits; args.R = R; args.tables = tables; args.table_base = 0;
+  args.Gs = table_groups(n); args.seg_tot = seg_tot; args.dev_stride = vr_dev_stride(n);
+  args.dev = dev; args.ss = ss; args.nkept = nkept;
+  args.mat_dev = mat_dev; args.mat_ss = mat_ss; args.n_mat = nM;
+  args.out = out; args.out_stride_f = stride_f; args.out_stride_m = stride_m;
+  return launch_rank(args, fused, stream);
+}
+
 }  // namespace vr
 
 using namespace vr;
@@ -574,8 +519,45 @@ extern "C" int vr_build_masks(const int32_t* idx, int R, int m, int n, uint32_t*
 
 extern "C" int64_t vr_dev_stride(int n) { return n >= 2 ? round_up(triu_len(n), 32) : 32; }
 
+// ---- staged API ---------------------------------------------------------------------------------
+extern "C" size_t vr_rank_context_bytes(int n, int R) { return (n >= 2 && R >= 1) ? rank_context_bytes(n, R) : 256; }
+
+extern "C" int vr_rank_context_build(const uint32_t* masks, int n, int R, void* ctx, size_t ctx_bytes, vr_stream_t stream_) {
+  VR_REQUIRE(masks && ctx, "vr_rank_context_build: null pointer");
+  VR_REQUIRE(n >= 2 && n <= VR_MAX_STIMULI && R >= 1, "vr_rank_context_build: bad sizes n=%d R=%d", n, R);
+  if (ctx_bytes < rank_context_bytes(n, R)) { set_error("vr_rank_context_build: context %zu < %zu", ctx_bytes, rank_context_bytes(n, R)); return VR_ERR_WORKSPACE; }
+  return build_rank_context(masks, n, R, ctx, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" size_t vr_rank_workspace_bytes(int n, int nV, int R) { return (n >= 2 && nV >= 1 && R >= 1) ? tables_bytes(n, nV, R) + 256 : 256; }
+
+extern "C" int vr_rank_materialise(const void* const* blobs, int nV, int n, const void* ctx, int R, int32_t* dev, double* ss,
+                                   int64_t* nkept, void* ws, size_t ws_bytes, vr_stream_t stream_) {
+  VR_REQUIRE(blobs && ctx && dev && ss, "vr_rank_materialise: null pointer");
+  VR_REQUIRE(n >= 2 && n <= VR_MAX_STIMULI && R >= 1 && nV >= 1 && nV <= kMaxVectors, "vr_rank_materialise: bad sizes n=%d nV=%d R=%d", n, nV, R);
+  if (!ws || ws_bytes < vr_rank_workspace_bytes(n, nV, R)) { set_error("vr_rank_materialise: workspace %zu < %zu", ws_bytes, vr_rank_workspace_bytes(n, nV, R)); return VR_ERR_WORKSPACE; }
+  RankContext c = rank_context_view(const_cast<void*>(ctx), n, R);
+  return rank_stage(blobs, nV, n, c, R, false, dev, ss, nkept, nullptr, nullptr, 0, nullptr, 0, 0, ws, ws_bytes,
+                    static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int vr_rank_fused(const void* const* blobs, int nF, int n, const void* ctx, int R, const int32_t* mat_dev,
+                             const double* mat_ss, int nM, double* out, int64_t out_stride_fused, int64_t out_stride_mat,
+                             void* ws, size_t ws_bytes, vr_stream_t stream_) {
+  VR_REQUIRE(blobs && ctx && mat_dev && mat_ss && out, "vr_rank_fused: null pointer");
+  VR_REQUIRE(n >= 2 && n <= VR_MAX_STIMULI && R >= 1 && nF >= 1 && nF <= kMaxVectors, "vr_rank_fused: bad sizes n=%d nF=%d R=%d", n, nF, R);
+  VR_REQUIRE(nM >= 1 && nM <= kFuseMax, "vr_rank_fused: nM=%d outside [1, %d]", nM, kFuseMax);
+  if (!ws || ws_bytes < vr_rank_workspace_bytes(n, nF, R)) { set_error("vr_rank_fused: workspace %zu < %zu", ws_bytes, vr_rank_workspace_bytes(n, nF, R)); return VR_ERR_WORKSPACE; }
+  RankContext c = rank_context_view(const_cast<void*>(ctx), n, R);
+  return rank_stage(blobs, nF, n, c, R, true, nullptr, nullptr, nullptr, mat_dev, mat_ss, nM, out, out_stride_fused,
+                    out_stride_mat, ws, ws_bytes, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int vr_rank_fuse_max(void) { return kFuseMax; }
+
+// ---- single-vector convenience (context + materialise) -------------------------------------------
 extern "C" size_t vr_subsample_rank_workspace_bytes(int n, int R) {
-  return (n >= 2 && R >= 1) ? count_scratch_bytes(n, 1, R) + 256 : 256;
+  return (n >= 2 && R >= 1) ? rank_context_bytes(n, R) + tables_bytes(n, 1, R) + 512 : 256;
 }
 
 extern "C" int vr_subsample_rank(const void* presorted, int n, const uint32_t* masks, int R, int32_t* dev,
@@ -587,47 +569,45 @@ extern "C" int vr_subsample_rank(const void* presorted, int n, const uint32_t* m
     set_error("vr_subsample_rank: workspace %zu < %zu", ws_bytes, vr_subsample_rank_workspace_bytes(n, R));
     return VR_ERR_WORKSPACE;
   }
-  RankArgs args{};
-  args.blobs.p[0] = presorted;
-  CountScratch cs;
-  int st = launch_count(args.blobs, 1, n, masks, R, ws, ws_bytes, &cs, stream);
+  Arena a(ws, ws_bytes);
+  void* ctx = a.take<char>(rank_context_bytes(n, R));
+  void* rest = a.take<char>(tables_bytes(n, 1, R) + 256);
+  int st = build_rank_context(masks, n, R, ctx, stream);
   if (st != VR_OK) return st;
-  args.n_vectors = 1; args.n = n; args.pairbits = cs.pairbits; args.R = R;
-  args.tables = cs.tables; args.table_base = 0; args.Gs = table_groups(n); args.seg_tot = cs.seg_tot;
-  args.dev_stride = vr_dev_stride(n); args.dev = dev; args.ss = ss; args.nkept = nkept;
-  return launch_rank(args, false, stream);
+  RankContext c = rank_context_view(ctx, n, R);
+  const void* blobs[1] = {presorted};
+  return rank_stage(blobs, 1, n, c, R, false, dev, ss, nkept, nullptr, nullptr, 0, nullptr, 0, 0, rest, tables_bytes(n, 1, R) + 256, stream);
 }
 
+// ---- one-call grouped bootstrap ---------------------------------------------------------------------
 namespace {
-// VR_SPEARMAN_FUSED=1: the larger side multiplies on the fly (no dev vectors for it, no dot kernel).
-// Default: both sides are materialised and dot_kernel combines them.
-inline bool fused_mode() {
-  static const bool f = [] { const char* e = getenv("VR_SPEARMAN_FUSED"); return e && e[0] == '1'; }();
-  return f;
-}
 struct SpearmanPlan {
-  size_t fixed;     // transposed masks + slack
-  size_t per_rep;   // tables + segment totals of every vector, dev + ss of one materialised group
+  size_t fixed;
+  size_t per_rep;   // context + tables of the larger stage + dev/ss of one materialised group, per replicate
 };
-SpearmanPlan spearman_plan(int n, int nV, int n_mat) {
+inline int mat_group(int nA, int nB) { int m = nA <= nB ? nA : nB; return m < kFuseMax ? m : kFuseMax; }
+SpearmanPlan spearman_plan(int n, int nA, int nB) {
+  const int group = mat_group(nA, nB);
+  const int nF = nA <= nB ? nB : nA;
+  const int stage = group > nF ? group : nF;
   SpearmanPlan p;
-  p.fixed = arena_bytes((size_t)n * 2100, 4) + 8192;   // transposed masks of up to 65535 replicates + slack
-  p.per_rep = (size_t)nV * ((size_t)table_groups(n) * 8 + 4 * kCountWarps) +
-              (size_t)(fused_mode() ? n_mat : nV) * ((size_t)vr_dev_stride(n) * 4 + 8) + (size_t)vr_dev_stride(n) / 8;
+  p.fixed = 16 * 256 + (size_t)n * 4 * 2 + 4096;
+  p.per_rep = (size_t)vr_dev_stride(n) / 8 + (size_t)n / 8 + 8 +                      // context
+              (size_t)stage * ((size_t)table_groups(n) * 8 + 4 * kCountWarps) +      // count tables
+              (size_t)group * ((size_t)vr_dev_stride(n) * 4 + 8);                    // dev + ss
   return p;
 }
 constexpr size_t kSoftCap = (size_t)40 << 30;  // default upper bound on one call's workspace
-inline int mat_group(int nA, int nB) { int m = nA <= nB ? nA : nB; return m < kFuseMax ? m : kFuseMax; }
 }  // namespace
 
 extern "C" size_t vr_bootstrap_spearman_workspace_bytes(int n, int nA, int nB, int R) {
   if (n < 2 || nA < 1 || nB < 1 || R < 1) return 4096;
-  SpearmanPlan p = spearman_plan(n, nA + nB, mat_group(nA, nB));
+  SpearmanPlan p = spearman_plan(n, nA, nB);
   size_t reps = (size_t)R;
   size_t cap = kSoftCap / p.per_rep;
-  if (cap < 1) cap = 1;
+  if (cap < 32) cap = 32;
   if (reps > cap) reps = cap;
-  return p.fixed + reps * p.per_rep + 8 * 256;
+  return p.fixed + reps * p.per_rep;
 }
 
 extern "C" int vr_bootstrap_spearman(const void* const* A, int nA, const void* const* B, int nB, int n,
@@ -638,71 +618,45 @@ extern "C" int vr_bootstrap_spearman(const void* const* A, int nA, const void* c
   VR_REQUIRE(n >= 2 && n <= VR_MAX_STIMULI, "vr_bootstrap_spearman: n=%d outside [2, %d]", n, VR_MAX_STIMULI);
   VR_REQUIRE(nA >= 1 && nB >= 1 && nA + nB <= kMaxVectors, "vr_bootstrap_spearman: nA=%d nB=%d (max %d in total)", nA, nB, kMaxVectors);
   VR_REQUIRE(R >= 1, "vr_bootstrap_spearman: R=%d", R);
-  const int nV = nA + nB;
   // The side with fewer vectors is materialised (in groups of <= kFuseMax); the other side is fused.
   const bool mat_is_A = nA <= nB;
   const int nM = mat_is_A ? nA : nB, nF = mat_is_A ? nB : nA;
+  const void* const* M = mat_is_A ? A : B;
+  const void* const* F = mat_is_A ? B : A;
   const int group = mat_group(nA, nB);
-  SpearmanPlan plan = spearman_plan(n, nV, group);
-  if (!ws || ws_bytes < plan.fixed + plan.per_rep + 8 * 256) {
-    set_error("vr_bootstrap_spearman: workspace %zu < minimum %zu", ws_bytes, plan.fixed + plan.per_rep + 8 * 256);
+  SpearmanPlan plan = spearman_plan(n, nA, nB);
+  const size_t min_ws = plan.fixed + (size_t)(R < 32 ? R : 32) * plan.per_rep;
+  if (!ws || ws_bytes < min_ws) {
+    set_error("vr_bootstrap_spearman: workspace %zu < minimum %zu", ws_bytes, min_ws);
     return VR_ERR_WORKSPACE;
   }
-  BlobList all{};   // materialised side first, fused side after
-  for (int i = 0; i < nM; ++i) { const void* p = mat_is_A ? A[i] : B[i]; VR_REQUIRE(p, "null blob"); all.p[i] = p; }
-  for (int i = 0; i < nF; ++i) { const void* p = mat_is_A ? B[i] : A[i]; VR_REQUIRE(p, "null blob"); all.p[nM + i] = p; }
-  int64_t chunk = (int64_t)((ws_bytes - plan.fixed - 8 * 256) / plan.per_rep);
+  int64_t chunk = (int64_t)((ws_bytes - plan.fixed) / plan.per_rep);
   if (chunk > R) chunk = R;
   if (chunk > 65535) chunk = 65535;
+  if (chunk < R) chunk = chunk / 32 * 32;                   // keep replicate batches of 32 whole
+  const int stage = group > nF ? group : nF;
   Arena a(ws, ws_bytes);
-  const size_t scratch_bytes = count_scratch_bytes(n, nV, chunk) + 256;
-  void* scratch = a.take<char>(scratch_bytes);
-  const int n_dev = fused_mode() ? group : nV;
-  double* ss = a.take<double>((size_t)n_dev * chunk);
-  int32_t* dev = a.take<int32_t>((size_t)n_dev * chunk * vr_dev_stride(n));
+  void* ctx = a.take<char>(rank_context_bytes(n, chunk));
+  const size_t tb = tables_bytes(n, stage, chunk) + 256;
+  void* tws = a.take<char>(tb);
+  double* ss = a.take<double>((size_t)group * chunk);
+  int32_t* dev = a.take<int32_t>((size_t)group * chunk * vr_dev_stride(n));
   if (!a.ok) { set_error("vr_bootstrap_spearman: internal workspace plan overflow"); return VR_ERR_WORKSPACE; }
   const int W = vr_mask_words(n);
+  // out is (nA, nB, R): strides of the fused / materialised index
+  const int64_t stride_f = mat_is_A ? (int64_t)R : (int64_t)nB * R;
+  const int64_t stride_m = mat_is_A ? (int64_t)nB * R : (int64_t)R;
   for (int64_t r0 = 0; r0 < R; r0 += chunk) {
     const int rc = (int)(R - r0 < chunk ? R - r0 : chunk);
-    const uint32_t* mk = masks + (size_t)r0 * W;
-    CountScratch cs;
-    int st = launch_count(all, nV, n, mk, rc, scratch, scratch_bytes, &cs, stream);
+    int st = build_rank_context(masks + (size_t)r0 * W, n, rc, ctx, stream);
     if (st != VR_OK) return st;
-    if (!fused_mode()) {
-      // materialise every vector (model side first, as laid out in `all` when mat_is_A, else neural first)
-      RankArgs mat{};
-      mat.n = n; mat.pairbits = cs.pairbits; mat.R = rc; mat.tables = cs.tables; mat.Gs = table_groups(n);
-      mat.seg_tot = cs.seg_tot; mat.dev_stride = vr_dev_stride(n);
-      for (int i = 0; i < nV; ++i) mat.blobs.p[i] = all.p[i];
-      mat.n_vectors = nV; mat.table_base = 0; mat.dev = dev; mat.ss = ss; mat.nkept = nullptr;
-      st = launch_rank(mat, false, stream);
-      if (st != VR_OK) return st;
-      // dot_kernel expects the model vectors first: when the neural side was laid out first, swap the roles
-      // and transpose on output by calling it with (nM = rows) and writing through a strided view.
-      const int tiles = ((nM + kDotTile - 1) / kDotTile) * ((nF + kDotTile - 1) / kDotTile);
-      dim3 grid(tiles, rc);
-      ProfScope prof(F_DOT, stream);
-      dot_kernel<<<grid, kDotThreads, 0, stream>>>(dev, vr_dev_stride(n), ss, nM, nF, rc, (int)r0, R, out,
-                                                   mat_is_A ? 1 : 0, nB);
-      VR_CHECK_LAUNCH();
-      continue;
-    }
+    RankContext c = rank_context_view(ctx, n, rc);
     for (int m0 = 0; m0 < nM; m0 += group) {
       const int mg = nM - m0 < group ? nM - m0 : group;
-      RankArgs base{};
-      base.n = n; base.pairbits = cs.pairbits; base.R = rc; base.tables = cs.tables; base.Gs = table_groups(n);
-      base.seg_tot = cs.seg_tot; base.dev_stride = vr_dev_stride(n);
-      RankArgs mat = base;          // materialise vectors [m0, m0 + mg)
-      for (int i = 0; i < mg; ++i) mat.blobs.p[i] = all.p[m0 + i];
-      mat.n_vectors = mg; mat.table_base = m0; mat.dev = dev; mat.ss = ss; mat.nkept = nullptr;
-      st = launch_rank(mat, false, stream);
+      st = rank_stage(M + m0, mg, n, c, rc, false, dev, ss, nullptr, nullptr, nullptr, 0, nullptr, 0, 0, tws, tb, stream);
       if (st != VR_OK) return st;
-      RankArgs fu = base;           // every fused vector against this group
-      for (int i = 0; i < nF; ++i) fu.blobs.p[i] = all.p[nM + i];
-      fu.n_vectors = nF; fu.table_base = nM; fu.mat_dev = dev; fu.mat_ss = ss; fu.n_mat = mg;
-      fu.out = out; fu.out_nB = nB; fu.out_Rtot = R; fu.out_r0 = (int)r0;
-      fu.mat_is_A = mat_is_A ? 1 : 0; fu.mat_off = m0; fu.fused_off = 0;
-      st = launch_rank(fu, true, stream);
+      st = rank_stage(F, nF, n, c, rc, true, nullptr, nullptr, nullptr, dev, ss, mg, out + m0 * stride_m + r0, stride_f,
+                      stride_m, tws, tb, stream);
       if (st != VR_OK) return st;
     }
   }

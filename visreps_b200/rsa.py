@@ -112,22 +112,38 @@ def build_masks(index_sets: Optional[np.ndarray], n: int, device: torch.device, 
     """(R, W) int32 device tensor of membership bit masks; row 0 is the full mask if with_full.
 
     index_sets: host (B, m) integer array, the reference's `rng.choice(n, m, replace=False)` draws.
+    The index array is staged in pinned host memory and read by the mask kernel directly over PCIe
+    (unified addressing), so it never queues behind bulk host->device copies on the DMA engine.
     """
     lib = _lib.load()
     w = lib.vr_mask_words(n)
     b = 0 if index_sets is None else int(index_sets.shape[0])
     masks = torch.empty((b + (1 if with_full else 0), w), dtype=torch.int32, device=device)
     if with_full:
-        masks[0].copy_(torch.from_numpy(full_mask(n).view(np.int32)), non_blocking=False)
+        masks[0].fill_(-1)
+        if n % 32:
+            masks[0, w - 1:].fill_((1 << (n % 32)) - 1)
     if b:
-        idx_host = torch.from_numpy(np.ascontiguousarray(index_sets, dtype=np.int32))
-        if idx_host.numel() and (int(idx_host.min()) < 0 or int(idx_host.max()) >= n):
+        idx_np = np.ascontiguousarray(index_sets, dtype=np.int32)
+        if idx_np.size and (int(idx_np.min()) < 0 or int(idx_np.max()) >= n):
             raise ValueError("bootstrap index out of range")
-        idx = idx_host.pin_memory().to(device, non_blocking=True)
+        idx = torch.from_numpy(idx_np).pin_memory()
         sub = masks[1:] if with_full else masks
         _lib.check(lib.vr_build_masks(idx.data_ptr(), b, int(idx.shape[1]), n, sub.data_ptr(), _lib.stream_ptr()),
                    "vr_build_masks")
+        _keep_alive(idx)
     return masks
+
+
+_pinned_in_flight: list = []
+
+
+def _keep_alive(t: torch.Tensor) -> None:
+    """Hold a pinned staging buffer until the kernels reading it have run (released at the next sync point)."""
+    _pinned_in_flight.append((t, torch.cuda.Event()))
+    _pinned_in_flight[-1][1].record()
+    while len(_pinned_in_flight) > 1 and _pinned_in_flight[0][1].query():
+        _pinned_in_flight.pop(0)
 
 
 def draw_index_sets(n: int, n_bootstrap: int, seed: int = 42, rng: Optional[np.random.RandomState] = None) -> np.ndarray:
@@ -480,6 +496,180 @@ def _rdm_device(x: torch.Tensor, dev: torch.device, correction: float, flags: to
     return rdm
 
 
+class RankContext:
+    """Everything the ranking kernels derive from the subsample masks alone (library-opaque), built once
+    per job and shared by every RDM that is ranked against those masks."""
+
+    def __init__(self, masks: torch.Tensor, n: int):
+        lib = _lib.load()
+        self.n, self.R, self.masks = n, int(masks.shape[0]), masks
+        self.buf = torch.empty(lib.vr_rank_context_bytes(n, self.R), dtype=torch.uint8, device=masks.device)
+        _lib.check(lib.vr_rank_context_build(masks.data_ptr(), n, self.R, self.buf.data_ptr(), self.buf.numel(),
+                                             _lib.stream_ptr()), "vr_rank_context_build")
+
+    def materialise(self, items: Sequence[PresortedRDM]):
+        """dev (nV, R, stride) int32 and ss (nV, R) fp64 of the given presorted RDMs."""
+        lib = _lib.load()
+        dev = self.buf.device
+        nV = len(items)
+        stride = lib.vr_dev_stride(self.n)
+        out = torch.empty((nV, self.R, stride), dtype=torch.int32, device=dev)
+        ss = torch.empty((nV, self.R), dtype=torch.float64, device=dev)
+        ws = _lib.workspace(lib.vr_rank_workspace_bytes(self.n, nV, self.R), dev, "rank")
+        _lib.check(lib.vr_rank_materialise(_ptr_array([p.blob for p in items]), nV, self.n, self.buf.data_ptr(), self.R,
+                                           out.data_ptr(), ss.data_ptr(), None, ws.data_ptr(), ws.numel(),
+                                           _lib.stream_ptr()), "vr_rank_materialise")
+        return out, ss
+
+    def fused(self, items: Sequence[PresortedRDM], mat_dev: torch.Tensor, mat_ss: torch.Tensor, out: torch.Tensor,
+              out_offset: int, stride_fused: int, stride_mat: int) -> None:
+        """Rank `items` and write their Spearman coefficients against the materialised vectors into `out`
+        (flat fp64) at out_offset + f * stride_fused + m * stride_mat + r."""
+        lib = _lib.load()
+        dev = self.buf.device
+        ws = _lib.workspace(lib.vr_rank_workspace_bytes(self.n, len(items), self.R), dev, "rank")
+        _lib.check(lib.vr_rank_fused(_ptr_array([p.blob for p in items]), len(items), self.n, self.buf.data_ptr(), self.R,
+                                     mat_dev.data_ptr(), mat_ss.data_ptr(), int(mat_dev.shape[0]),
+                                     out.data_ptr() + 8 * out_offset, stride_fused, stride_mat, ws.data_ptr(), ws.numel(),
+                                     _lib.stream_ptr()), "vr_rank_fused")
+
+
+def _spearman_pipeline(inputs_a: Sequence[torch.Tensor], inputs_b: Sequence[torch.Tensor], index_sets: Optional[np.ndarray],
+                       draw, n_draws: int, correction: float, dev: torch.device):
+    """Pearson RDMs + grouped Spearman for host or device inputs, with host->device copies, RDM builds and
+    ranking overlapped.  Returns (out (nA, nB, R) fp64 device tensor, zero-variance flags tensor).
+
+    The side with fewer matrices is "materialised" first (its centred rank vectors are kept in HBM); every
+    matrix of the other side is then copied (smallest first), turned into an RDM, presorted and ranked
+    against the materialised vectors as soon as its copy lands, so only the last matrix's work is exposed
+    after the final copy.
+    """
+    lib = _lib.load()
+    nA, nB = len(inputs_a), len(inputs_b)
+    n = int(inputs_a[0].shape[0])
+    mat_is_a = nA < nB                                   # ties: the neural side is materialised
+    mats = list(inputs_a if mat_is_a else inputs_b)
+    fus = list(inputs_b if mat_is_a else inputs_a)
+    order = sorted(range(len(fus)), key=lambda k: fus[k].numel())     # smallest copy first
+    # size the scratch for the largest matrix now, so no allocation (and no implicit sync) happens mid-pipeline
+    _lib.workspace(max(lib.vr_rdm_workspace_bytes(n, int(np.prod(x.shape[1:]))) for x in mats + fus), dev)
+    compute = torch.cuda.current_stream()
+    copier = _copy_stream(dev)
+    copier.wait_stream(compute)
+
+    def stage(x):                                        # enqueue the H2D copy (if any) on the copy stream
+        x = _flat(x) if x.ndim > 2 else x
+        if x.device == dev:
+            return x, None
+        with torch.cuda.stream(copier):
+            xd = x.to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copier)
+            _mark(f"copied {tuple(x.shape)}", copier)
+        xd.record_stream(compute)
+        return xd, ev
+
+    _mark("start")
+
+    staged_m = [stage(x) for x in mats]
+    staged_f = {k: stage(fus[k]) for k in order}
+    flags = torch.zeros(nA + nB, dtype=torch.int32, device=dev)
+    gmax = lib.vr_rank_fuse_max()
+
+    def rdm_of(staged, slot):
+        xd, ev = staged
+        if ev is not None:
+            compute.wait_event(ev)
+        return _rdm_device(xd, dev, correction, flags, slot)
+
+    slot_m = lambda k: k if mat_is_a else nA + k
+    slot_f = lambda k: nA + k if mat_is_a else k
+    fus_on_device = all(ev is None for _, ev in staged_f.values())
+    # Work that does not need the masks is enqueued before the host draws the index sets: the
+    # materialised side, and as many of the fused side's matrices (smallest first) as will have landed
+    # by the time the draw is done (host draw ~8.5 ns per index, copies ~50 GB/s).  The compute stream
+    # only waits on copy events, never the host.
+    m_items = PresortedRDM.batch([rdm_of(st, slot_m(k)) for k, st in enumerate(staged_m)])
+    f_items: Dict[int, PresortedRDM] = {}
+    if fus_on_device:
+        for k, it in enumerate(PresortedRDM.batch([rdm_of(staged_f[k], slot_f(k)) for k in range(len(fus))])):
+            f_items[k] = it
+    elif index_sets is None:
+        budget = 8.5e-9 * n * max(1, n_draws) * 50e9
+        sent = sum(x.numel() * 4 for x in mats)
+        for k in order:
+            sent += fus[k].numel() * 4
+            if sent > budget:
+                break
+            f_items[k] = PresortedRDM(rdm_of(staged_f[k], slot_f(k)))
+    # ... while the host replays the reference's RNG stream and the copies fly
+    if index_sets is None:
+        index_sets = draw()
+    _mark("drawn")
+    masks = build_masks(index_sets, n, dev, with_full=True)
+    R = int(masks.shape[0])
+    ctx = RankContext(masks, n)
+    out = torch.empty((nA, nB, R), dtype=torch.float64, device=dev)
+    _mark("context")
+
+    # materialised side
+    groups = []
+    for g0 in range(0, len(m_items), gmax):
+        mdev, mss = ctx.materialise(m_items[g0:g0 + gmax])
+        groups.append((g0, mdev, mss))
+    _mark("materialised")
+    # fused side
+    stride_m = nB * R if mat_is_a else R
+    stride_f = R if mat_is_a else nB * R
+    if fus_on_device:                                    # nothing to overlap with: one batched pass
+        batch = [f_items[k] for k in range(len(fus))]
+        for g0, mdev, mss in groups:
+            ctx.fused(batch, mdev, mss, out, g0 * stride_m, stride_f, stride_m)
+    else:
+        ready = [k for k in order if k in f_items]       # presorted before the draw: one batched call per group
+        if ready:
+            # fused vector k lives at k * stride_f: the batch is addressed through its first member and the
+            # (uniform) distance between consecutive members only when they are contiguous; otherwise one by one
+            contiguous = all(b - a == 1 for a, b in zip(sorted(ready), sorted(ready)[1:]))
+            if contiguous and len(ready) > 1:
+                ks = sorted(ready)
+                for g0, mdev, mss in groups:
+                    ctx.fused([f_items[k] for k in ks], mdev, mss, out, ks[0] * stride_f + g0 * stride_m, stride_f, stride_m)
+            else:
+                for k in ready:
+                    for g0, mdev, mss in groups:
+                        ctx.fused([f_items[k]], mdev, mss, out, k * stride_f + g0 * stride_m, stride_f, stride_m)
+            _mark(f"fused batch {sorted(ready)}")
+        for k in order:
+            if k in f_items:
+                continue
+            item = PresortedRDM(rdm_of(staged_f[k], slot_f(k)))
+            for g0, mdev, mss in groups:
+                ctx.fused([item], mdev, mss, out, k * stride_f + g0 * stride_m, stride_f, stride_m)
+            _mark(f"fused {k}")
+    _mark("done")
+    return out, flags
+
+
+_copy_streams: Dict[int, torch.cuda.Stream] = {}
+TRACE: Optional[list] = None      # set to [] to collect (label, stream-event, host-seconds) marks of the pipeline
+
+
+def _mark(label: str, stream=None) -> None:
+    if TRACE is not None:
+        import time
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(stream if stream is not None else torch.cuda.current_stream())
+        TRACE.append((label, ev, time.perf_counter()))
+
+
+def _copy_stream(dev: torch.device) -> torch.cuda.Stream:
+    s = _copy_streams.get(dev.index)
+    if s is None:
+        s = _copy_streams[dev.index] = torch.cuda.Stream(device=dev)
+    return s
+
+
 def rsa_grouped(model_features: Sequence[torch.Tensor], neural_responses: Sequence[torch.Tensor],
                 method: str = "spearman", bootstrap: bool = True, n_bootstrap: int = 1000, seed: int = 42,
                 correction: float = 1e-12, replicate_range: Optional[Tuple[int, int]] = None,
@@ -504,24 +694,33 @@ def rsa_grouped(model_features: Sequence[torch.Tensor], neural_responses: Sequen
     if any(int(t.shape[0]) != n for t in list(model_features) + list(neural_responses)):
         raise ValueError("all inputs must have the same number of stimuli")
     nA, nB = len(model_features), len(neural_responses)
-    flags = torch.zeros(nA + nB, dtype=torch.int32, device=dev)
-    # enqueue RDM + presort for every matrix (asynchronous) ...
-    rdms = [_rdm_device(x, dev, correction, flags, k)
-            for k, x in enumerate(list(model_features) + list(neural_responses))]
-    prepared = _prepare_many(rdms, method)
-    # ... and draw the index sets on the host meanwhile
-    if bootstrap and index_sets is None:
-        index_sets = draw_index_sets(n, n_bootstrap, seed)
+
+    def draw():
+        if not bootstrap:
+            return None
+        idx = draw_index_sets(n, n_bootstrap, seed)
+        return idx if replicate_range is None else idx[replicate_range[0]:replicate_range[1]]
+
+    if index_sets is not None and replicate_range is not None:
+        index_sets = index_sets[replicate_range[0]:replicate_range[1]]
     if not bootstrap:
         index_sets = None
-    elif replicate_range is not None:
-        index_sets = index_sets[replicate_range[0]:replicate_range[1]]
     if n <= 1:
-        b = 0 if index_sets is None else len(index_sets)
+        b = 0 if not bootstrap else (len(index_sets) if index_sets is not None else n_bootstrap)
         return {"point": np.full((nA, nB), np.nan), "scores": np.full((nA, nB, b), np.nan),
                 "ci_low": np.full((nA, nB), np.nan), "ci_high": np.full((nA, nB), np.nan)}
-    masks = build_masks(index_sets, n, dev, with_full=True)
-    out_dev = compare_grouped(prepared[:nA], prepared[nA:], method, masks)
+    if method == "spearman" and _pipeline_fits(n, nA, nB, (n_bootstrap if bootstrap else 0) + 1, dev):
+        out_dev, flags = _spearman_pipeline(model_features, neural_responses, index_sets, draw,
+                                            n_bootstrap if bootstrap else 0, correction, dev)
+    else:
+        flags = torch.zeros(nA + nB, dtype=torch.int32, device=dev)
+        rdms = [_rdm_device(x, dev, correction, flags, k)
+                for k, x in enumerate(list(model_features) + list(neural_responses))]
+        prepared = _prepare_many(rdms, method)
+        if index_sets is None:
+            index_sets = draw()
+        masks = build_masks(index_sets, n, dev, with_full=True)
+        out_dev = compare_grouped(prepared[:nA], prepared[nA:], method, masks)
     host = torch.empty(out_dev.shape, dtype=torch.float64, pin_memory=True)
     host.copy_(out_dev, non_blocking=True)
     flags_host = flags.cpu()            # synchronises the stream: results are complete after this
@@ -535,3 +734,15 @@ def rsa_grouped(model_features: Sequence[torch.Tensor], neural_responses: Sequen
         res["ci_low"] = np.percentile(res["scores"], 2.5, axis=2)
         res["ci_high"] = np.percentile(res["scores"], 97.5, axis=2)
     return res
+
+
+def _pipeline_fits(n: int, nA: int, nB: int, R: int, dev: torch.device) -> bool:
+    """The pipelined path keeps all R replicates of the materialised side resident; fall back to the
+    replicate-chunked one-call path when that would not fit comfortably."""
+    lib = _lib.load()
+    n_mat = min(nA, nB)
+    need = n_mat * R * (lib.vr_dev_stride(n) * 4 + 8) + lib.vr_rank_context_bytes(n, R) + \
+        lib.vr_rank_workspace_bytes(n, max(min(n_mat, lib.vr_rank_fuse_max()), max(nA, nB)), R)
+    free, _total = torch.cuda.mem_get_info(dev)
+    cached = torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
+    return need < 0.6 * (free + cached)
