@@ -103,7 +103,7 @@ def run_reference_arm(args):
         "gpu_launches": 0,
         "note": "ms_per_step is the whole-job time scaled from the bounded sample; a CPU job does not speed up with --gpus",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -321,12 +321,31 @@ def run_ours(args):
         "device_ms_per_step": ms_dev / args.steps, "wall_ms_per_step": wall_dev / args.steps,
         "score_sample": {"point_00": float(res["point"][0, 0]), "ci_00": [float(res["ci_low"][0, 0]), float(res["ci_high"][0, 0])]},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def _claim_stdout():
+    """Everything that writes to fd 1 during the run (NCCL's version banner, library chatter) goes to stderr;
+    the one JSON line is written to the real stdout at the end."""
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
+    return real
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    _REAL_STDOUT = _claim_stdout()
     args = parse()
     if args.impl == "reference":
         run_reference_arm(args)
