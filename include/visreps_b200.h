@@ -176,6 +176,17 @@ int vr_bootstrap_pearson(const float* const* rdmA_host, int nA,
                          int n, int64_t ld, const uint32_t* masks, int R, double* out,
                          void* ws, size_t ws_bytes, vr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * Kendall tau-a of two RDMs' upper triangles for R subsample masks: replaces _kendall_tau_a,
+ * rsa.py:22-40 (SciPy tau-b rescaled to (C - D) / n0) inside compute_rdm_correlation (rsa.py:122)
+ * and inside the bootstrap loops when compare_method = kendall (evals.py:229, utils.py:518).
+ * out is (R,) fp64; NaN for < 2 kept pairs, a constant vector or a NaN entry.
+ * ---------------------------------------------------------------------------------- */
+size_t vr_kendall_workspace_bytes(int n);
+int vr_kendall_tau_a(const float* rdmA, const float* rdmB, int n, int64_t ld,
+                     const uint32_t* masks, int R, double* out,
+                     void* ws, size_t ws_bytes, vr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -159,6 +159,36 @@ def test_compare_with_heavy_ties(tag, n, levels, seed, dev, golden_dir):
         assert abs(s - float(gold[f"{tag}/{method.lower()}"])) <= SCORE_TOL
 
 
+@pytest.mark.parametrize("name", ["p64", "p220"])
+def test_kendall_tau_a_matches_oracle_and_golden(name, dev, golden_dir):
+    gold = np.load(os.path.join(golden_dir, "compare.npz"))
+    x, y = cases.pair_inputs(name)
+    a, b = orc.rdm(x), orc.rdm(y)
+    s = vb.compute_rdm_correlation(a, b, correlation="Kendall")
+    assert abs(s - float(gold[f"{name}/kendall"])) <= SCORE_TOL
+    assert abs(vb.compute_rdm_correlation(a, b) - s) == 0.0                     # Kendall is the default
+    n = a.shape[0]
+    idx = orc.draw_subsamples(n, 5, 42)
+    point, lo, hi, scores = vb.bootstrap_rdm_correlation(a, b, "kendall", n_bootstrap=5, seed=42)
+    np.testing.assert_allclose(scores, orc.bootstrap_compare_with_indices(a, b, "kendall", idx), atol=SCORE_TOL, rtol=0)
+    assert abs(point - s) <= 1e-15
+
+
+def test_kendall_ties_and_hand_counts(dev, golden_dir):
+    gold = np.load(os.path.join(golden_dir, "compare.npz"))
+    for tag, n, levels, seed in [("ties24", 24, 7, 301), ("ties90", 90, 40, 302)]:
+        va, vbv = cases.tied_vectors(n * (n - 1) // 2, levels, seed)
+        a, b = cases.vector_to_rdm(va, n), cases.vector_to_rdm(vbv, n)
+        assert abs(vb.compute_rdm_correlation(a.to(dev), b.to(dev), correlation="Kendall") - float(gold[f"{tag}/kendall"])) <= SCORE_TOL
+    # hand-counted examples on a 3-stimulus RDM (3 pairs): x = (1,2,3)
+    mk = lambda v: cases.vector_to_rdm(np.asarray(v, dtype=np.float32), 3)
+    assert vb.compute_rdm_correlation(mk([1, 2, 3]), mk([1, 3, 2]), correlation="Kendall") == pytest.approx(1 / 3)
+    assert vb.compute_rdm_correlation(mk([1, 2, 3]), mk([3, 1, 2]), correlation="Kendall") == pytest.approx(-1 / 3)
+    assert vb.compute_rdm_correlation(mk([1, 2, 3]), mk([3, 2, 1]), correlation="Kendall") == pytest.approx(-1.0)
+    # ties lower |tau-a| (no tie correction): x = (1,1,2), y = (1,2,3): C = 2, D = 0, n0 = 3
+    assert vb.compute_rdm_correlation(mk([1, 1, 2]), mk([1, 2, 3]), correlation="Kendall") == pytest.approx(2 / 3)
+
+
 def test_compare_edge_semantics(dev):
     x = torch.randn(20, 10)
     r = vb.compute_rdm(x.to(dev))
@@ -180,8 +210,8 @@ def test_compare_edge_semantics(dev):
         vb.compute_rdm_correlation(torch.zeros(5, 5), torch.zeros(6, 6))
     with pytest.raises(ValueError):
         vb.compute_rdm_correlation(r, r, correlation="cosine")
-    with pytest.raises(NotImplementedError):
-        vb.compute_rdm_correlation(r, r)                                  # default is Kendall (rsa.py:97)
+    assert vb.compute_rdm_correlation(r, r) == pytest.approx(1.0, abs=1e-12)   # default is Kendall (rsa.py:97)
+    assert math.isnan(vb.compute_rdm_correlation(torch.ones(6, 6).to(dev), r[:6, :6], correlation="Kendall"))
     # negative values, -0.0 and wide dynamic range sort correctly
     rs = np.random.RandomState(9)
     n = 40
@@ -345,8 +375,12 @@ def test_compute_rsa_matches_reference_fixture(dev, golden_dir):
     r2 = vb.compute_rsa({"compare_method": "spearman"}, vb.AlignmentData(**tr), vb.AlignmentData(**te), bootstrap=False,
                         re_extract_fn=re_extract)[0]
     assert calls == [("good", te["stimulus_ids"])] and abs(r2["score"] - nb["score"]) <= 1e-12
-    with pytest.raises(NotImplementedError):
-        vb.compute_rsa({"compare_method": "kendall"}, vb.AlignmentData(**tr), vb.AlignmentData(**te), bootstrap=False)
+    # compare_method = kendall (config-valid, utils.py:518): tau-a for selection, point estimate and replicates
+    kw = dict(bootstrap=True, n_bootstrap=4, seed=3)
+    got = vb.compute_rsa({"compare_method": "kendall"}, vb.AlignmentData(**tr), vb.AlignmentData(**te), **kw)[0]
+    want = orc.rsa_traintest({"compare_method": "kendall"}, orc.Split(**tr), orc.Split(**te), **kw)[0]
+    assert got["layer"] == want["layer"] and abs(got["score"] - want["score"]) <= SCORE_TOL
+    np.testing.assert_allclose(got["bootstrap_scores"], want["bootstrap_scores"], atol=SCORE_TOL, rtol=0)
 
 
 # ------------------------------------------------------------------ full-size properties (no oracle loop)

@@ -51,6 +51,8 @@ SIGNATURES = {
     "vr_rank_fused": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _i64, _i64, _vp, _sz, _vp]),
     "vr_bootstrap_spearman_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "vr_bootstrap_spearman": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _vp, _vp, _sz, _vp]),
+    "vr_kendall_workspace_bytes": (_sz, [_i]),
+    "vr_kendall_tau_a": (_i, [_vp, _vp, _i, _i64, _vp, _i, _vp, _vp, _sz, _vp]),
     "vr_bootstrap_pearson_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "vr_bootstrap_pearson": (_i, [_vp, _i, _vp, _i, _i, _i64, _vp, _i, _vp, _vp, _sz, _vp]),
 }

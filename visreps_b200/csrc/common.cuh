@@ -19,7 +19,7 @@ void count_launch(unsigned n = 1);
 // start/stop event pair; stop() synchronises them and returns per-family device time and
 // kernel-launch counts.  bench.py uses it to time the dominant kernel inside the timed region.
 enum Family {
-  F_MASKS = 0, F_PRESORT, F_KEPT, F_RANK, F_RANK_FUSED, F_PEARSON, F_RDM_CENTER, F_RDM_SYRK, F_RDM_EPILOGUE, F_ROWRANK,
+  F_MASKS = 0, F_PRESORT, F_KEPT, F_RANK, F_RANK_FUSED, F_PEARSON, F_KENDALL, F_RDM_CENTER, F_RDM_SYRK, F_RDM_EPILOGUE, F_ROWRANK,
   F_NUM_FAMILIES
 };
 struct ProfScope {
@@ -126,6 +126,18 @@ __host__ __device__ inline uint32_t run_sbits(uint32_t N) {
   while (b < 32 && (1ull << b) < (unsigned long long)N + 1ull) ++b;
   return b;                 // n <= VR_MAX_STIMULI gives N < 2^29, so at least 3 length bits remain
 }
+// Compact run word, used while the table index fits 20 bits (N < 2^25 pairs):
+//   [ gs : gbits ][ shlo : 6 ][ f1 : 32 - gbits - 6 ]      gs = s >> 5, shlo = 32 - (s & 31), f1 = e - s
+// so that C(s) = cnt[gs] + popc(kept[gs] << shlo) and, when the run ends inside the 32-group (f1 <= shlo),
+// C(e) = cnt[gs] + popc(kept[gs] << (shlo - f1)) from the SAME table entry.  A run too long for the f1
+// field is marked shlo = 0, f1 = (s & 31) + 1 and resolved from the head tables.
+__host__ __device__ inline uint32_t run_gbits(uint32_t N) {
+  const uint32_t G = (N + 31u) / 32u;
+  uint32_t b = 1;
+  while ((1u << b) < G + 1u) ++b;
+  return b;
+}
+__host__ __device__ inline bool run_compact(uint32_t N) { return run_gbits(N) <= 20u; }
 __host__ __device__ inline uint32_t presort_groups(int n) { return (uint32_t)((triu_len(n) + 31) / 32); }
 inline size_t presort_blob_bytes(int n) {
   size_t G = presort_groups(n);

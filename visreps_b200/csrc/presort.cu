@@ -146,10 +146,19 @@ runs_kernel(uint32_t N, uint32_t G, uint32_t n, const __grid_constant__ PresortB
   const uint32_t s = below ? g * 32u + (31u - __clz(below)) : blob.prev_head[g - 1];
   const uint32_t above = H & lanemask_gt();
   const uint32_t e = above ? g * 32u + (__ffs(above) - 1u) : blob.next_head[g + 1];
-  const uint32_t sbits = run_sbits(N);
-  const uint32_t esc = (1u << (32u - sbits)) - 1u;
-  const uint32_t f = min(e - s - 1u, esc);
-  blob.runs[triu_pos(pair_i(wd), pair_j(wd), n)] = s | (f << sbits);
+  uint32_t word;
+  if (run_compact(N)) {
+    const uint32_t gbits = run_gbits(N);
+    const uint32_t fcap = 1u << (32u - gbits - 6u);          // f1 field capacity (>= 64)
+    const uint32_t gs = s >> 5, ls = s & 31u, len = e - s;
+    word = len < fcap ? (gs | ((32u - ls) << gbits) | (len << (gbits + 6u)))
+                      : (gs | ((ls + 1u) << (gbits + 6u)));   // shlo = 0: long run
+  } else {
+    const uint32_t sbits = run_sbits(N);
+    const uint32_t esc = (1u << (32u - sbits)) - 1u;
+    word = s | (min(e - s - 1u, esc) << sbits);
+  }
+  blob.runs[triu_pos(pair_i(wd), pair_j(wd), n)] = word;
 }
 
 // ---- row-wise ordinal ranks ------------------------------------------------------------

@@ -26,6 +26,7 @@
 #include <cstdlib>
 #include <type_traits>
 #include "common.cuh"
+#include "pairmask.cuh"
 
 namespace vr {
 
@@ -63,52 +64,12 @@ __global__ void transpose_masks_kernel(const uint32_t* __restrict__ masks, int R
   maskT[(int64_t)batch * n + i] = w;
 }
 
-// pairbits[r][w]: bit b = canonical pair 32w+b has both stimuli in mask r (0 beyond N).
-// One thread per word; the row is decoded once and then walked.
-__global__ void __launch_bounds__(256)
-pair_mask_kernel(const uint32_t* __restrict__ masks, int R, int n, int W, uint32_t words,
-                 uint32_t* __restrict__ pairbits);
-
 __device__ __forceinline__ uint32_t low_mask(uint32_t bit) { return (1u << bit) - 1u; }  // bit in [0,31]
 // x << k with PTX semantics: k >= 32 gives 0 (C++ leaves that undefined).
 __device__ __forceinline__ uint32_t shl_clamp(uint32_t x, uint32_t k) {
   uint32_t r;
   asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(k));
   return r;
-}
-
-// Row of canonical pair p: largest i with i(2n-i-1)/2 <= p.
-__device__ __forceinline__ uint32_t triu_row(uint32_t p, uint32_t n) {
-  const float b = (float)(2u * n - 1u);
-  float disc = b * b - 8.0f * (float)p;
-  int i = (int)((b - sqrtf(fmaxf(disc, 0.f))) * 0.5f);
-  i = max(0, min(i, (int)n - 2));
-  while (i > 0 && (uint32_t)i * (2u * n - (uint32_t)i - 1u) / 2u > p) --i;
-  while ((uint32_t)(i + 1) * (2u * n - (uint32_t)(i + 1) - 1u) / 2u <= p) ++i;
-  return (uint32_t)i;
-}
-
-__global__ void __launch_bounds__(256)
-pair_mask_kernel(const uint32_t* __restrict__ masks, int R, int n, int W, uint32_t words,
-                 uint32_t* __restrict__ pairbits) {
-  extern __shared__ uint32_t s_m[];
-  const int r = blockIdx.y;
-  for (int w = threadIdx.x; w < W; w += 256) s_m[w] = masks[(int64_t)r * W + w];
-  __syncthreads();
-  const uint32_t N = (uint32_t)triu_len(n);
-  for (uint32_t w = blockIdx.x * 256u + threadIdx.x; w < words; w += gridDim.x * 256u) {
-    uint32_t p = w * 32u, bits = 0;
-    if (p < N) {
-      uint32_t i = triu_row(p, (uint32_t)n);
-      uint32_t j = p - i * (2u * n - i - 1u) / 2u + i + 1u;
-      uint32_t ki = (s_m[i >> 5] >> (i & 31u)) & 1u;
-      for (uint32_t b = 0; b < 32u && p + b < N; ++b) {
-        bits |= (ki & (s_m[j >> 5] >> (j & 31u)) & 1u) << b;
-        if (++j == (uint32_t)n) { ++i; j = i + 1u; ki = (s_m[min(i, (uint32_t)n - 1u) >> 5] >> (i & 31u)) & 1u; }
-      }
-    }
-    pairbits[(int64_t)r * words + w] = bits;
-  }
 }
 
 // Transpose a 32x32 bit matrix held one row per lane (row = lane, column = bit).
@@ -205,7 +166,7 @@ struct RankArgs {
   int64_t out_stride_m;
 };
 
-template <bool kSmemTable, bool kFused, typename Acc>
+template <bool kSmemTable, bool kFused, typename Acc, bool kCompact>
 __global__ void __launch_bounds__(kRankThreads, 1)
 rank_kernel(const __grid_constant__ RankArgs A) {
   extern __shared__ __align__(16) uint32_t smem[];
@@ -223,6 +184,9 @@ rank_kernel(const __grid_constant__ RankArgs A) {
   const uint32_t sbits = run_sbits(N);
   const uint32_t smask = (1u << sbits) - 1u;
   const uint32_t esc = (1u << (32u - sbits)) - 1u;
+  const uint32_t gbits = run_gbits(N);                       // compact run words
+  const uint32_t gmask = (1u << gbits) - 1u;
+  const uint32_t fshift = gbits + 6u;
   const int64_t dev_stride = A.dev_stride;
 
   const int64_t items = (int64_t)A.n_vectors * R;
@@ -284,6 +248,34 @@ rank_kernel(const __grid_constant__ RankArgs A) {
       }
       if (p0 < N) {
         const uint32_t rw[4] = {q.x, q.y, q.z, q.w};
+        if (kCompact) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const uint32_t w = rw[e];
+            const uint32_t gs = w & gmask;
+            const uint32_t shlo = (w >> gbits) & 63u;
+            const uint32_t f1 = w >> fshift;
+            const uint2 ts = table[gs];
+            // C(s) + C(e): both from this entry when the run ends inside the 32-group (95 % of pairs)
+            uint32_t sum = 2u * ts.y + __popc(shl_clamp(ts.x, shlo)) + __popc(shl_clamp(ts.x, shlo - f1));
+            if (f1 > shlo) {
+              uint32_t ls, endpos;
+              if (shlo == 0u) {                              // run longer than the f1 field: head tables
+                ls = f1 - 1u;
+                const uint32_t above = ls == 31u ? 0u : (__ldg(blob.head_bits + gs) >> (ls + 1u));
+                endpos = above ? gs * 32u + ls + (uint32_t)__ffs(above) : __ldg(blob.next_head + gs + 1);
+              } else {
+                ls = 32u - shlo;
+                endpos = gs * 32u + ls + f1;
+              }
+              const uint2 te = table[endpos >> 5];
+              sum = ts.y + __popc(shl_clamp(ts.x, 32u - ls)) + te.y + __popc(shl_clamp(te.x, 32u - (endpos & 31u)));
+            }
+            const int32_t d = ((kw >> e) & 1u) ? (int32_t)sum - (int32_t)Ns : 0;
+            d4[e] = d;
+            acc_ss += (Acc)d * (Acc)d;
+          }
+        } else {
         uint32_t s4[4], e4[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) { s4[e] = rw[e] & smask; e4[e] = s4[e] + (rw[e] >> sbits) + 1u; }
@@ -309,6 +301,7 @@ rank_kernel(const __grid_constant__ RankArgs A) {
           const int32_t d = ((kw >> e) & 1u) ? (int32_t)(lo + hi) - (int32_t)Ns : 0;
           d4[e] = d;
           acc_ss += (Acc)d * (Acc)d;
+        }
         }
       }
       if (kFused) {
@@ -441,37 +434,38 @@ static int launch_count(const BlobList& blobs, int nV, int n, const RankContext&
   return VR_OK;
 }
 
-template <bool kSmem, bool kFused, typename Acc>
+template <bool kSmem, bool kFused, typename Acc, bool kCompact>
 static int launch_rank_variant(const RankArgs& args, int grid, size_t smem, cudaStream_t stream) {
   static bool attr_set = false;
   if (kSmem && !attr_set) {
-    VR_CHECK_CUDA(cudaFuncSetAttribute(rank_kernel<kSmem, kFused, Acc>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    VR_CHECK_CUDA(cudaFuncSetAttribute(rank_kernel<kSmem, kFused, Acc, kCompact>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(kRankSmemTableMax + 8192)));
     attr_set = true;
   }
-  rank_kernel<kSmem, kFused, Acc><<<grid, kRankThreads, smem, stream>>>(args);
+  rank_kernel<kSmem, kFused, Acc, kCompact><<<grid, kRankThreads, smem, stream>>>(args);
   VR_CHECK_LAUNCH();
   return VR_OK;
 }
 
-static int launch_rank(const RankArgs& args, bool fused, cudaStream_t stream) {
+template <bool kFused>
+static int launch_rank_side(const RankArgs& args, cudaStream_t stream) {
   const int n = args.n;
+  const int64_t N = triu_len(n);
   const bool in_smem = rank_table_in_smem(n);
   const size_t smem = rank_smem_bytes(n, in_smem);
   const int64_t items = (int64_t)args.n_vectors * args.R;
   const int grid = (int)(items < kNumSMs ? items : kNumSMs);
-  const bool exact = triu_len(n) <= (1ll << 20);            // N^3 < 2^60: integer accumulation cannot overflow
+  const bool exact = N <= (1ll << 20);                      // N^3 < 2^60: integer accumulation cannot overflow
+  const bool compact = run_compact((uint32_t)N);
+  if (in_smem) return launch_rank_variant<true, kFused, long long, true>(args, grid, smem, stream);   // N <= ~816k
+  if (exact) return launch_rank_variant<false, kFused, long long, true>(args, grid, smem, stream);
+  if (compact) return launch_rank_variant<false, kFused, double, true>(args, grid, smem, stream);
+  return launch_rank_variant<false, kFused, double, false>(args, grid, smem, stream);
+}
+
+static int launch_rank(const RankArgs& args, bool fused, cudaStream_t stream) {
   ProfScope prof(fused ? F_RANK_FUSED : F_RANK, stream);
-  if (in_smem) {
-    if (fused) return exact ? launch_rank_variant<true, true, long long>(args, grid, smem, stream)
-                            : launch_rank_variant<true, true, double>(args, grid, smem, stream);
-    return exact ? launch_rank_variant<true, false, long long>(args, grid, smem, stream)
-                 : launch_rank_variant<true, false, double>(args, grid, smem, stream);
-  }
-  if (fused) return exact ? launch_rank_variant<false, true, long long>(args, grid, smem, stream)
-                          : launch_rank_variant<false, true, double>(args, grid, smem, stream);
-  return exact ? launch_rank_variant<false, false, long long>(args, grid, smem, stream)
-               : launch_rank_variant<false, false, double>(args, grid, smem, stream);
+  return fused ? launch_rank_side<true>(args, stream) : launch_rank_side<false>(args, stream);
 }
 
 // count + rank of nV vectors: materialise (dev/ss) or fused against nM materialised vectors

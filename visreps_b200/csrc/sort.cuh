@@ -25,7 +25,7 @@ inline size_t sort_count_elems(int64_t len, int segments) {
   return (size_t)segments * kRadix * sort_num_tiles(len);
 }
 
-__global__ void __launch_bounds__(kSortThreads)
+static __global__ void __launch_bounds__(kSortThreads)
 tile_count_kernel(const uint32_t* __restrict__ keys, int64_t len, int64_t seg_stride, int shift,
                   uint32_t* __restrict__ counts, int tiles) {
   __shared__ uint32_t hist[kRadix];
@@ -44,7 +44,7 @@ tile_count_kernel(const uint32_t* __restrict__ keys, int64_t len, int64_t seg_st
 }
 
 // Exclusive scan, in place, of each segment's [256][tiles] count table (digit-major).
-__global__ void __launch_bounds__(1024)
+static __global__ void __launch_bounds__(1024)
 scan_counts_kernel(uint32_t* __restrict__ counts, int tiles) {
   __shared__ uint32_t warp_tot[32];
   uint32_t* c = counts + (size_t)blockIdx.x * kRadix * tiles;
@@ -81,7 +81,7 @@ scan_counts_kernel(uint32_t* __restrict__ counts, int tiles) {
   }
 }
 
-__global__ void __launch_bounds__(kSortThreads)
+static __global__ void __launch_bounds__(kSortThreads)
 tile_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                     int64_t len, int64_t seg_stride, int shift,

@@ -185,9 +185,6 @@ def compare_grouped(model: Sequence[PresortedRDM], neural: Sequence[PresortedRDM
     method = method.lower()
     if method not in _METHODS:
         raise ValueError("correlation must be 'Pearson', 'Spearman', or 'Kendall'")
-    if method == "kendall":
-        raise NotImplementedError("Kendall tau-a is not built on the device yet (SURVEY.md section 8f-1); "
-                                  "there is deliberately no CPU fallback")
     n = model[0].n
     if any(p.n != n for p in list(model) + list(neural)):
         raise ValueError("RDMs must share the same 2-D shape")
@@ -199,7 +196,16 @@ def compare_grouped(model: Sequence[PresortedRDM], neural: Sequence[PresortedRDM
             ma, mb = model[a0:a0 + _MAX_GROUP], neural[b0:b0 + _MAX_GROUP]
             full = len(ma) == nA and len(mb) == nB
             part = out if full else torch.empty((len(ma), len(mb), R), dtype=torch.float64, device=dev)
-            if method == "spearman":
+            if method == "kendall":
+                ws = _lib.workspace(lib.vr_kendall_workspace_bytes(n), dev)
+                for ia, a in enumerate(ma):
+                    for ib, b in enumerate(mb):
+                        ra = a.rdm if a.rdm.stride(0) == n else a.rdm.contiguous()
+                        rb = b.rdm if b.rdm.stride(0) == n else b.rdm.contiguous()
+                        _lib.check(lib.vr_kendall_tau_a(ra.data_ptr(), rb.data_ptr(), n, n, masks.data_ptr(), R,
+                                                        part[ia, ib].data_ptr(), ws.data_ptr(), ws.numel(),
+                                                        _lib.stream_ptr()), "vr_kendall_tau_a")
+            elif method == "spearman":
                 pa, pb = _ptr_array([p.blob for p in ma]), _ptr_array([p.blob for p in mb])
                 ws = _lib.workspace(lib.vr_bootstrap_spearman_workspace_bytes(n, len(ma), len(mb), R), dev)
                 _lib.check(lib.vr_bootstrap_spearman(pa, len(ma), pb, len(mb), n, masks.data_ptr(), R, part.data_ptr(),
@@ -386,9 +392,6 @@ def compute_rsa(cfg: Dict, selection: "AlignmentData", evaluation: "AlignmentDat
     # 1. layer selection: all layers against the neural RDM in one grouped device call
     if method not in _METHODS:
         raise ValueError("correlation must be 'Pearson', 'Spearman', or 'Kendall'")
-    if method == "kendall":
-        raise NotImplementedError("compare_method=kendall is not built on the device yet (SURVEY.md section 8f-1); "
-                                  "there is deliberately no CPU fallback")
     dev = _lib.require_cuda()
     neural_sel = _prepare(compute_rdm(selection.neural[sel_idx].to(dev)), method)
     names = list(selection.activations.keys())
@@ -687,8 +690,6 @@ def rsa_grouped(model_features: Sequence[torch.Tensor], neural_responses: Sequen
     method = method.lower()
     if method not in _METHODS:
         raise ValueError("correlation must be 'Pearson', 'Spearman', or 'Kendall'")
-    if method == "kendall":
-        raise NotImplementedError("compare_method=kendall is not built on the device yet (SURVEY.md section 8f-1)")
     dev = _lib.require_cuda()
     n = int(model_features[0].shape[0])
     if any(int(t.shape[0]) != n for t in list(model_features) + list(neural_responses)):
