@@ -6,24 +6,15 @@
 //   rdm_epilogue_kernel sum of K-splits, /d, /(std_i std_j + c), clamp, diag,
 //                       1 - corr, mirrored to the lower triangle              rsa.py:89-92
 //
-// The SYRK is the tcgen05 / TMEM / TMA kernel of syrk_tc.cuh (3xTF32, fp32-accurate).  An fp32
-// CUDA-core SYRK is kept only as a cross-check, selectable with VR_SYRK_IMPL=ffma.
-#include <cstdlib>
+// The SYRK is the tcgen05 / TMEM / TMA kernel of syrk_tc.cuh (3xTF32, fp32-accurate).
 #include "common.cuh"
 #include "syrk_tc.cuh"
 
 namespace vr {
 
-constexpr int kTileMN = 64;   // FFMA SYRK output tile
-constexpr int kTileK = 16;
-
 struct RdmPlan {
-  int n_pad;        // multiple of 128 (covers both the FFMA and the tensor tile grids)
-  int64_t d_pad;    // multiple of 32
-  int splits;       // K-splits
-  int64_t k_per_split;  // multiple of 32
-  int nb;           // 64-row blocks
-  // tensor-core plan
+  int n_pad;        // multiple of 128 (tensor tile rows)
+  int64_t d_pad;    // multiple of 32 (one TMA box row)
   int nb128;        // 128-row blocks
   int kb_total;     // 32-column K blocks
   int kb_per_split;
@@ -34,18 +25,6 @@ inline RdmPlan rdm_plan(int n, int64_t d) {
   RdmPlan p;
   p.n_pad = (int)round_up(n, 128);
   p.d_pad = round_up(d, 32);
-  p.nb = p.n_pad / kTileMN;
-  const int64_t tiles = (int64_t)p.nb * (p.nb + 1) / 2;
-  // aim for >= 4 waves of CTAs, K-splits of at least 512 and at most 4096 columns
-  int64_t want = (4 * kNumSMs * 4 + tiles - 1) / tiles;
-  int64_t max_splits = (p.d_pad + 511) / 512;
-  int64_t min_splits = (p.d_pad + 4095) / 4096;
-  int64_t s = want;
-  if (s > max_splits) s = max_splits;
-  if (s < min_splits) s = min_splits;
-  if (s < 1) s = 1;
-  p.k_per_split = round_up((p.d_pad + s - 1) / s, 32);
-  p.splits = (int)((p.d_pad + p.k_per_split - 1) / p.k_per_split);
   // tensor-core plan: <= 1024 columns per accumulation chain, >= 2 CTAs per SM worth of work if K allows
   p.nb128 = p.n_pad / tc::kBM;
   p.kb_total = (int)(p.d_pad / tc::kBK);
@@ -68,12 +47,12 @@ row_center_kernel(const float* __restrict__ X, int n, int64_t d, int64_t ldx, fl
   __shared__ double s_red[8];
   __shared__ float s_mean;
   const int row = blockIdx.x;
-  // Zlo == nullptr: Z receives the centred fp32 row.  Otherwise Z / Zlo receive the tf32 split
-  // hi = rn_tf32(z), lo = rn_tf32(z - hi)  (z - hi is exact in fp32).
+  // Z / Zlo receive the tf32 split of the centred row: hi = rn_tf32(z), lo = rn_tf32(z - hi)
+  // (z - hi is exact in fp32).
   float* z = Z + (int64_t)row * d_pad;
-  float* zl = Zlo ? Zlo + (int64_t)row * d_pad : nullptr;
+  float* zl = Zlo + (int64_t)row * d_pad;
   if (row >= n) {
-    for (int64_t c = threadIdx.x; c < d_pad; c += 256) { z[c] = 0.f; if (zl) zl[c] = 0.f; }
+    for (int64_t c = threadIdx.x; c < d_pad; c += 256) { z[c] = 0.f; zl[c] = 0.f; }
     return;
   }
   const float* x = X + (int64_t)row * ldx;
@@ -93,16 +72,12 @@ row_center_kernel(const float* __restrict__ X, int n, int64_t d, int64_t ldx, fl
   for (int64_t c = threadIdx.x; c < d_pad; c += 256) {
     float v = 0.f;
     if (c < d) { v = x[c] - mean; acc += (double)v * (double)v; }
-    if (zl) {
-      uint32_t hb, lb;
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
-      const float hi = __uint_as_float(hb);
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(v - hi));
-      z[c] = hi;
-      zl[c] = __uint_as_float(lb);
-    } else {
-      z[c] = v;
-    }
+    uint32_t hb, lb;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+    const float hi = __uint_as_float(hb);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(v - hi));
+    z[c] = hi;
+    zl[c] = __uint_as_float(lb);
   }
   acc = warp_sum(acc);
   __syncthreads();
@@ -114,57 +89,6 @@ row_center_kernel(const float* __restrict__ X, int n, int64_t d, int64_t ldx, fl
     float sd = (float)sqrt(t / (double)d + (double)correction);
     if (sd < correction * 10.f) { sd = 1.f; if (zero_rows) atomicAdd(zero_rows, 1); }
     stdv[row] = sd;
-  }
-}
-
-__device__ __forceinline__ void decode_tile(int t, int nb, int& bi, int& bj) {
-  bi = 0;
-  while (t >= nb - bi) { t -= nb - bi; ++bi; }
-  bj = bi + t;
-}
-
-// partial[split][i][j] for i-block <= j-block.  256 threads, each a 4x4 micro-tile.
-__global__ void __launch_bounds__(256)
-syrk_ffma_kernel(const float* __restrict__ Z, int64_t d_pad, int n_pad, int nb, int64_t k_per_split,
-                 float* __restrict__ partial) {
-  __shared__ float As[kTileK][kTileMN + 4];
-  __shared__ float Bs[kTileK][kTileMN + 4];
-  int bi, bj;
-  decode_tile(blockIdx.x, nb, bi, bj);
-  const int split = blockIdx.y;
-  const int64_t k0 = (int64_t)split * k_per_split;
-  const int64_t k1 = min(d_pad, k0 + k_per_split);
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  // loader mapping: 64 rows x 16 cols = 1024 floats = 256 threads x float4
-  const int lrow = threadIdx.x >> 2, lcol = (threadIdx.x & 3) * 4;
-  const float* a_src = Z + (int64_t)(bi * kTileMN + lrow) * d_pad + lcol;
-  const float* b_src = Z + (int64_t)(bj * kTileMN + lrow) * d_pad + lcol;
-  float acc[4][4] = {};
-  for (int64_t k = k0; k < k1; k += kTileK) {
-    const float4 av = *reinterpret_cast<const float4*>(a_src + k);
-    const float4 bv = *reinterpret_cast<const float4*>(b_src + k);
-    __syncthreads();
-    As[lcol + 0][lrow] = av.x; As[lcol + 1][lrow] = av.y; As[lcol + 2][lrow] = av.z; As[lcol + 3][lrow] = av.w;
-    Bs[lcol + 0][lrow] = bv.x; Bs[lcol + 1][lrow] = bv.y; Bs[lcol + 2][lrow] = bv.z; Bs[lcol + 3][lrow] = bv.w;
-    __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < kTileK; ++kk) {
-      const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
-      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
-      const float b[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-      for (int x = 0; x < 4; ++x)
-#pragma unroll
-        for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(a[x], b[y], acc[x][y]);
-    }
-  }
-  float* out = partial + (int64_t)split * n_pad * n_pad;
-#pragma unroll
-  for (int x = 0; x < 4; ++x) {
-    const int i = bi * kTileMN + ty * 4 + x;
-    float4 v = make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]);
-    *reinterpret_cast<float4*>(out + (int64_t)i * n_pad + bj * kTileMN + tx * 4) = v;
   }
 }
 
@@ -194,9 +118,8 @@ using namespace vr;
 extern "C" size_t vr_rdm_workspace_bytes(int n, int64_t d) {
   if (n < 1 || d < 1) return 256;
   RdmPlan p = rdm_plan(n, d);
-  const int splits = p.splits > p.tc_splits ? p.splits : p.tc_splits;
   return 2 * arena_bytes((size_t)p.n_pad * p.d_pad, 4) + arena_bytes(p.n_pad, 4) +
-         arena_bytes((size_t)splits * p.n_pad * p.n_pad, 4) + 256;
+         arena_bytes((size_t)p.tc_splits * p.n_pad * p.n_pad, 4) + 256;
 }
 
 extern "C" int vr_rdm_pearson_f32(const float* X, int n, int64_t d, int64_t ldx, float correction, float* rdm,
@@ -210,28 +133,21 @@ extern "C" int vr_rdm_pearson_f32(const float* X, int n, int64_t d, int64_t ldx,
     return VR_ERR_WORKSPACE;
   }
   RdmPlan p = rdm_plan(n, d);
-  static const bool use_ffma = [] { const char* e = getenv("VR_SYRK_IMPL"); return e && e[0] == 'f'; }();
   Arena a(ws, ws_bytes);
-  float* Z = a.take<float>((size_t)p.n_pad * p.d_pad);
+  float* Zhi = a.take<float>((size_t)p.n_pad * p.d_pad);
   float* Zlo = a.take<float>((size_t)p.n_pad * p.d_pad);
   float* stdv = a.take<float>(p.n_pad);
-  const int splits = use_ffma ? p.splits : p.tc_splits;
-  float* partial = a.take<float>((size_t)(p.splits > p.tc_splits ? p.splits : p.tc_splits) * p.n_pad * p.n_pad);
+  const int splits = p.tc_splits;
+  float* partial = a.take<float>((size_t)p.tc_splits * p.n_pad * p.n_pad);
   if (zero_var_rows) VR_CHECK_CUDA(cudaMemsetAsync(zero_var_rows, 0, sizeof(int), stream));
   {
     ProfScope prof(F_RDM_CENTER, stream);
-    row_center_kernel<<<p.n_pad, 256, 0, stream>>>(X, n, d, ldx, correction, Z, use_ffma ? nullptr : Zlo, p.d_pad, stdv,
-                                                   zero_var_rows);
+    row_center_kernel<<<p.n_pad, 256, 0, stream>>>(X, n, d, ldx, correction, Zhi, Zlo, p.d_pad, stdv, zero_var_rows);
     VR_CHECK_LAUNCH();
   }
-  if (use_ffma) {
-    ProfScope prof(F_RDM_SYRK, stream);
-    dim3 grid(p.nb * (p.nb + 1) / 2, p.splits);
-    syrk_ffma_kernel<<<grid, 256, 0, stream>>>(Z, p.d_pad, p.n_pad, p.nb, p.k_per_split, partial);
-    VR_CHECK_LAUNCH();
-  } else {
+  {
     CUtensorMap map_hi, map_lo;
-    int rc = tc::make_plane_map(&map_hi, Z, p.n_pad, p.d_pad);
+    int rc = tc::make_plane_map(&map_hi, Zhi, p.n_pad, p.d_pad);
     if (rc != VR_OK) return rc;
     rc = tc::make_plane_map(&map_lo, Zlo, p.n_pad, p.d_pad);
     if (rc != VR_OK) return rc;
