@@ -295,6 +295,28 @@ def test_large_n_global_table_path(dev):
     assert abs(pe - orc.rdm_compare(a.cpu(), b.cpu(), correlation="Pearson")) <= SCORE_TOL
 
 
+def test_things_shape_behaviour_rdm(dev):
+    """BASELINE config 3 shape: 1854 concepts, 66-d behavioural embedding (non-negative) vs model layers.
+    d = 66 is not a multiple of the TMA box; N = 1,717,731 pairs uses the global-table, fp64-accumulator kernels."""
+    rs = np.random.RandomState(41)
+    n = 1854
+    z = rs.standard_normal((n, 20)).astype(np.float32)
+    beh = torch.from_numpy(np.maximum(z @ rs.standard_normal((20, 66)).astype(np.float32), 0))
+    layers = [torch.from_numpy(np.maximum(z @ rs.standard_normal((20, d)).astype(np.float32) + rs.standard_normal((n, d)).astype(np.float32), 0))
+              for d in (96, 513)]
+    rb = vb.compute_rdm(beh.to(dev))
+    assert float((rb.cpu() - orc.rdm(beh)).abs().max()) <= RDM_TOL
+    idx = vrsa.draw_index_sets(n, 2, 42)
+    res = vb.rsa_grouped(layers, [beh], "spearman", n_bootstrap=2, seed=42)
+    assert res["scores"].shape == (2, 1, 2)
+    for i, x in enumerate(layers):
+        ra, rbb = orc.rdm(x), orc.rdm(beh)
+        assert abs(res["point"][i, 0] - orc.rdm_compare(ra, rbb, correlation="Spearman")) <= SCORE_TOL
+        if i == 0:
+            want = orc.bootstrap_compare_with_indices(ra, rbb, "spearman", idx[:1])
+            assert abs(res["scores"][0, 0, 0] - want[0]) <= SCORE_TOL
+
+
 def test_grouped_with_more_than_one_materialised_group(dev):
     """10 model x 9 neural RDMs: the smaller side is materialised in groups of 8, so two groups."""
     rs = np.random.RandomState(21)

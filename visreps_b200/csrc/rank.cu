@@ -30,8 +30,8 @@
 
 namespace vr {
 
-constexpr int kRankThreads = 1024;
-constexpr int kRankWarps = kRankThreads / 32;
+constexpr int kRankThreadsMat = 1024;   // materialise: 64 registers per thread
+constexpr int kRankThreadsFused = 768;  // fused: 85 registers per thread, all 8 materialised loads in flight
 constexpr int kCountThreads = 512;
 constexpr int kCountWarps = kCountThreads / 32;
 constexpr int kMaxVectors = 64;
@@ -167,8 +167,10 @@ struct RankArgs {
 };
 
 template <bool kSmemTable, bool kFused, typename Acc, bool kCompact>
-__global__ void __launch_bounds__(kRankThreads, 1)
+__global__ void __launch_bounds__(kFused ? kRankThreadsFused : kRankThreadsMat, 1)
 rank_kernel(const __grid_constant__ RankArgs A) {
+  constexpr int kRankThreads = kFused ? kRankThreadsFused : kRankThreadsMat;
+  constexpr int kRankWarps = kRankThreads / 32;
   extern __shared__ __align__(16) uint32_t smem[];
   uint2* s_table = reinterpret_cast<uint2*>(smem);
   __shared__ double s_red[kRankWarps][kFuseMax + 1];
@@ -235,10 +237,10 @@ rank_kernel(const __grid_constant__ RankArgs A) {
     if (p0 < N) { q_cur = __ldg(reinterpret_cast<const uint4*>(runs + p0)); kw_cur = __ldg(keptw + (p0 >> 5)); }
     for (; p0 < (uint32_t)dev_stride; p0 += kRankThreads * 4u) {
       int32_t d4[4] = {0, 0, 0, 0};
-      int4 m4[4];
-      if (kFused && p0 < N) {   // first batch of materialised vectors: issued before the ranking work hides their latency
+      int4 m4[kFuseMax];
+      if (kFused && p0 < N) {   // all materialised vectors are requested before the ranking work, which hides their latency
 #pragma unroll
-        for (int a = 0; a < 4; ++a) m4[a] = __ldg(reinterpret_cast<const int4*>(mat + min(a, A.n_mat - 1) * mat_step + p0));
+        for (int a = 0; a < kFuseMax; ++a) m4[a] = __ldg(reinterpret_cast<const int4*>(mat + min(a, A.n_mat - 1) * mat_step + p0));
       }
       const uint4 q = q_cur;
       const uint32_t kw = kw_cur >> (p0 & 31u);              // 4 kept bits (p0 is a multiple of 4)
@@ -307,17 +309,9 @@ rank_kernel(const __grid_constant__ RankArgs A) {
       if (kFused) {
         if (p0 < N) {
 #pragma unroll
-          for (int a = 0; a < 4; ++a)
+          for (int a = 0; a < kFuseMax; ++a)
             if (a < A.n_mat)
               acc[a] += (Acc)d4[0] * (Acc)m4[a].x + (Acc)d4[1] * (Acc)m4[a].y + (Acc)d4[2] * (Acc)m4[a].z + (Acc)d4[3] * (Acc)m4[a].w;
-          if (A.n_mat > 4) {
-#pragma unroll
-            for (int a = 0; a < 4; ++a) m4[a] = __ldg(reinterpret_cast<const int4*>(mat + min(a + 4, A.n_mat - 1) * mat_step + p0));
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-              if (a + 4 < A.n_mat)
-                acc[a + 4] += (Acc)d4[0] * (Acc)m4[a].x + (Acc)d4[1] * (Acc)m4[a].y + (Acc)d4[2] * (Acc)m4[a].z + (Acc)d4[3] * (Acc)m4[a].w;
-          }
         }
       } else {
         *reinterpret_cast<int4*>(out_dev + p0) = make_int4(d4[0], d4[1], d4[2], d4[3]);
@@ -442,7 +436,7 @@ static int launch_rank_variant(const RankArgs& args, int grid, size_t smem, cuda
                                        (int)(kRankSmemTableMax + 8192)));
     attr_set = true;
   }
-  rank_kernel<kSmem, kFused, Acc, kCompact><<<grid, kRankThreads, smem, stream>>>(args);
+  rank_kernel<kSmem, kFused, Acc, kCompact><<<grid, kFused ? kRankThreadsFused : kRankThreadsMat, smem, stream>>>(args);
   VR_CHECK_LAUNCH();
   return VR_OK;
 }
