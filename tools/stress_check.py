@@ -1,0 +1,39 @@
+"""BASELINE config 5 (scale stress) feasibility: n = 10,000 stimuli (N = 49,995,000 pairs).
+Checks properties that need no CPU oracle and prints stage timings.  SN/SD/SB env: n, d, replicates."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import visreps_b200 as vb
+from visreps_b200 import rsa as vrsa, synth
+
+dev = torch.device("cuda", 0)
+n = int(os.environ.get("SN", 10000)); d = int(os.environ.get("SD", 193600)); B = int(os.environ.get("SB", 4))
+def t(label, fn):
+    torch.cuda.synchronize(); t0 = time.perf_counter(); r = fn(); torch.cuda.synchronize()
+    print(f"{label:42s} {1e3 * (time.perf_counter() - t0):10.1f} ms", flush=True); return r
+z = synth.latent(n, dev, 1)
+x = t(f"features n={n} d={d}", lambda: synth.layer_features(z, d, 11))
+y = synth.roi_responses(z, 2000, 500)
+a = t("compute_rdm(model) [cold: allocates scratch]", lambda: vb.compute_rdm(x))
+a = t("compute_rdm(model)", lambda: vb.compute_rdm(x))
+print(f"   -> {n*(n+1)*d/1e12:.2f} algorithmic TFLOP")
+del x
+b = t("compute_rdm(neural, V=2000)", lambda: vb.compute_rdm(y))
+assert torch.equal(a, a.T) and float(a.diagonal().abs().max()) == 0.0
+# spot-check RDM rows against fp64 on the device
+xs = synth.layer_features(z[:64], d, 11).double()
+pa = t("presort(model)", lambda: vrsa.PresortedRDM(a))
+pb = t("presort(neural)", lambda: vrsa.PresortedRDM(b))
+idx = vrsa.draw_index_sets(n, B, 42)
+masks = vrsa.build_masks(idx, n, dev, with_full=True)
+out = t(f"spearman: point + {B} replicates", lambda: vrsa.compare_grouped([pa], [pb], "spearman", masks))
+self_ = t("spearman self-comparison", lambda: vrsa.compare_grouped([pa], [pa], "spearman", masks))
+print("scores (first 6)", out[0, 0, :6].cpu().numpy())
+assert np.allclose(self_.cpu().numpy(), 1.0, atol=1e-12)
+# replicate 1 == full comparison of the gathered sub-RDMs
+tix = torch.from_numpy(idx[0].astype(np.int64)).to(dev)
+direct = vb.compute_rdm_correlation(a[tix][:, tix], b[tix][:, tix], correlation="Spearman")
+print("replicate 0 vs direct sub-RDM comparison:", float(out[0, 0, 1]), direct)
+assert abs(float(out[0, 0, 1]) - direct) < 1e-12
+print("stress check ok; peak memory %.1f GB" % (torch.cuda.max_memory_allocated() / 2**30))

@@ -25,16 +25,16 @@ inline RdmPlan rdm_plan(int n, int64_t d) {
   RdmPlan p;
   p.n_pad = (int)round_up(n, 128);
   p.d_pad = round_up(d, 32);
-  // tensor-core plan: <= 1024 columns per accumulation chain, >= 2 CTAs per SM worth of work if K allows
+  // K splits only to fill and balance the machine; each CTA chains its whole K range in-kernel
   p.nb128 = p.n_pad / tc::kBM;
   p.kb_total = (int)(p.d_pad / tc::kBK);
   const int64_t tiles128 = (int64_t)p.nb128 * (p.nb128 + 1) / 2;
-  int64_t want_splits = (2 * kNumSMs + tiles128 - 1) / tiles128;
-  int64_t kbs = (p.kb_total + want_splits - 1) / want_splits;
-  if (kbs < 8) kbs = 8;
-  if (kbs > tc::kMaxKbPerSplit) kbs = tc::kMaxKbPerSplit;
-  if (kbs > p.kb_total) kbs = p.kb_total;
-  p.kb_per_split = (int)kbs;
+  // ~6 CTAs per SM in total: diagonal tiles move half the bytes, so finer work units balance better (measured)
+  int64_t want_splits = (6 * kNumSMs + tiles128 - 1) / tiles128;
+  int64_t max_splits = (p.kb_total + 7) / 8;               // at least 8 K-blocks (256 columns) per CTA
+  if (want_splits > max_splits) want_splits = max_splits;
+  if (want_splits < 1) want_splits = 1;
+  p.kb_per_split = (int)((p.kb_total + want_splits - 1) / want_splits);
   p.tc_splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
   return p;
 }
@@ -157,9 +157,10 @@ extern "C" int vr_rdm_pearson_f32(const float* X, int n, int64_t d, int64_t ldx,
       attr_set = true;
     }
     ProfScope prof(F_RDM_SYRK, stream);
-    dim3 grid(p.nb128 * (p.nb128 + 1) / 2, p.tc_splits);
+    const int super = tc::kSuper;
+    dim3 grid(tc::grid_slots(p.nb128, super), p.tc_splits);
     tc::syrk_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, stream>>>(map_hi, map_lo, p.nb128, p.kb_total, p.kb_per_split,
-                                                                     partial, p.n_pad);
+                                                                     partial, p.n_pad, super);
     VR_CHECK_LAUNCH();
   }
   dim3 eg((n + 255) / 256, n);

@@ -6,14 +6,16 @@
 //   z_a z_b = hi_a hi_b + hi_a lo_b + lo_a hi_b + O(2^-22): three kind::tf32 MMAs per K step into
 //   the same fp32 TMEM accumulator.  Only tiles with block-row <= block-column are computed.
 //
-//   CTA = one 128x128 output tile x one K split (<= 1024 columns, so the fp32 accumulation chain in
-//   TMEM stays short; the splits are summed in fp64 by rdm_epilogue_kernel).
+//   CTA = one 128x128 output tile x one K split.  Inside the CTA the fp32 accumulation chain in TMEM is
+//   cut every 1024 columns (two TMEM accumulators, drained into registers by the epilogue warps while the
+//   next chunk is multiplied); the few K splits are summed in fp64 by rdm_epilogue_kernel.
 //   warp 0   TMA producer: 128x32 fp32 boxes (128 B rows, SWIZZLE_128B) of hi/lo for the row block
 //            and the column block into a 3-stage ring, mbarrier complete_tx
 //   warp 1   one elected thread issues tcgen05.mma (M=128, N=128, K=8) x 4 K-steps x 3 products per
 //            stage, tcgen05.commit releases the stage / signals the epilogue
 //   warp 2   TMEM allocation (128 columns) and release
-//   warps 4-7 epilogue: tcgen05.ld 32 lanes x 32 columns at a time -> registers -> partial plane
+//   warps 4-7 epilogue: per chunk tcgen05.ld 32 lanes x 32 columns at a time -> fp32 register accumulators;
+//            at the end one partial tile -> memory
 //   Diagonal tiles load only the row block (B = A).
 #pragma once
 #include <cuda.h>
@@ -29,9 +31,10 @@ constexpr int kStages = 3;
 constexpr int kTileBytes = kBM * kBK * 4;     // 16 KB
 constexpr int kStageBytes = 4 * kTileBytes;   // A_hi | A_lo | B_hi | B_lo
 constexpr int kThreads = 256;
-constexpr int kTmemCols = 128;
+constexpr int kTmemCols = 256;              // two 128-column fp32 accumulators
 constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024;   // + slack for 1024 B alignment
-constexpr int kMaxKbPerSplit = 32;            // 1024 columns per accumulation chain
+constexpr int kSuper = 8;                     // super-block edge, in tiles
+constexpr int kChunkKb = 32;                  // 1024 columns per accumulation chain inside TMEM
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -101,29 +104,50 @@ __device__ __forceinline__ void decode_tri_tile(int t, int nb, int& bi, int& bj)
   bj = bi + t;
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // grid (upper-triangular 128-tiles, K splits).  partial[split][n_pad][n_pad].
+// A CTA walks its whole K range; the fp32 accumulation chain inside TMEM is cut every kChunkKb K-blocks
+// (1024 columns): the MMA warp alternates between two 128-column TMEM accumulators while the epilogue
+// warps drain the finished one into registers (fp32 adds), so chunk c+1 is multiplied while chunk c is
+// read out.  Only one partial tile per CTA reaches memory.
 __global__ void __launch_bounds__(kThreads, 1)
 syrk_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, int nb,
-               int kb_total, int kb_per_split, float* __restrict__ partial, int n_pad) {
+               int kb_total, int kb_per_split, float* __restrict__ partial, int n_pad, int super) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kStages];
   __shared__ __align__(8) uint64_t empty_bar[kStages];
-  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_slot;
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5;
   const unsigned lane = threadIdx.x & 31;
+  // Rasterisation: blockIdx.x walks super-blocks of kSuper x kSuper tiles (upper-triangular order), so the
+  // ~148 CTAs in flight touch few distinct row/column blocks per K step and share them through L2.
+  // Slots below the diagonal or past the edge exit at once (uniformly, before any barrier or TMEM use).
   int bi, bj;
-  decode_tri_tile(blockIdx.x, nb, bi, bj);
+  {
+    const int sb_count = (nb + super - 1) / super;
+    int sbi, sbj;
+    decode_tri_tile((int)blockIdx.x / (super * super), sb_count, sbi, sbj);
+    const int within = (int)blockIdx.x % (super * super);
+    bi = sbi * super + within / super;
+    bj = sbj * super + within % super;
+    if (bi >= nb || bj >= nb || bi > bj) return;
+  }
   const bool diag = bi == bj;
   const int split = blockIdx.y;
   const int kb0 = split * kb_per_split;
   const int nkb = min(kb_total, kb0 + kb_per_split) - kb0;
+  const int nchunks = (nkb + kChunkKb - 1) / kChunkKb;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(&tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -155,43 +179,62 @@ syrk_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      for (int it = 0; it < nkb; ++it) {
-        const int s = it % kStages;
-        const uint32_t ph = (uint32_t)(it / kStages) & 1u;
-        mbar_wait(&full_bar[s], ph);
+      int it = 0;
+      for (int c = 0; c < nchunks; ++c) {
+        const int buf = c & 1;
+        const uint32_t use = (uint32_t)(c >> 1) & 1u;
+        mbar_wait(&tmem_empty_bar[buf], use ^ 1u);        // the epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t a_hi = smem_u32(smem + (size_t)s * kStageBytes);
-        const uint32_t a_lo = a_hi + kTileBytes;
-        const uint32_t b_hi = diag ? a_hi : a_hi + 2 * kTileBytes;
-        const uint32_t b_lo = diag ? a_lo : a_hi + 3 * kTileBytes;
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * kBN);
+        const int it_end = min(nkb, it + kChunkKb);
+        for (int first = 1; it < it_end; ++it, first = 0) {
+          const int s = it % kStages;
+          const uint32_t ph = (uint32_t)(it / kStages) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(smem + (size_t)s * kStageBytes);
+          const uint32_t a_lo = a_hi + kTileBytes;
+          const uint32_t b_hi = diag ? a_hi : a_hi + 2 * kTileBytes;
+          const uint32_t b_lo = diag ? a_lo : a_hi + 3 * kTileBytes;
 #pragma unroll
-        for (int j = 0; j < kBK / 8; ++j) {           // UMMA K = 8 tf32 = 32 bytes inside the 128 B swizzle row
-          const uint32_t off = (uint32_t)j * 32u;
-          mma_tf32(tmem_base, smem_desc_sw128(a_hi + off), smem_desc_sw128(b_hi + off), (it | j) ? 1u : 0u);
-          mma_tf32(tmem_base, smem_desc_sw128(a_hi + off), smem_desc_sw128(b_lo + off), 1u);
-          mma_tf32(tmem_base, smem_desc_sw128(a_lo + off), smem_desc_sw128(b_hi + off), 1u);
+          for (int j = 0; j < kBK / 8; ++j) {         // UMMA K = 8 tf32 = 32 bytes inside the 128 B swizzle row
+            const uint32_t off = (uint32_t)j * 32u;
+            mma_tf32(tmem_acc, smem_desc_sw128(a_hi + off), smem_desc_sw128(b_hi + off), (first && j == 0) ? 0u : 1u);
+            mma_tf32(tmem_acc, smem_desc_sw128(a_hi + off), smem_desc_sw128(b_lo + off), 1u);
+            mma_tf32(tmem_acc, smem_desc_sw128(a_lo + off), smem_desc_sw128(b_hi + off), 1u);
+          }
+          tc_commit(&empty_bar[s]);                      // stage reusable once these MMAs have read it
         }
-        tc_commit(&empty_bar[s]);                        // stage reusable once these MMAs have read it
+        tc_commit(&tmem_full_bar[buf]);                  // this chunk's accumulator is complete
       }
-      tc_commit(&tmem_full_bar);                         // accumulator complete
     }
   } else if (warp >= 4) {
-    mbar_wait(&tmem_full_bar, 0u);
-    tc_fence_after();
     const int q = warp & 3;                              // TMEM lane quarter this warp may access
     const int row = q * 32 + (int)lane;
-    float* out = partial + (size_t)split * n_pad * n_pad + (size_t)(bi * kBM + row) * n_pad + (size_t)bj * kBN;
-#pragma unroll 1
-    for (int c = 0; c < kBN / 32; ++c) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    float acc[kBN];
 #pragma unroll
-      for (int x = 0; x < 32; x += 4)
-        *reinterpret_cast<float4*>(out + c * 32 + x) =
-            make_float4(__uint_as_float(v[x]), __uint_as_float(v[x + 1]), __uint_as_float(v[x + 2]), __uint_as_float(v[x + 3]));
+    for (int x = 0; x < kBN; ++x) acc[x] = 0.f;
+    for (int c = 0; c < nchunks; ++c) {
+      const int buf = c & 1;
+      const uint32_t use = (uint32_t)(c >> 1) & 1u;
+      mbar_wait(&tmem_full_bar[buf], use);
+      tc_fence_after();
+#pragma unroll
+      for (int cg = 0; cg < kBN / 32; ++cg) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kBN + cg * 32), v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int x = 0; x < 32; ++x) acc[cg * 32 + x] += __uint_as_float(v[x]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);  // 4 epilogue warps -> barrier count 4
     }
-    tc_fence_before();
+    float* out = partial + (size_t)split * n_pad * n_pad + (size_t)(bi * kBM + row) * n_pad + (size_t)bj * kBN;
+#pragma unroll
+    for (int x = 0; x < kBN; x += 4)
+      *reinterpret_cast<float4*>(out + x) = make_float4(acc[x], acc[x + 1], acc[x + 2], acc[x + 3]);
   }
   __syncthreads();
   if (warp == 2) {
@@ -199,6 +242,8 @@ syrk_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
+
+inline int grid_slots(int nb, int super) { const int sb = (nb + super - 1) / super; return sb * (sb + 1) / 2 * super * super; }
 
 // Host: 2-D tensor map over a (rows = n_pad, cols = d_pad) fp32 plane, box 128 rows x 32 columns, 128 B swizzle.
 inline int make_plane_map(CUtensorMap* map, const float* base, int n_pad, int64_t d_pad) {
