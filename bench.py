@@ -293,6 +293,14 @@ def run_ours(args):
                     "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": per_launch_ms,
                     "definition": "4*N_sub bytes per ranked vector (SURVEY 8d: 8*N_sub per replicate comparison = two ranked vectors) "
                                   "x vectors*(B+1) ranked per launch"}
+        try:   # DRAM bytes per launch of this kernel from the committed ncu capture, if it is for this workload
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            wl = tr.get("workload", {})
+            if (wl.get("n"), wl.get("nA"), wl.get("nB"), wl.get("masks")) == (n, nA, nB, B + 1) and roofline["kernel"] in tr:
+                roofline["traffic"] = tr[roofline["kernel"]]["dram_bytes_per_launch"]
+                roofline["traffic_source"] = "ncu --set full, profiles/r1_rank_kernels_nsd_full.txt"
+        except Exception:
+            pass
     elif dom == "rdm_syrk":
         flops = sum(n * (n + 1) * t.shape[1] for t in X + Y)
         tf_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))

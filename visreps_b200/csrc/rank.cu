@@ -65,6 +65,19 @@ __global__ void transpose_masks_kernel(const uint32_t* __restrict__ masks, int R
 }
 
 __device__ __forceinline__ uint32_t low_mask(uint32_t bit) { return (1u << bit) - 1u; }  // bit in [0,31]
+// acc += d . m  over 4 int32 pairs, exact: four 32x32->64 multiply-adds (IMAD.WIDE).
+__device__ __forceinline__ long long mad_wide(int a, int b, long long c) {
+  long long r;
+  asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ long long mac4(long long acc, const int32_t (&d)[4], const int4& m) {
+  return mad_wide(d[3], m.w, mad_wide(d[2], m.z, mad_wide(d[1], m.y, mad_wide(d[0], m.x, acc))));
+}
+// fp64 accumulator (very long vectors): the four products are summed exactly in int64 (< 2^60), then folded in
+__device__ __forceinline__ double mac4(double acc, const int32_t (&d)[4], const int4& m) {
+  return acc + (double)mac4(0ll, d, m);
+}
 // x << k with PTX semantics: k >= 32 gives 0 (C++ leaves that undefined).
 __device__ __forceinline__ uint32_t shl_clamp(uint32_t x, uint32_t k) {
   uint32_t r;
@@ -221,7 +234,12 @@ rank_kernel(const __grid_constant__ RankArgs A) {
 
     int32_t* __restrict__ out_dev = kFused ? nullptr : A.dev + ((int64_t)v * R + r) * dev_stride;
     const int32_t* __restrict__ mat = kFused ? A.mat_dev + (int64_t)r * dev_stride : nullptr;
-    const int64_t mat_step = (int64_t)R * dev_stride;        // between materialised vectors
+    // materialised vectors as int4 streams; 32-bit offsets (host guarantees n_mat * R * dev_stride < 2^34)
+    const int4* __restrict__ mat4 = reinterpret_cast<const int4*>(mat);
+    const uint32_t mat_step4 = (uint32_t)(((int64_t)R * dev_stride) >> 2);
+    uint32_t moff[kFuseMax];                                 // vectors past n_mat alias the last one (results unused)
+#pragma unroll
+    for (int a = 0; a < kFuseMax; ++a) moff[a] = kFused ? (uint32_t)min(a, A.n_mat - 1) * mat_step4 + threadIdx.x : 0u;
     const uint32_t* __restrict__ runs = blob.runs;
     const uint32_t* __restrict__ keptw = A.pairbits + (int64_t)r * (dev_stride >> 5);
     Acc acc_ss = 0;
@@ -240,7 +258,7 @@ rank_kernel(const __grid_constant__ RankArgs A) {
       int4 m4[kFuseMax];
       if (kFused && p0 < N) {   // all materialised vectors are requested before the ranking work, which hides their latency
 #pragma unroll
-        for (int a = 0; a < kFuseMax; ++a) m4[a] = __ldg(reinterpret_cast<const int4*>(mat + min(a, A.n_mat - 1) * mat_step + p0));
+        for (int a = 0; a < kFuseMax; ++a) m4[a] = __ldg(mat4 + (moff[a] + ((p0 >> 2) - threadIdx.x)));
       }
       const uint4 q = q_cur;
       const uint32_t kw = kw_cur >> (p0 & 31u);              // 4 kept bits (p0 is a multiple of 4)
@@ -309,9 +327,7 @@ rank_kernel(const __grid_constant__ RankArgs A) {
       if (kFused) {
         if (p0 < N) {
 #pragma unroll
-          for (int a = 0; a < kFuseMax; ++a)
-            if (a < A.n_mat)
-              acc[a] += (Acc)d4[0] * (Acc)m4[a].x + (Acc)d4[1] * (Acc)m4[a].y + (Acc)d4[2] * (Acc)m4[a].z + (Acc)d4[3] * (Acc)m4[a].w;
+          for (int a = 0; a < kFuseMax; ++a) acc[a] = mac4(acc[a], d4, m4[a]);
         }
       } else {
         *reinterpret_cast<int4*>(out_dev + p0) = make_int4(d4[0], d4[1], d4[2], d4[3]);
@@ -535,6 +551,7 @@ extern "C" int vr_rank_fused(const void* const* blobs, int nF, int n, const void
   VR_REQUIRE(blobs && ctx && mat_dev && mat_ss && out, "vr_rank_fused: null pointer");
   VR_REQUIRE(n >= 2 && n <= VR_MAX_STIMULI && R >= 1 && nF >= 1 && nF <= kMaxVectors, "vr_rank_fused: bad sizes n=%d nF=%d R=%d", n, nF, R);
   VR_REQUIRE(nM >= 1 && nM <= kFuseMax, "vr_rank_fused: nM=%d outside [1, %d]", nM, kFuseMax);
+  VR_REQUIRE((int64_t)nM * R * vr_dev_stride(n) < (1ll << 34), "vr_rank_fused: nM * R * stride = %lld exceeds the 2^34-element addressing window; use fewer replicates per call", (long long)nM * R * vr_dev_stride(n));
   if (!ws || ws_bytes < vr_rank_workspace_bytes(n, nF, R)) { set_error("vr_rank_fused: workspace %zu < %zu", ws_bytes, vr_rank_workspace_bytes(n, nF, R)); return VR_ERR_WORKSPACE; }
   RankContext c = rank_context_view(const_cast<void*>(ctx), n, R);
   return rank_stage(blobs, nF, n, c, R, true, nullptr, nullptr, nullptr, mat_dev, mat_ss, nM, out, out_stride_fused,
@@ -621,7 +638,12 @@ extern "C" int vr_bootstrap_spearman(const void* const* A, int nA, const void* c
   int64_t chunk = (int64_t)((ws_bytes - plan.fixed) / plan.per_rep);
   if (chunk > R) chunk = R;
   if (chunk > 65535) chunk = 65535;
+  {                                                         // 32-bit int4 offsets into the materialised group
+    const int64_t cap = ((1ll << 34) - 1) / ((int64_t)group * vr_dev_stride(n));
+    if (chunk > cap) chunk = cap;
+  }
   if (chunk < R) chunk = chunk / 32 * 32;                   // keep replicate batches of 32 whole
+  if (chunk < 1) { set_error("vr_bootstrap_spearman: n too large for one replicate chunk"); return VR_ERR_UNSUPPORTED; }
   const int stage = group > nF ? group : nF;
   Arena a(ws, ws_bytes);
   void* ctx = a.take<char>(rank_context_bytes(n, chunk));
