@@ -54,6 +54,19 @@ struct ProfScope {
     }                                                                                    \
   } while (0)
 
+// Opt-in dynamic shared memory is a per-device function attribute: `done` is a per-kernel bit set of the
+// devices already configured (a process may drive several GPUs).
+template <typename Kernel>
+inline cudaError_t ensure_dynamic_smem(Kernel kernel, int bytes, unsigned long long* done) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 64 && ((*done >> dev) & 1ull)) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && dev < 64) *done |= 1ull << dev;
+  return e;
+}
+
 // ---- sizes ---------------------------------------------------------------------------
 __host__ __device__ inline int64_t triu_len(int64_t n) { return n * (n - 1) / 2; }
 __host__ __device__ inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }

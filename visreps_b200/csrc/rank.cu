@@ -256,17 +256,18 @@ rank_kernel(const __grid_constant__ RankArgs A) {
     for (; p0 < (uint32_t)dev_stride; p0 += kRankThreads * 4u) {
       int32_t d4[4] = {0, 0, 0, 0};
       int4 m4[kFuseMax];
-      if (kFused && p0 < N) {   // all materialised vectors are requested before the ranking work, which hides their latency
+      const uint4 q = q_cur;
+      const uint32_t kw = kw_cur >> (p0 & 31u);              // 4 kept bits (p0 is a multiple of 4)
+      const bool any_kept = p0 < N && (kw & 0xFu) != 0u;      // a dropped stimulus' row: all four pairs are out
+      if (kFused && any_kept) {   // all materialised vectors are requested before the ranking work, which hides their latency
 #pragma unroll
         for (int a = 0; a < kFuseMax; ++a) m4[a] = __ldg(mat4 + (moff[a] + ((p0 >> 2) - threadIdx.x)));
       }
-      const uint4 q = q_cur;
-      const uint32_t kw = kw_cur >> (p0 & 31u);              // 4 kept bits (p0 is a multiple of 4)
       {
         const uint32_t pn = p0 + kRankThreads * 4u;
         if (pn < N) { q_cur = __ldg(reinterpret_cast<const uint4*>(runs + pn)); kw_cur = __ldg(keptw + (pn >> 5)); }
       }
-      if (p0 < N) {
+      if (any_kept) {
         const uint32_t rw[4] = {q.x, q.y, q.z, q.w};
         if (kCompact) {
 #pragma unroll
@@ -325,7 +326,7 @@ rank_kernel(const __grid_constant__ RankArgs A) {
         }
       }
       if (kFused) {
-        if (p0 < N) {
+        if (any_kept) {
 #pragma unroll
           for (int a = 0; a < kFuseMax; ++a) acc[a] = mac4(acc[a], d4, m4[a]);
         }
@@ -431,12 +432,9 @@ static int launch_count(const BlobList& blobs, int nV, int n, const RankContext&
   *tables = a.take<uint2>((size_t)nV * R * Gs);
   *seg_tot = a.take<uint32_t>((size_t)nV * R * kCountWarps);
   if (!a.ok) { set_error("rank workspace too small for the count tables"); return VR_ERR_WORKSPACE; }
-  static bool attr_set = false;
+  static unsigned long long attr_done = 0;
   const size_t smem = (size_t)n * 4;
-  if (!attr_set && smem > 40 * 1024) {
-    VR_CHECK_CUDA(cudaFuncSetAttribute(count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_set = true;
-  }
+  if (smem > 40 * 1024) VR_CHECK_CUDA(ensure_dynamic_smem(count_kernel, 160 * 1024, &attr_done));
   ProfScope prof(F_KEPT, stream);
   dim3 grid((R + 31) / 32, nV);
   count_kernel<<<grid, kCountThreads, smem, stream>>>(blobs, n, ctx.maskT, R, *tables, Gs, *seg_tot);
@@ -446,12 +444,8 @@ static int launch_count(const BlobList& blobs, int nV, int n, const RankContext&
 
 template <bool kSmem, bool kFused, typename Acc, bool kCompact>
 static int launch_rank_variant(const RankArgs& args, int grid, size_t smem, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (kSmem && !attr_set) {
-    VR_CHECK_CUDA(cudaFuncSetAttribute(rank_kernel<kSmem, kFused, Acc, kCompact>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(kRankSmemTableMax + 8192)));
-    attr_set = true;
-  }
+  static unsigned long long attr_done = 0;
+  if (kSmem) VR_CHECK_CUDA(ensure_dynamic_smem(rank_kernel<kSmem, kFused, Acc, kCompact>, (int)(kRankSmemTableMax + 8192), &attr_done));
   rank_kernel<kSmem, kFused, Acc, kCompact><<<grid, kFused ? kRankThreadsFused : kRankThreadsMat, smem, stream>>>(args);
   VR_CHECK_LAUNCH();
   return VR_OK;

@@ -151,11 +151,8 @@ extern "C" int vr_rdm_pearson_f32(const float* X, int n, int64_t d, int64_t ldx,
     if (rc != VR_OK) return rc;
     rc = tc::make_plane_map(&map_lo, Zlo, p.n_pad, p.d_pad);
     if (rc != VR_OK) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
-      VR_CHECK_CUDA(cudaFuncSetAttribute(tc::syrk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes));
-      attr_set = true;
-    }
+    static unsigned long long attr_done = 0;
+    VR_CHECK_CUDA(ensure_dynamic_smem(tc::syrk_tc_kernel, (int)tc::kSmemBytes, &attr_done));
     ProfScope prof(F_RDM_SYRK, stream);
     const int super = tc::kSuper;
     dim3 grid(tc::grid_slots(p.nb128, super), p.tc_splits);
