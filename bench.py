@@ -292,7 +292,11 @@ def run_ours(args):
                     "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": per_launch_ms,
                     "definition": "4*N_sub bytes per ranked vector (SURVEY 8d: 8*N_sub per replicate comparison = two ranked vectors) "
-                                  "x vectors*(B+1) ranked per launch"}
+                                  "x vectors*(B+1) ranked per launch",
+                    "note": "conservative unit: work sharing lets one launch finish nA*nB*(B+1) replicate comparisons from "
+                            "(nA+nB)*(B+1) rankings; per finished comparison (8*N_sub each) the same launch would read "
+                            f"{(nA * nB * (B + 1) * 8.0 * N_sub) / (per_launch_ms * 1e-3) / 1e9:.0f} GB/s. ncu: the kernel is instruction-issue bound "
+                            "(65 % issue-active, DRAM 18 %), not HBM bound."}
         try:   # DRAM bytes per launch of this kernel from the committed ncu capture, if it is for this workload
             tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
             wl = tr.get("workload", {})

@@ -317,6 +317,31 @@ def test_things_shape_behaviour_rdm(dev):
             assert abs(res["scores"][0, 0, 0] - want[0]) <= SCORE_TOL
 
 
+def test_replicate_chunking_with_a_small_workspace(dev):
+    """vr_bootstrap_spearman processes the replicates in chunks when the caller's workspace is small:
+    same scores as one pass."""
+    import ctypes as C
+    from visreps_b200 import _lib
+    lib = _lib.load()
+    x, y = cases.pair_inputs("p64")
+    n, R = 64, 150
+    a, b = vrsa.PresortedRDM(vb.compute_rdm(x.to(dev))), vrsa.PresortedRDM(vb.compute_rdm(y.to(dev)))
+    masks = vrsa.build_masks(vrsa.draw_index_sets(n, R - 1, 42), n, dev, with_full=True)
+    full = vrsa.compare_grouped([a], [b], "spearman", masks)
+    small_bytes = lib.vr_bootstrap_spearman_workspace_bytes(n, 1, 1, 64)       # room for 64 of the 150 replicates
+    assert small_bytes < lib.vr_bootstrap_spearman_workspace_bytes(n, 1, 1, R)
+    ws = torch.empty(small_bytes, dtype=torch.uint8, device=dev)
+    out = torch.full((1, 1, R), -7.0, dtype=torch.float64, device=dev)
+    pa, pb = (C.c_void_p * 1)(a.blob.data_ptr()), (C.c_void_p * 1)(b.blob.data_ptr())
+    _lib.check(lib.vr_bootstrap_spearman(pa, 1, pb, 1, n, masks.data_ptr(), R, out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                         _lib.stream_ptr()), "vr_bootstrap_spearman")
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(out.cpu().numpy(), full.cpu().numpy())
+    # a workspace below the minimum is refused with a message, nothing is launched
+    rc = lib.vr_bootstrap_spearman(pa, 1, pb, 1, n, masks.data_ptr(), R, out.data_ptr(), ws.data_ptr(), 1024, _lib.stream_ptr())
+    assert rc == _lib.VR_ERR_WORKSPACE and b"workspace" in lib.vr_last_error_string()
+
+
 def test_grouped_with_more_than_one_materialised_group(dev):
     """10 model x 9 neural RDMs: the smaller side is materialised in groups of 8, so two groups."""
     rs = np.random.RandomState(21)
