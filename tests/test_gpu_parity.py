@@ -342,6 +342,25 @@ def test_replicate_chunking_with_a_small_workspace(dev):
     assert rc == _lib.VR_ERR_WORKSPACE and b"workspace" in lib.vr_last_error_string()
 
 
+def test_very_large_n_paths_agree(dev):
+    """n = 3700 (N = 6.8 M pairs, global-table kernels, fp64 accumulators): a replicate must equal the full
+    comparison of the gathered sub-RDMs (N = 5.5 M), and self-comparison must be 1 (no CPU loop at this size)."""
+    g = torch.Generator(device=dev).manual_seed(3)
+    n = 3700
+    z = torch.randn(n, 32, device=dev, generator=g)
+    a = vb.compute_rdm(torch.relu(z @ torch.randn(32, 256, device=dev, generator=g) + torch.randn(n, 256, device=dev, generator=g)))
+    b = vb.compute_rdm(z @ torch.randn(32, 100, device=dev, generator=g) + 2 * torch.randn(n, 100, device=dev, generator=g))
+    idx = vrsa.draw_index_sets(n, 2, 42)
+    res = vb.bootstrap_rdm_correlation_grouped([a], [b], "spearman", index_sets=idx)
+    for r in range(2):
+        t = torch.from_numpy(idx[r].astype(np.int64)).to(dev)
+        direct = vb.compute_rdm_correlation(a[t][:, t], b[t][:, t], correlation="Spearman")
+        assert abs(direct - res["scores"][0, 0, r]) <= 1e-12
+    self_s = vb.bootstrap_rdm_correlation_grouped([a], [a], "spearman", index_sets=idx)
+    np.testing.assert_allclose(self_s["scores"], 1.0, atol=1e-12)
+    assert 0.0 < res["point"][0, 0] < 1.0
+
+
 def test_grouped_with_more_than_one_materialised_group(dev):
     """10 model x 9 neural RDMs: the smaller side is materialised in groups of 8, so two groups."""
     rs = np.random.RandomState(21)
