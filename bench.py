@@ -16,6 +16,7 @@ step (weak scaling; value = all ranks' replicates / max-over-ranks time).
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -226,6 +227,10 @@ def run_ours(args):
     clocks = ClockSampler(local_rank) if (rank == 0 and not os.environ.get('VR_BENCH_NO_CLOCKS')) else None
     if clocks is not None:
         time.sleep(1.5)
+    # the imports leave ~1.5 M long-lived Python objects; a full collection of that heap costs ~34 ms here, more
+    # than a whole step.  Park them in the permanent generation so later collections only see the steps' garbage.
+    gc.collect()
+    gc.freeze()
     for _ in range(args.warmup):
         step_device()
     ms_dev, wall_dev, prof, launches, res = timed(step_device, args.steps, profile=True)

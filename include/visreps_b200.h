@@ -112,7 +112,16 @@ int vr_presort_triu_batch_f32(const float* const* rdms_host, int count, int n, i
  * mt_pos are RandomState.get_state()[1:3], updated in place so the generator can be handed back
  * with set_state().  out is a HOST (B, m) int32 array, draw order preserved. */
 int vr_host_draw_subsamples(uint32_t* mt_key, int* mt_pos, int n, int m, int B, int32_t* out);
+/* HOST function: the same stream, but emitting only each draw's n-bit membership mask (the kept set is
+ * the complement of the shuffle's last n-m slots, final after n-m swap steps; the other steps only
+ * consume the generator).  Writes replicates [b_begin, b_end) to the HOST array masks
+ * ((b_end-b_begin), vr_mask_words(n)); the generator is advanced through all B draws. */
+int vr_host_draw_subsample_masks(uint32_t* mt_key, int* mt_pos, int n, int m, int B, int b_begin, int b_end,
+                                 uint32_t* masks);
 int vr_mask_words(int n);
+/* Device copy of host-built masks; host_masks must be page-locked (it is read by the kernel, not by a
+ * copy engine, so it never waits behind bulk host->device transfers). */
+int vr_fetch_masks(const uint32_t* host_masks, int R, int n, uint32_t* masks, vr_stream_t stream);
 int vr_build_masks(const int32_t* idx, int R, int m, int n, uint32_t* masks, vr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------

@@ -70,3 +70,60 @@ def test_ranking_algorithm_equals_scipy_average_ranks(levels):
         assert Ns == kept.sum()
         np.testing.assert_array_equal(dev[kept], orc.rank2x(v[kept]) - (Ns + 1))
         assert not dev[~kept].any()
+
+
+@pytest.mark.parametrize("n,B", [(1, 3), (2, 4), (3, 5), (10, 7), (33, 20), (64, 9), (100, 50), (1000, 40), (1854, 6)])
+def test_mask_only_draw_matches_the_index_draw(n, B):
+    """vr_host_draw_subsample_masks == bit masks of rng.choice(n, int(0.9 n), replace=False) draws, and
+    leaves the generator exactly where numpy's loop leaves it (evals.py:356-364)."""
+    from visreps_b200 import rsa as vrsa
+    m = int(n * 0.9)
+    ref_rng = np.random.RandomState(42)
+    want = np.zeros((B, (n + 31) // 32 * 32), dtype=bool)
+    for b in range(B):
+        want[b, ref_rng.choice(n, size=m, replace=False)] = True
+    want_words = np.packbits(want, axis=1, bitorder="little").view(np.uint32)
+    rng = np.random.RandomState(42)
+    got = vrsa.draw_subsample_masks(n, B, rng=rng)
+    assert len(got) == B
+    np.testing.assert_array_equal(got.words.numpy().view(np.uint32), want_words)
+    assert rng.randint(0, 2**31 - 1) == ref_rng.randint(0, 2**31 - 1)       # generators still in step
+    # a rank's share: same rows, same final generator state
+    rng2 = np.random.RandomState(42)
+    lo, hi = B // 3, B - B // 4
+    part = vrsa.draw_subsample_masks(n, B, rng=rng2, replicate_range=(lo, hi))
+    np.testing.assert_array_equal(part.words.numpy().view(np.uint32), want_words[lo:hi])
+    rng3 = np.random.RandomState(42)
+    vrsa.draw_subsample_masks(n, B, rng=rng3, replicate_range=(lo, hi))
+    rng4 = np.random.RandomState(42)
+    vrsa.draw_index_sets(n, B, rng=rng4)
+    assert np.array_equal(rng3.get_state()[1], rng4.get_state()[1]) and rng3.get_state()[2] == rng4.get_state()[2]
+
+
+def test_mask_only_draw_from_a_generator_in_mid_stream():
+    from visreps_b200 import rsa as vrsa
+    a, b = np.random.RandomState(7), np.random.RandomState(7)
+    a.standard_normal(1001); b.standard_normal(1001)          # odd count: leaves a cached gaussian and a mid-block position
+    a.choice(500, 77, replace=False); b.choice(500, 77, replace=False)
+    got = vrsa.draw_subsample_masks(300, 25, rng=a)
+    want = np.zeros((25, 320), dtype=bool)
+    for r in range(25):
+        want[r, b.choice(300, size=270, replace=False)] = True
+    np.testing.assert_array_equal(got.words.numpy().view(np.uint32), np.packbits(want, axis=1, bitorder="little").view(np.uint32))
+    assert a.standard_normal() == b.standard_normal()
+
+
+@pytest.mark.parametrize("b", [1, 2, 3, 10, 40, 41, 100, 999, 1000, 1001])
+def test_percentile_ci_is_numpy_percentile(b):
+    """evals.py:371-372 / rsa.py:262-263 use np.percentile(scores, [2.5, 97.5]); ours must be the same bits."""
+    from visreps_b200.rsa import percentile_ci
+    rs = np.random.RandomState(b)
+    x = rs.standard_normal((5, 4, b))
+    x[0, 0, :] = 1.0
+    if b > 3:
+        x[1, 1, 2] = np.nan
+    want = np.percentile(x, [2.5, 97.5], axis=2)
+    lo, hi = percentile_ci(x)
+    assert np.array_equal(want[0], lo, equal_nan=True) and np.array_equal(want[1], hi, equal_nan=True)
+    lo1, hi1 = percentile_ci(x[2, 3])
+    assert float(lo1) == np.percentile(x[2, 3], 2.5) and float(hi1) == np.percentile(x[2, 3], 97.5)

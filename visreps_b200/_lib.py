@@ -40,6 +40,8 @@ SIGNATURES = {
     "vr_host_draw_subsamples": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "vr_mask_words": (_i, [_i]),
     "vr_build_masks": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "vr_host_draw_subsample_masks": (_i, [_vp, C.POINTER(C.c_int), _i, _i, _i, _i, _i, _vp]),
+    "vr_fetch_masks": (_i, [_vp, _i, _i, _vp, _vp]),
     "vr_dev_stride": (_i64, [_i]),
     "vr_subsample_rank_workspace_bytes": (_sz, [_i, _i]),
     "vr_subsample_rank": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),

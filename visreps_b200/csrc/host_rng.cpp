@@ -75,3 +75,60 @@ extern "C" int vr_host_draw_subsamples(uint32_t* mt_key, int* mt_pos, int n, int
   *mt_pos = pos;
   return VR_OK;
 }
+
+// Same stream, but only what the device needs: the n-bit membership mask of each draw.  The kept set of
+// `permutation(n)[:m]` is the complement of the shuffle's last n-m slots, and those are final after the
+// first n-m swap steps (i = n-1 .. m); the remaining m-1 steps only have to consume the generator
+// exactly as numpy does, which needs no array at all: per 32-bit output, `i -= ((w & mask) <= i)`.
+// Replicates outside [b_begin, b_end) (another rank's share) are consumed without any swaps.
+// masks: HOST ((b_end - b_begin), vr_mask_words(n)) uint32.
+extern "C" int vr_host_draw_subsample_masks(uint32_t* mt_key, int* mt_pos, int n, int m, int B, int b_begin, int b_end,
+                                            uint32_t* masks) {
+  VR_REQUIRE(mt_key && mt_pos, "vr_host_draw_subsample_masks: null pointer");
+  VR_REQUIRE(n >= 1 && m >= 0 && m <= n && B >= 0 && *mt_pos >= 0 && *mt_pos <= 624 && b_begin >= 0 && b_begin <= b_end && b_end <= B,
+             "vr_host_draw_subsample_masks: bad arguments n=%d m=%d B=%d range=[%d,%d) pos=%d", n, m, B, b_begin, b_end, *mt_pos);
+  VR_REQUIRE(masks || b_begin == b_end, "vr_host_draw_subsample_masks: null mask buffer");
+  MT g{mt_key, *mt_pos};
+  uint32_t tempered[624];
+  int pos = g.pos;
+  temper_range(g.key, tempered, pos);
+  const int W = (n + 31) / 32;
+  std::vector<int32_t> arr((size_t)n);
+  for (int b = 0; b < B; ++b) {
+    const bool wanted = b >= b_begin && b < b_end && m > 0;
+    uint32_t i = (uint32_t)n - 1;
+    if (wanted) {
+      for (int k = 0; k < n; ++k) arr[k] = k;
+      for (; i >= (uint32_t)m && i >= 1; --i) {                    // the slots that end up dropped
+        const uint32_t mask = 0xffffffffu >> __builtin_clz(i);
+        uint32_t j;
+        do {
+          if (pos == 624) { mt_refill(g); temper_range(g.key, tempered, 0); pos = 0; }
+          j = tempered[pos++] & mask;
+        } while (j > i);
+        const int32_t t = arr[i]; arr[i] = arr[j]; arr[j] = t;
+      }
+    }
+    while (i >= 1) {                                               // consume-only steps, one mask range at a time
+      const uint32_t mask = 0xffffffffu >> __builtin_clz(i);
+      const uint32_t lo = (mask >> 1) + 1;                         // mask is constant for i in [lo, mask]
+      while (i >= lo) {
+        if (pos == 624) { mt_refill(g); temper_range(g.key, tempered, 0); pos = 0; }
+        int room = 624 - pos;
+        const uint32_t* w = tempered + pos;
+        int k = 0;
+        for (; k < room && i >= lo; ++k) i -= ((w[k] & mask) <= i) ? 1u : 0u;
+        pos += k;
+      }
+    }
+    if (b >= b_begin && b < b_end) {
+      uint32_t* row = masks + (size_t)(b - b_begin) * W;
+      if (m == 0) { for (int k = 0; k < W; ++k) row[k] = 0u; continue; }
+      for (int k = 0; k < W; ++k) row[k] = 0xffffffffu;
+      if (n % 32) row[W - 1] = (1u << (n % 32)) - 1u;
+      for (int k = m; k < n; ++k) row[arr[k] >> 5] &= ~(1u << (arr[k] & 31));
+    }
+  }
+  *mt_pos = pos;
+  return VR_OK;
+}

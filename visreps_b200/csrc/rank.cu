@@ -515,6 +515,25 @@ extern "C" int vr_build_masks(const int32_t* idx, int R, int m, int n, uint32_t*
   return VR_OK;
 }
 
+// Host-built masks (vr_host_draw_subsample_masks) -> device, read by the SMs straight from pinned host
+// memory: 4*R*W bytes, never queued behind bulk transfers on the copy engines.
+__global__ void fetch_masks_kernel(const uint32_t* __restrict__ src, int64_t count, uint32_t* __restrict__ dst) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < count) dst[t] = src[t];
+}
+
+extern "C" int vr_fetch_masks(const uint32_t* host_masks, int R, int n, uint32_t* masks, vr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  VR_REQUIRE(masks && (host_masks || R == 0), "vr_fetch_masks: null pointer");
+  VR_REQUIRE(R >= 0 && n >= 1 && n <= VR_MAX_STIMULI, "vr_fetch_masks: bad sizes R=%d n=%d", R, n);
+  const int64_t count = (int64_t)R * vr_mask_words(n);
+  if (count == 0) return VR_OK;
+  ProfScope prof(F_MASKS, stream);
+  fetch_masks_kernel<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(host_masks, count, masks);
+  VR_CHECK_LAUNCH();
+  return VR_OK;
+}
+
 extern "C" int64_t vr_dev_stride(int n) { return n >= 2 ? round_up(triu_len(n), 32) : 32; }
 
 // ---- staged API ---------------------------------------------------------------------------------

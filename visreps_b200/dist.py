@@ -63,5 +63,5 @@ def rsa_grouped_sharded(model_features: Sequence[torch.Tensor], neural_responses
         return res
     dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
     scores = gather_replicate_scores(torch.from_numpy(res["scores"]).to(dev), n_bootstrap, group).cpu().numpy()
-    return {"point": res["point"], "scores": scores,
-            "ci_low": np.percentile(scores, 2.5, axis=2), "ci_high": np.percentile(scores, 97.5, axis=2)}
+    ci_low, ci_high = rsa.percentile_ci(scores)
+    return {"point": res["point"], "scores": scores, "ci_low": ci_low, "ci_high": ci_high}

@@ -117,13 +117,19 @@ def build_masks(index_sets: Optional[np.ndarray], n: int, device: torch.device, 
     """
     lib = _lib.load()
     w = lib.vr_mask_words(n)
-    b = 0 if index_sets is None else int(index_sets.shape[0])
+    b = 0 if index_sets is None else len(index_sets)
     masks = torch.empty((b + (1 if with_full else 0), w), dtype=torch.int32, device=device)
     if with_full:
         masks[0].fill_(-1)
         if n % 32:
             masks[0, w - 1:].fill_((1 << (n % 32)) - 1)
-    if b:
+    if b and isinstance(index_sets, HostMasks):
+        if index_sets.n != n:
+            raise ValueError("masks were drawn for a different number of stimuli")
+        sub = masks[1:] if with_full else masks
+        _lib.check(lib.vr_fetch_masks(index_sets.words.data_ptr(), b, n, sub.data_ptr(), _lib.stream_ptr()), "vr_fetch_masks")
+        _keep_alive(index_sets.words)
+    elif b:
         idx_np = np.ascontiguousarray(index_sets, dtype=np.int32)
         if idx_np.size and (int(idx_np.min()) < 0 or int(idx_np.max()) >= n):
             raise ValueError("bootstrap index out of range")
@@ -169,6 +175,71 @@ def draw_index_sets(n: int, n_bootstrap: int, seed: int = 42, rng: Optional[np.r
                "vr_host_draw_subsamples")
     rng.set_state((state[0], key, pos.value, state[3], state[4]))
     return out
+
+
+def percentile_ci(scores: np.ndarray, lo: float = 2.5, hi: float = 97.5) -> Tuple[np.ndarray, np.ndarray]:
+    """`np.percentile(scores, [lo, hi], axis=-1)` (default 'linear' method) bit for bit -- the CI of
+    evals.py:371-372 / rsa.py:262-263 -- from one vectorised sort of the last axis instead of NumPy's
+    generic quantile machinery (which costs ~4 ms for 64 x 1000 scores, on the critical path of a step)."""
+    scores = np.asarray(scores, dtype=np.float64)
+    b = scores.shape[-1]
+    if b == 0:
+        nan = np.full(scores.shape[:-1], np.nan)
+        return nan, nan.copy()
+    srt = np.sort(scores, axis=-1)                      # NaNs last; a row with any NaN yields NaN, as NumPy does
+    bad = np.isnan(srt[..., -1])
+    out = []
+    for q in (lo, hi):
+        virt = q / 100.0 * (b - 1)
+        k = int(np.floor(virt))
+        t = virt - k
+        lower, upper = srt[..., k], srt[..., min(k + 1, b - 1)]
+        diff = upper - lower
+        val = upper - diff * (1 - t) if t >= 0.5 else lower + diff * t          # numpy's _lerp
+        out.append(np.where(bad, np.nan, val))
+    return out[0], out[1]
+
+
+class HostMasks:
+    """Page-locked (B, W) uint32 membership masks drawn on the host (row b = kept stimuli of draw b)."""
+
+    def __init__(self, words: torch.Tensor, n: int):
+        self.words, self.n = words, n
+
+    def __len__(self) -> int:
+        return int(self.words.shape[0])
+
+
+def draw_subsample_masks(n: int, n_bootstrap: int, seed: int = 42, rng: Optional[np.random.RandomState] = None,
+                         replicate_range: Optional[Tuple[int, int]] = None) -> HostMasks:
+    """The index draws of `draw_index_sets`, delivered as membership masks only (what the device needs):
+    same generator stream, same final generator state, but each shuffle is carried out only for the
+    int(0.1 n)+ slots that end up dropped while the rest of its draws are merely consumed, so the host
+    is off the critical path ~3x sooner.  `replicate_range` keeps only that slice of the draws (a rank's
+    share, visreps_b200/dist.py) -- the generator still advances through all of them."""
+    rng = np.random.RandomState(seed) if rng is None else rng
+    m = int(n * SUBSAMPLE_FRACTION)
+    lib = _lib.load()
+    b0, b1 = (0, n_bootstrap) if replicate_range is None else (int(replicate_range[0]), int(replicate_range[1]))
+    b0, b1 = max(0, min(b0, n_bootstrap)), max(0, min(b1, n_bootstrap))
+    b1 = max(b0, b1)
+    w = lib.vr_mask_words(n)
+    words = torch.empty((b1 - b0, w), dtype=torch.int32, pin_memory=torch.cuda.is_available())
+    if n_bootstrap == 0:
+        return HostMasks(words, n)
+    state = rng.get_state()
+    if state[0] != "MT19937" or n < 1:
+        idx = np.stack([rng.choice(n, size=m, replace=False) for _ in range(n_bootstrap)])[b0:b1]
+        bits = np.zeros((b1 - b0, w * 32), dtype=bool)
+        np.put_along_axis(bits, idx.astype(np.int64), True, axis=1)
+        words.copy_(torch.from_numpy(np.packbits(bits, axis=1, bitorder="little").view(np.int32).reshape(b1 - b0, w)))
+        return HostMasks(words, n)
+    key = np.ascontiguousarray(state[1], dtype=np.uint32).copy()
+    pos = C.c_int(int(state[2]))
+    _lib.check(lib.vr_host_draw_subsample_masks(key.ctypes.data, C.byref(pos), n, m, n_bootstrap, b0, b1, words.data_ptr()),
+               "vr_host_draw_subsample_masks")
+    rng.set_state((state[0], key, pos.value, state[3], state[4]))
+    return HostMasks(words, n)
 
 
 def _ptr_array(tensors: Sequence[torch.Tensor]):
@@ -347,8 +418,8 @@ def bootstrap_rdm_correlation_grouped(model_rdms: Sequence, neural_rdms: Sequenc
     A, B = both[:len(model_rdms)], both[len(model_rdms):]
     n = A[0].n
     if index_sets is None:
-        index_sets = draw_index_sets(n, n_bootstrap, seed, rng)
-    if replicate_range is not None:
+        index_sets = draw_subsample_masks(n, n_bootstrap, seed, rng, replicate_range)
+    elif replicate_range is not None:
         index_sets = index_sets[replicate_range[0]:replicate_range[1]]
     masks = build_masks(index_sets, n, dev, with_full=True)
     out = compare_grouped(A, B, method, masks).cpu().numpy()
@@ -360,7 +431,8 @@ def bootstrap_rdm_correlation(model_rdm, neural_rdm, method: str, n_bootstrap: i
     (run_reconstruction.py:137-158) and its inlined twins (evals.py:355-373, :506-522)."""
     res = bootstrap_rdm_correlation_grouped([model_rdm], [neural_rdm], method, n_bootstrap, seed)
     scores = res["scores"][0, 0]
-    return (float(res["point"][0, 0]), float(np.percentile(scores, 2.5)), float(np.percentile(scores, 97.5)),
+    ci_low, ci_high = percentile_ci(scores)
+    return (float(res["point"][0, 0]), float(ci_low), float(ci_high),
             scores.tolist())
 
 
@@ -420,7 +492,7 @@ def compute_rsa(cfg: Dict, selection: "AlignmentData", evaluation: "AlignmentDat
     # 3. point estimate + bootstrap in one grouped call (mask 0 = all stimuli)
     idx = None
     if bootstrap:
-        idx = draw_index_sets(n_test, n_bootstrap, rng=rng)
+        idx = draw_subsample_masks(n_test, n_bootstrap, rng=rng)
     if n_test <= 1:
         point, scores = float("nan"), np.full(n_bootstrap if bootstrap else 0, np.nan)
     else:
@@ -431,7 +503,7 @@ def compute_rsa(cfg: Dict, selection: "AlignmentData", evaluation: "AlignmentDat
     result = {"layer": best_layer, "compare_method": method, "score": point, "ci_low": None, "ci_high": None,
               "analysis": "rsa", "layer_selection_scores": selection_scores}
     if bootstrap:
-        ci_low, ci_high = float(np.percentile(scores, 2.5)), float(np.percentile(scores, 97.5))
+        ci_low, ci_high = (float(v) for v in percentile_ci(scores))
         result["ci_low"], result["ci_high"] = ci_low, ci_high
         result["bootstrap_scores"] = scores.tolist()
     if verbose:
@@ -687,10 +759,17 @@ def rsa_grouped(model_features: Sequence[torch.Tensor], neural_responses: Sequen
     percentile CI (evals.py:371-372).
     Returns host arrays: point (nA, nB), scores (nA, nB, B) in draw order, ci_low / ci_high (nA, nB).
     """
+    with _no_gc():
+        return _rsa_grouped(model_features, neural_responses, method, bootstrap, n_bootstrap, seed, correction,
+                            replicate_range, index_sets)
+
+
+def _rsa_grouped(model_features, neural_responses, method, bootstrap, n_bootstrap, seed, correction, replicate_range, index_sets):
     method = method.lower()
     if method not in _METHODS:
         raise ValueError("correlation must be 'Pearson', 'Spearman', or 'Kendall'")
     dev = _lib.require_cuda()
+    _mark("enter")
     n = int(model_features[0].shape[0])
     if any(int(t.shape[0]) != n for t in list(model_features) + list(neural_responses)):
         raise ValueError("all inputs must have the same number of stimuli")
@@ -699,8 +778,7 @@ def rsa_grouped(model_features: Sequence[torch.Tensor], neural_responses: Sequen
     def draw():
         if not bootstrap:
             return None
-        idx = draw_index_sets(n, n_bootstrap, seed)
-        return idx if replicate_range is None else idx[replicate_range[0]:replicate_range[1]]
+        return draw_subsample_masks(n, n_bootstrap, seed, replicate_range=replicate_range)
 
     if index_sets is not None and replicate_range is not None:
         index_sets = index_sets[replicate_range[0]:replicate_range[1]]
@@ -726,14 +804,15 @@ def rsa_grouped(model_features: Sequence[torch.Tensor], neural_responses: Sequen
     host.copy_(out_dev, non_blocking=True)
     flags_host = flags.cpu()            # synchronises the stream: results are complete after this
     torch.cuda.current_stream().synchronize()
+    _mark("synced")
     nz = int(flags_host.sum())
     if nz:
         logger.warning("%d rows have ~zero variance across %d RDMs", nz, nA + nB)
     out = host.numpy()
     res = {"point": out[:, :, 0].copy(), "scores": out[:, :, 1:].copy()}
     if bootstrap and res["scores"].shape[2] > 0:
-        res["ci_low"] = np.percentile(res["scores"], 2.5, axis=2)
-        res["ci_high"] = np.percentile(res["scores"], 97.5, axis=2)
+        res["ci_low"], res["ci_high"] = percentile_ci(res["scores"])
+    _mark("exit")
     return res
 
 
@@ -744,6 +823,30 @@ def _pipeline_fits(n: int, nA: int, nB: int, R: int, dev: torch.device) -> bool:
     n_mat = min(nA, nB)
     need = n_mat * R * (lib.vr_dev_stride(n) * 4 + 8) + lib.vr_rank_context_bytes(n, R) + \
         lib.vr_rank_workspace_bytes(n, max(min(n_mat, lib.vr_rank_fuse_max()), max(nA, nB)), R)
-    free, _total = torch.cuda.mem_get_info(dev)
-    cached = torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
-    return need < 0.6 * (free + cached)
+    key = (n, nA, nB, R, dev.index)
+    hit = _fit_cache.get(key)
+    if hit is None:      # cudaMemGetInfo costs 0.2-1.5 ms: asked once per problem shape, not once per call
+        free, _total = torch.cuda.mem_get_info(dev)
+        cached = torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
+        hit = _fit_cache[key] = need < 0.6 * (free + cached)
+    return hit
+
+
+_fit_cache: Dict[tuple, bool] = {}
+
+
+class _no_gc:
+    """The enqueue phase of a step is a few hundred microseconds of host work that gates ~25 ms of device
+    work; a generational collection landing in it (tens of ms on a large heap) stalls the whole step.
+    Collection is deferred until the step's results are back."""
+
+    def __enter__(self):
+        import gc
+        self._was = gc.isenabled()
+        gc.disable()
+
+    def __exit__(self, *exc):
+        if self._was:
+            import gc
+            gc.enable()
+        return False
