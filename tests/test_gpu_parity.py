@@ -475,3 +475,43 @@ def test_nsd_shape_properties(dev):
     np.testing.assert_allclose(swapped, s, atol=1e-15)
     # (5) scores are plausible and spread around the point estimate
     assert abs(np.median(s) - res["point"][0, 0]) < 0.02 and s.std() > 0
+
+
+def test_tied_and_tie_free_vectors_in_one_launch(dev):
+    """Vectors without ties take the 2 C(s) + 1 sweep, vectors with ties the general one; which is which is decided
+    on the device from the presort header, so one grouped call may hold both kinds on either side."""
+    n, B = 130, 9
+    N = n * (n - 1) // 2
+    rs = np.random.RandomState(77)
+
+    def tied(levels, seed):
+        return cases.vector_to_rdm(cases.tied_vectors(N, levels, seed)[0], n)
+
+    def smooth(seed):
+        return orc.rdm(torch.from_numpy(np.random.RandomState(seed).standard_normal((n, 50)).astype(np.float32)))
+
+    one_tie = smooth(5).clone()
+    one_tie[3, 7] = one_tie[7, 3] = one_tie[90, 120]; one_tie[120, 90] = one_tie[90, 120]      # a single tied pair
+    models = [smooth(1), tied(5, 2), smooth(3), one_tie, tied(2000, 4)]
+    neurals = [tied(9, 6), smooth(7), smooth(8)]
+    idx = orc.draw_subsamples(n, B, 42)
+    res = vb.bootstrap_rdm_correlation_grouped(models, neurals, "spearman", n_bootstrap=B, seed=42)
+    for i, m in enumerate(models):
+        for j, q in enumerate(neurals):
+            want = orc.bootstrap_compare_with_indices(m, q, "spearman", idx)
+            np.testing.assert_allclose(res["scores"][i, j], want, atol=SCORE_TOL, rtol=0)
+            assert abs(res["point"][i, j] - orc.rdm_compare(m, q, correlation="Spearman")) <= SCORE_TOL
+    # ranks and the sum of squares of a tie-free vector (closed form on the device) are bit-exact
+    masks = vrsa.build_masks(idx, n, dev, with_full=True)
+    for m in (models[0], models[3]):
+        devv, ss, nk = vrsa.subsample_rank(m.to(dev), masks)
+        devv = devv.cpu().numpy().astype(np.int64)
+        v = orc.triu_vector(m)
+        iu = np.triu_indices(n, 1)
+        for r in range(B + 1):
+            keep = np.ones(n, bool) if r == 0 else np.isin(np.arange(n), idx[r - 1])
+            kp = keep[iu[0]] & keep[iu[1]]
+            Ns = int(kp.sum())
+            np.testing.assert_array_equal(devv[r][kp] + (Ns + 1), orc.rank2x(v[kp]))
+            assert not devv[r][~kp].any()
+            assert float(ss[r]) == float((devv[r] ** 2).sum())

@@ -139,18 +139,28 @@ __host__ __device__ inline uint32_t run_sbits(uint32_t N) {
   while (b < 32 && (1ull << b) < (unsigned long long)N + 1ull) ++b;
   return b;                 // n <= VR_MAX_STIMULI gives N < 2^29, so at least 3 length bits remain
 }
-// Compact run word, used while the table index fits 20 bits (N < 2^25 pairs):
-//   [ gs : gbits ][ shlo : 6 ][ f1 : 32 - gbits - 6 ]      gs = s >> 5, shlo = 32 - (s & 31), f1 = e - s
-// so that C(s) = cnt[gs] + popc(kept[gs] << shlo) and, when the run ends inside the 32-group (f1 <= shlo),
-// C(e) = cnt[gs] + popc(kept[gs] << (shlo - f1)) from the SAME table entry.  A run too long for the f1
-// field is marked shlo = 0, f1 = (s & 31) + 1 and resolved from the head tables.
+// Compact run word, used while the table index fits 16 bits (N <= 2,097,120 pairs, n <= 2048):
+//   [ 000 ][ gs : 16 ][ cross : 1 ][ she : 6 ][ shlo : 6 ]
+// for the run [s, e) of equal values that holds the pair:  gs = s >> 5, shlo = 32 - (s & 31), and the end e is
+// described relative to the same table entry: cross = 0 when e lies in group gs (she = 32 - (e & 31)) or is
+// exactly the next group boundary (she = 0: every bit of the group counts); cross = 1 when e lies inside
+// group gs + 1.  With table entries {kept word, kept count before the group},
+//     C(s) = cnt[gs] + popc(kept[gs] << shlo),      C(e) = cnt[gs + cross] + popc(kept[gs + cross] << she)
+// with no data-dependent branch.  The low field is the BYTE offset of the 8-byte entry and shlo sits in the
+// top bits, so each is one instruction away.  A run that ends beyond group gs + 1 (longer than 32) is marked
+// shlo = 0 with she = (s & 31) + 1 and resolved from the head tables.  A vector without ties (header
+// n_runs == N) has e = s + 1 everywhere: C(s) + C(e) = 2 C(s) + 1 for a kept pair.
 __host__ __device__ inline uint32_t run_gbits(uint32_t N) {
   const uint32_t G = (N + 31u) / 32u;
   uint32_t b = 1;
   while ((1u << b) < G + 1u) ++b;
   return b;
 }
-__host__ __device__ inline bool run_compact(uint32_t N) { return run_gbits(N) <= 20u; }
+__host__ __device__ inline bool run_compact(uint32_t N) { return run_gbits(N) <= 16u; }
+constexpr uint32_t kRunOffMask = 0x7FFF8u;     // gs << 3
+constexpr uint32_t kRunCrossBit = 1u << 19;
+constexpr uint32_t kRunSheShift = 20u;
+constexpr uint32_t kRunShloShift = 26u;
 __host__ __device__ inline uint32_t presort_groups(int n) { return (uint32_t)((triu_len(n) + 31) / 32); }
 inline size_t presort_blob_bytes(int n) {
   size_t G = presort_groups(n);

@@ -141,18 +141,19 @@ runs_kernel(uint32_t N, uint32_t G, uint32_t n, const __grid_constant__ PresortB
   const uint32_t k = g * 32u + lane;
   const uint32_t wd = blob.stream[k];
   const uint32_t H = blob.head_bits[g];
-  if (k >= N) { blob.runs[k] = 0u; return; }        // canonical padding
+  if (k >= N) { blob.runs[k] = run_compact(N) ? 32u << kRunShloShift : 0u; return; }   // canonical padding (never kept, never a long run)
   const uint32_t below = H & lanemask_le();
   const uint32_t s = below ? g * 32u + (31u - __clz(below)) : blob.prev_head[g - 1];
   const uint32_t above = H & lanemask_gt();
   const uint32_t e = above ? g * 32u + (__ffs(above) - 1u) : blob.next_head[g + 1];
   uint32_t word;
   if (run_compact(N)) {
-    const uint32_t gbits = run_gbits(N);
-    const uint32_t fcap = 1u << (32u - gbits - 6u);          // f1 field capacity (>= 64)
-    const uint32_t gs = s >> 5, ls = s & 31u, len = e - s;
-    word = len < fcap ? (gs | ((32u - ls) << gbits) | (len << (gbits + 6u)))
-                      : (gs | ((ls + 1u) << (gbits + 6u)));   // shlo = 0: long run
+    const uint32_t gs = s >> 5, ls = s & 31u, ge = e >> 5, le = e & 31u;
+    const uint32_t head = (gs << 3) | ((32u - ls) << kRunShloShift);
+    if (ge == gs) word = head | ((32u - le) << kRunSheShift);                       // le > ls: she in 1..31
+    else if (ge == gs + 1u && le == 0u) word = head;                                // she = 0: the whole group
+    else if (ge == gs + 1u) word = head | kRunCrossBit | ((32u - le) << kRunSheShift);
+    else word = (gs << 3) | ((ls + 1u) << kRunSheShift);                            // shlo = 0: long run
   } else {
     const uint32_t sbits = run_sbits(N);
     const uint32_t esc = (1u << (32u - sbits)) - 1u;

@@ -78,6 +78,9 @@ __device__ __forceinline__ long long mac4(long long acc, const int32_t (&d)[4], 
 __device__ __forceinline__ double mac4(double acc, const int32_t (&d)[4], const int4& m) {
   return acc + (double)mac4(0ll, d, m);
 }
+// acc += d * d: one IMAD.WIDE for the exact accumulator
+__device__ __forceinline__ long long square_acc(long long acc, int d) { return mad_wide(d, d, acc); }
+__device__ __forceinline__ double square_acc(double acc, int d) { return acc + (double)d * (double)d; }
 // x << k with PTX semantics: k >= 32 gives 0 (C++ leaves that undefined).
 __device__ __forceinline__ uint32_t shl_clamp(uint32_t x, uint32_t k) {
   uint32_t r;
@@ -179,9 +182,10 @@ struct RankArgs {
   int64_t out_stride_m;
 };
 
-template <bool kSmemTable, bool kFused, typename Acc, bool kCompact>
+template <bool kSmemTable, bool kFused, typename Acc, bool kCompact, bool kUntied>
 __global__ void __launch_bounds__(kFused ? kRankThreadsFused : kRankThreadsMat, 1)
 rank_kernel(const __grid_constant__ RankArgs A) {
+  static_assert(kCompact || !kUntied, "the tie-free sweep reads compact run words");
   constexpr int kRankThreads = kFused ? kRankThreadsFused : kRankThreadsMat;
   constexpr int kRankWarps = kRankThreads / 32;
   extern __shared__ __align__(16) uint32_t smem[];
@@ -199,16 +203,28 @@ rank_kernel(const __grid_constant__ RankArgs A) {
   const uint32_t sbits = run_sbits(N);
   const uint32_t smask = (1u << sbits) - 1u;
   const uint32_t esc = (1u << (32u - sbits)) - 1u;
-  const uint32_t gbits = run_gbits(N);                       // compact run words
-  const uint32_t gmask = (1u << gbits) - 1u;
-  const uint32_t fshift = gbits + 6u;
   const int64_t dev_stride = A.dev_stride;
 
-  const int64_t items = (int64_t)A.n_vectors * R;
+  // This instantiation takes the vectors of its kind: tie-free ones (header n_runs == N, decided on the device by
+  // the presort) go to the kUntied sweep, the others to the general one; the host launches both.
+  __shared__ int s_vec[kMaxVectors];
+  __shared__ int s_nvec;
+  if (threadIdx.x == 0) {
+    int c = 0;
+    for (int v = 0; v < A.n_vectors; ++v) {
+      const bool tie_free = kCompact && __ldg(&static_cast<const PresortHeader*>(A.blobs.p[v])->n_runs) == N;
+      if (tie_free == kUntied) s_vec[c++] = v;
+    }
+    s_nvec = c;
+  }
+  __syncthreads();
+  const int n_vec = s_nvec;
+
+  const int64_t items = (int64_t)n_vec * R;
   for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
     // materialise: vector-major (CTAs share the vector's `runs` stream); fused: replicate-major
-    const int v = kFused ? (int)(item % A.n_vectors) : (int)(item / R);
-    const int r = kFused ? (int)(item / A.n_vectors) : (int)(item % R);
+    const int v = s_vec[kFused ? (int)(item % n_vec) : (int)(item / R)];
+    const int r = kFused ? (int)(item / n_vec) : (int)(item % R);
     PresortView blob = presort_view(const_cast<void*>(A.blobs.p[v]), n);
     const int64_t tix = (int64_t)(A.table_base + v) * R + r;
     uint2* __restrict__ g_table = A.tables + tix * Gs;
@@ -247,91 +263,112 @@ rank_kernel(const __grid_constant__ RankArgs A) {
 #pragma unroll
     for (int a = 0; a < kFuseMax; ++a) acc[a] = 0;
 
+    // A vector without ties has run length 1 everywhere, so C(s) + C(e) = 2 C(s) + 1 for every kept pair:
+    // one table entry, one shift, one popc -- and its sum of squares is the closed form N_r (N_r^2 - 1) / 3.
+    const char* __restrict__ table_bytes = reinterpret_cast<const char*>(table);
+
     // software pipeline: the run words and kept bits of the NEXT step are in flight while this one is ranked
     const uint32_t esc_word = esc << sbits;                  // a run word >= esc_word carries the escape code
-    uint32_t p0 = threadIdx.x * 4u;
-    uint4 q_cur = make_uint4(0u, 0u, 0u, 0u);
-    uint32_t kw_cur = 0u;
-    if (p0 < N) { q_cur = __ldg(reinterpret_cast<const uint4*>(runs + p0)); kw_cur = __ldg(keptw + (p0 >> 5)); }
-    for (; p0 < (uint32_t)dev_stride; p0 += kRankThreads * 4u) {
-      int32_t d4[4] = {0, 0, 0, 0};
-      int4 m4[kFuseMax];
-      const uint4 q = q_cur;
-      const uint32_t kw = kw_cur >> (p0 & 31u);              // 4 kept bits (p0 is a multiple of 4)
-      const bool any_kept = p0 < N && (kw & 0xFu) != 0u;      // a dropped stimulus' row: all four pairs are out
-      if (kFused && any_kept) {   // all materialised vectors are requested before the ranking work, which hides their latency
+    {
+      uint32_t p0 = threadIdx.x * 4u;
+      uint4 q_cur = make_uint4(0u, 0u, 0u, 0u);
+      uint32_t kw_cur = 0u;
+      if (p0 < N) { q_cur = __ldg(reinterpret_cast<const uint4*>(runs + p0)); kw_cur = __ldg(keptw + (p0 >> 5)); }
+      for (; p0 < (uint32_t)dev_stride; p0 += kRankThreads * 4u) {
+        int32_t d4[4] = {0, 0, 0, 0};
+        int4 m4[kFuseMax];
+        const uint4 q = q_cur;
+        const uint32_t kw = kw_cur >> (p0 & 31u);              // 4 kept bits (p0 is a multiple of 4)
+        const bool any_kept = p0 < N && (kw & 0xFu) != 0u;      // a dropped stimulus' row: all four pairs are out
+        if (kFused && any_kept) {   // all materialised vectors are requested before the ranking work, which hides their latency
 #pragma unroll
-        for (int a = 0; a < kFuseMax; ++a) m4[a] = __ldg(mat4 + (moff[a] + ((p0 >> 2) - threadIdx.x)));
-      }
-      {
-        const uint32_t pn = p0 + kRankThreads * 4u;
-        if (pn < N) { q_cur = __ldg(reinterpret_cast<const uint4*>(runs + pn)); kw_cur = __ldg(keptw + (pn >> 5)); }
-      }
-      if (any_kept) {
-        const uint32_t rw[4] = {q.x, q.y, q.z, q.w};
-        if (kCompact) {
+          for (int a = 0; a < kFuseMax; ++a) m4[a] = __ldg(mat4 + (moff[a] + ((p0 >> 2) - threadIdx.x)));
+        }
+        {
+          const uint32_t pn = p0 + kRankThreads * 4u;
+          if (pn < N) { q_cur = __ldg(reinterpret_cast<const uint4*>(runs + pn)); kw_cur = __ldg(keptw + (pn >> 5)); }
+        }
+        if (any_kept) {
+          const uint32_t rw[4] = {q.x, q.y, q.z, q.w};
+          if (kCompact && kUntied) {
+            const int32_t bias = 1 - (int32_t)Ns;
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const uint32_t w = rw[e];
-            const uint32_t gs = w & gmask;
-            const uint32_t shlo = (w >> gbits) & 63u;
-            const uint32_t f1 = w >> fshift;
-            const uint2 ts = table[gs];
-            // C(s) + C(e): both from this entry when the run ends inside the 32-group (95 % of pairs)
-            uint32_t sum = 2u * ts.y + __popc(shl_clamp(ts.x, shlo)) + __popc(shl_clamp(ts.x, shlo - f1));
-            if (f1 > shlo) {
-              uint32_t ls, endpos;
-              if (shlo == 0u) {                              // run longer than the f1 field: head tables
-                ls = f1 - 1u;
-                const uint32_t above = ls == 31u ? 0u : (__ldg(blob.head_bits + gs) >> (ls + 1u));
-                endpos = above ? gs * 32u + ls + (uint32_t)__ffs(above) : __ldg(blob.next_head + gs + 1);
-              } else {
-                ls = 32u - shlo;
-                endpos = gs * 32u + ls + f1;
-              }
-              const uint2 te = table[endpos >> 5];
-              sum = ts.y + __popc(shl_clamp(ts.x, 32u - ls)) + te.y + __popc(shl_clamp(te.x, 32u - (endpos & 31u)));
+            for (int e = 0; e < 4; ++e) {
+              const uint32_t w = rw[e];
+              const uint2 ts = *reinterpret_cast<const uint2*>(table_bytes + (w & kRunOffMask));
+              const int32_t c = (int32_t)(ts.y + __popc(shl_clamp(ts.x, w >> kRunShloShift)));
+              // fused: a dropped pair's materialised partner is 0, so its (meaningless) value needs no masking
+              d4[e] = (kFused || ((kw >> e) & 1u)) ? 2 * c + bias : 0;
             }
-            const int32_t d = ((kw >> e) & 1u) ? (int32_t)sum - (int32_t)Ns : 0;
-            d4[e] = d;
-            acc_ss += (Acc)d * (Acc)d;
+          } else if (kCompact) {
+            uint32_t sum[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const uint32_t w = rw[e];
+              const char* entry = table_bytes + (w & kRunOffMask);
+              const uint2 ts = *reinterpret_cast<const uint2*>(entry);
+              uint2 te = ts;
+              if (w & kRunCrossBit) te = *reinterpret_cast<const uint2*>(entry + 8);     // the run ends inside the next group
+              sum[e] = ts.y + __popc(shl_clamp(ts.x, w >> kRunShloShift)) +
+                       te.y + __popc(shl_clamp(te.x, (w >> kRunSheShift) & 63u));
+            }
+            // a long run (shlo == 0) among the four?  Rare (more than 32 equal values): its end comes from the head tables
+            if (min(min(rw[0], rw[1]), min(rw[2], rw[3])) < (1u << kRunShloShift)) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const uint32_t w = rw[e];
+                if ((w >> kRunShloShift) == 0u) {
+                  const uint32_t gs = (w & kRunOffMask) >> 3, ls = ((w >> kRunSheShift) & 63u) - 1u;
+                  const uint32_t above = ls == 31u ? 0u : (__ldg(blob.head_bits + gs) >> (ls + 1u));
+                  const uint32_t endpos = above ? gs * 32u + ls + (uint32_t)__ffs(above) : __ldg(blob.next_head + gs + 1);
+                  const uint2 ts = table[gs], tl = table[endpos >> 5];
+                  sum[e] = ts.y + __popc(shl_clamp(ts.x, 32u - ls)) + tl.y + __popc(shl_clamp(tl.x, 32u - (endpos & 31u)));
+                }
+              }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int32_t d = ((kw >> e) & 1u) ? (int32_t)sum[e] - (int32_t)Ns : 0;
+              d4[e] = d;
+              acc_ss = square_acc(acc_ss, d);
+            }
+          } else {
+            uint32_t s4[4], e4[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { s4[e] = rw[e] & smask; e4[e] = s4[e] + (rw[e] >> sbits) + 1u; }
+            if (max(max(rw[0], rw[1]), max(rw[2], rw[3])) >= esc_word) {   // rare: a run longer than the packed field
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if (rw[e] >= esc_word) {
+                  const uint32_t g = s4[e] >> 5, l = s4[e] & 31u;
+                  const uint32_t above = l == 31u ? 0u : (__ldg(blob.head_bits + g) >> (l + 1u));
+                  e4[e] = above ? s4[e] + (uint32_t)__ffs(above) : __ldg(blob.next_head + g + 1);
+                }
+              }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const uint32_t gs = s4[e] >> 5, ge = e4[e] >> 5;
+              const uint2 ts = table[gs];
+              uint2 te = ts;
+              if (ge != gs) te = table[ge];                      // ~5 % of pairs: the run leaves the 32-group
+              // popc of the low (x & 31) bits: shifting left by 32 - (x & 31) drops the others (PTX shl clamps at 32)
+              const uint32_t lo = ts.y + __popc(shl_clamp(ts.x, 32u - (s4[e] & 31u)));
+              const uint32_t hi = te.y + __popc(shl_clamp(te.x, 32u - (e4[e] & 31u)));
+              const int32_t d = ((kw >> e) & 1u) ? (int32_t)(lo + hi) - (int32_t)Ns : 0;
+              d4[e] = d;
+              acc_ss += (Acc)d * (Acc)d;
+            }
+          }
+        }
+        if (kFused) {
+          if (any_kept) {
+#pragma unroll
+            for (int a = 0; a < kFuseMax; ++a) acc[a] = mac4(acc[a], d4, m4[a]);
           }
         } else {
-        uint32_t s4[4], e4[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { s4[e] = rw[e] & smask; e4[e] = s4[e] + (rw[e] >> sbits) + 1u; }
-        if (max(max(rw[0], rw[1]), max(rw[2], rw[3])) >= esc_word) {   // rare: a run longer than the packed field
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            if (rw[e] >= esc_word) {
-              const uint32_t g = s4[e] >> 5, l = s4[e] & 31u;
-              const uint32_t above = l == 31u ? 0u : (__ldg(blob.head_bits + g) >> (l + 1u));
-              e4[e] = above ? s4[e] + (uint32_t)__ffs(above) : __ldg(blob.next_head + g + 1);
-            }
-          }
+          *reinterpret_cast<int4*>(out_dev + p0) = make_int4(d4[0], d4[1], d4[2], d4[3]);
         }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const uint32_t gs = s4[e] >> 5, ge = e4[e] >> 5;
-          const uint2 ts = table[gs];
-          uint2 te = ts;
-          if (ge != gs) te = table[ge];                      // ~5 % of pairs: the run leaves the 32-group
-          // popc of the low (x & 31) bits: shifting left by 32 - (x & 31) drops the others (PTX shl clamps at 32)
-          const uint32_t lo = ts.y + __popc(shl_clamp(ts.x, 32u - (s4[e] & 31u)));
-          const uint32_t hi = te.y + __popc(shl_clamp(te.x, 32u - (e4[e] & 31u)));
-          const int32_t d = ((kw >> e) & 1u) ? (int32_t)(lo + hi) - (int32_t)Ns : 0;
-          d4[e] = d;
-          acc_ss += (Acc)d * (Acc)d;
-        }
-        }
-      }
-      if (kFused) {
-        if (any_kept) {
-#pragma unroll
-          for (int a = 0; a < kFuseMax; ++a) acc[a] = mac4(acc[a], d4, m4[a]);
-        }
-      } else {
-        *reinterpret_cast<int4*>(out_dev + p0) = make_int4(d4[0], d4[1], d4[2], d4[3]);
       }
     }
 
@@ -361,6 +398,8 @@ rank_kernel(const __grid_constant__ RankArgs A) {
       // every participating lane needs ss of this item: recompute it locally from slot kFuseMax
       double ss_item = 0.0;
       for (int w = 0; w < kRankWarps; ++w) ss_item += s_red[w][kFuseMax];
+      if (kUntied)                   // ranks are a permutation of 1..N_r: sum of (2 rank - N_r - 1)^2, exact in int64
+        ss_item = (double)(((long long)Ns - 1) * (long long)Ns * ((long long)Ns + 1) / 3);
       if (blob.hdr->has_nan) ss_item = nan;
       if (!kFused) {
         if (slot == kFuseMax) {
@@ -442,13 +481,24 @@ static int launch_count(const BlobList& blobs, int nV, int n, const RankContext&
   return VR_OK;
 }
 
-template <bool kSmem, bool kFused, typename Acc, bool kCompact>
-static int launch_rank_variant(const RankArgs& args, int grid, size_t smem, cudaStream_t stream) {
+template <bool kSmem, bool kFused, typename Acc, bool kCompact, bool kUntied>
+static int launch_rank_kind(const RankArgs& args, int grid, size_t smem, cudaStream_t stream) {
   static unsigned long long attr_done = 0;
-  if (kSmem) VR_CHECK_CUDA(ensure_dynamic_smem(rank_kernel<kSmem, kFused, Acc, kCompact>, (int)(kRankSmemTableMax + 8192), &attr_done));
-  rank_kernel<kSmem, kFused, Acc, kCompact><<<grid, kFused ? kRankThreadsFused : kRankThreadsMat, smem, stream>>>(args);
+  auto kernel = rank_kernel<kSmem, kFused, Acc, kCompact, kUntied>;
+  if (kSmem) VR_CHECK_CUDA(ensure_dynamic_smem(kernel, (int)(kRankSmemTableMax + 8192), &attr_done));
+  kernel<<<grid, kFused ? kRankThreadsFused : kRankThreadsMat, smem, stream>>>(args);
   VR_CHECK_LAUNCH();
   return VR_OK;
+}
+// Whether a vector has ties is known only on the device (presort header), so both sweeps are launched and each
+// takes the vectors of its kind; the one with nothing to do returns after reading the headers.
+template <bool kSmem, bool kFused, typename Acc, bool kCompact>
+static int launch_rank_variant(const RankArgs& args, int grid, size_t smem, cudaStream_t stream) {
+  if (kCompact) {
+    int st = launch_rank_kind<kSmem, kFused, Acc, kCompact, kCompact>(args, grid, smem, stream);
+    if (st != VR_OK) return st;
+  }
+  return launch_rank_kind<kSmem, kFused, Acc, kCompact, false>(args, grid, smem, stream);
 }
 
 template <bool kFused>
