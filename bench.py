@@ -300,8 +300,9 @@ def run_ours(args):
                                   "x vectors*(B+1) ranked per launch",
                     "note": "conservative unit: work sharing lets one launch finish nA*nB*(B+1) replicate comparisons from "
                             "(nA+nB)*(B+1) rankings; per finished comparison (8*N_sub each) the same launch would read "
-                            f"{(nA * nB * (B + 1) * 8.0 * N_sub) / (per_launch_ms * 1e-3) / 1e9:.0f} GB/s. ncu: the kernel is instruction-issue bound "
-                            "(65 % issue-active, DRAM 18 %), not HBM bound."}
+                            f"{(nA * nB * (B + 1) * 8.0 * N_sub) / (per_launch_ms * 1e-3) / 1e9:.0f} GB/s. ncu (profiles/r1_rank_kernels_nsd_full.txt): the binding resource is the "
+                            "L1/shared-memory data pipe (random 8-byte table lookups + the materialised streams: 66 % of its peak, issue 62 %), "
+                            "DRAM 20 % -- not HBM bound."}
         try:   # DRAM bytes per launch of this kernel from the committed ncu capture, if it is for this workload
             tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
             wl = tr.get("workload", {})

@@ -32,6 +32,7 @@ namespace vr {
 
 constexpr int kRankThreadsMat = 1024;   // materialise: 64 registers per thread
 constexpr int kRankThreadsFused = 768;  // fused: 85 registers per thread, all 8 materialised loads in flight
+                                        // (512 threads x two groups: 11.2 ms, 1024 threads x two load batches: 11.0 ms, this: 10.1 ms)
 constexpr int kCountThreads = 512;
 constexpr int kCountWarps = kCountThreads / 32;
 constexpr int kMaxVectors = 64;
@@ -190,7 +191,8 @@ rank_kernel(const __grid_constant__ RankArgs A) {
   constexpr int kRankWarps = kRankThreads / 32;
   extern __shared__ __align__(16) uint32_t smem[];
   uint2* s_table = reinterpret_cast<uint2*>(smem);
-  __shared__ double s_red[kRankWarps][kFuseMax + 1];
+  using Red = std::conditional_t<std::is_integral<Acc>::value, long long, double>;   // integer sums stay exact to the end
+  __shared__ Red s_red[kRankWarps][kFuseMax + 1];
   __shared__ uint32_t s_base[kCountWarps + 1];
 
   const unsigned lane = lane_id();
@@ -267,20 +269,95 @@ rank_kernel(const __grid_constant__ RankArgs A) {
     // one table entry, one shift, one popc -- and its sum of squares is the closed form N_r (N_r^2 - 1) / 3.
     const char* __restrict__ table_bytes = reinterpret_cast<const char*>(table);
 
-    // software pipeline: the run words and kept bits of the NEXT step are in flight while this one is ranked
     const uint32_t esc_word = esc << sbits;                  // a run word >= esc_word carries the escape code
-    {
+    // ranks of four consecutive canonical pairs: q = their run words, kw = their kept bits (low four)
+    auto rank4 = [&](const uint4 q, const uint32_t kw, int32_t (&d4)[4]) {
+      const uint32_t rw[4] = {q.x, q.y, q.z, q.w};
+      if (kCompact && kUntied) {
+        const int32_t bias = 1 - (int32_t)Ns;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t w = rw[e];
+          const uint2 ts = *reinterpret_cast<const uint2*>(table_bytes + (w & kRunOffMask));
+          const int32_t c = (int32_t)(ts.y + __popc(shl_clamp(ts.x, w >> kRunShloShift)));
+          // fused: a dropped pair's materialised partner is 0, so its (meaningless) value needs no masking
+          d4[e] = (kFused || ((kw >> e) & 1u)) ? 2 * c + bias : 0;
+        }
+      } else if (kCompact) {
+        uint32_t sum[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t w = rw[e];
+          const char* entry = table_bytes + (w & kRunOffMask);
+          const uint2 ts = *reinterpret_cast<const uint2*>(entry);
+          uint2 te = ts;
+          if (w & kRunCrossBit) te = *reinterpret_cast<const uint2*>(entry + 8);     // the run ends inside the next group
+          sum[e] = ts.y + __popc(shl_clamp(ts.x, w >> kRunShloShift)) +
+                   te.y + __popc(shl_clamp(te.x, (w >> kRunSheShift) & 63u));
+        }
+        // a long run (shlo == 0) among the four?  Rare (more than 32 equal values): its end comes from the head tables
+        if (min(min(rw[0], rw[1]), min(rw[2], rw[3])) < (1u << kRunShloShift)) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const uint32_t w = rw[e];
+            if ((w >> kRunShloShift) == 0u) {
+              const uint32_t gs = (w & kRunOffMask) >> 3, ls = ((w >> kRunSheShift) & 63u) - 1u;
+              const uint32_t above = ls == 31u ? 0u : (__ldg(blob.head_bits + gs) >> (ls + 1u));
+              const uint32_t endpos = above ? gs * 32u + ls + (uint32_t)__ffs(above) : __ldg(blob.next_head + gs + 1);
+              const uint2 ts = table[gs], tl = table[endpos >> 5];
+              sum[e] = ts.y + __popc(shl_clamp(ts.x, 32u - ls)) + tl.y + __popc(shl_clamp(tl.x, 32u - (endpos & 31u)));
+            }
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int32_t d = ((kw >> e) & 1u) ? (int32_t)sum[e] - (int32_t)Ns : 0;
+          d4[e] = d;
+          acc_ss = square_acc(acc_ss, d);
+        }
+      } else {
+        uint32_t s4[4], e4[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { s4[e] = rw[e] & smask; e4[e] = s4[e] + (rw[e] >> sbits) + 1u; }
+        if (max(max(rw[0], rw[1]), max(rw[2], rw[3])) >= esc_word) {   // rare: a run longer than the packed field
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (rw[e] >= esc_word) {
+              const uint32_t g = s4[e] >> 5, l = s4[e] & 31u;
+              const uint32_t above = l == 31u ? 0u : (__ldg(blob.head_bits + g) >> (l + 1u));
+              e4[e] = above ? s4[e] + (uint32_t)__ffs(above) : __ldg(blob.next_head + g + 1);
+            }
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t gs = s4[e] >> 5, ge = e4[e] >> 5;
+          const uint2 ts = table[gs];
+          uint2 te = ts;
+          if (ge != gs) te = table[ge];                      // ~5 % of pairs: the run leaves the 32-group
+          // popc of the low (x & 31) bits: shifting left by 32 - (x & 31) drops the others (PTX shl clamps at 32)
+          const uint32_t lo = ts.y + __popc(shl_clamp(ts.x, 32u - (s4[e] & 31u)));
+          const uint32_t hi = te.y + __popc(shl_clamp(te.x, 32u - (e4[e] & 31u)));
+          const int32_t d = ((kw >> e) & 1u) ? (int32_t)(lo + hi) - (int32_t)Ns : 0;
+          d4[e] = d;
+          acc_ss += (Acc)d * (Acc)d;
+        }
+      }
+    };
+
+    // software pipeline: the run words and kept bits of the NEXT step are in flight while this one is ranked
+    if constexpr (kFused) {
       uint32_t p0 = threadIdx.x * 4u;
       uint4 q_cur = make_uint4(0u, 0u, 0u, 0u);
       uint32_t kw_cur = 0u;
       if (p0 < N) { q_cur = __ldg(reinterpret_cast<const uint4*>(runs + p0)); kw_cur = __ldg(keptw + (p0 >> 5)); }
       for (; p0 < (uint32_t)dev_stride; p0 += kRankThreads * 4u) {
         int32_t d4[4] = {0, 0, 0, 0};
-        int4 m4[kFuseMax];
         const uint4 q = q_cur;
         const uint32_t kw = kw_cur >> (p0 & 31u);              // 4 kept bits (p0 is a multiple of 4)
         const bool any_kept = p0 < N && (kw & 0xFu) != 0u;      // a dropped stimulus' row: all four pairs are out
-        if (kFused && any_kept) {   // all materialised vectors are requested before the ranking work, which hides their latency
+        int4 m4[kFuseMax];
+        if (any_kept) {   // all materialised vectors are requested before the ranking work, which hides their latency
 #pragma unroll
           for (int a = 0; a < kFuseMax; ++a) m4[a] = __ldg(mat4 + (moff[a] + ((p0 >> 2) - threadIdx.x)));
         }
@@ -289,100 +366,55 @@ rank_kernel(const __grid_constant__ RankArgs A) {
           if (pn < N) { q_cur = __ldg(reinterpret_cast<const uint4*>(runs + pn)); kw_cur = __ldg(keptw + (pn >> 5)); }
         }
         if (any_kept) {
-          const uint32_t rw[4] = {q.x, q.y, q.z, q.w};
-          if (kCompact && kUntied) {
-            const int32_t bias = 1 - (int32_t)Ns;
+          rank4(q, kw, d4);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const uint32_t w = rw[e];
-              const uint2 ts = *reinterpret_cast<const uint2*>(table_bytes + (w & kRunOffMask));
-              const int32_t c = (int32_t)(ts.y + __popc(shl_clamp(ts.x, w >> kRunShloShift)));
-              // fused: a dropped pair's materialised partner is 0, so its (meaningless) value needs no masking
-              d4[e] = (kFused || ((kw >> e) & 1u)) ? 2 * c + bias : 0;
-            }
-          } else if (kCompact) {
-            uint32_t sum[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const uint32_t w = rw[e];
-              const char* entry = table_bytes + (w & kRunOffMask);
-              const uint2 ts = *reinterpret_cast<const uint2*>(entry);
-              uint2 te = ts;
-              if (w & kRunCrossBit) te = *reinterpret_cast<const uint2*>(entry + 8);     // the run ends inside the next group
-              sum[e] = ts.y + __popc(shl_clamp(ts.x, w >> kRunShloShift)) +
-                       te.y + __popc(shl_clamp(te.x, (w >> kRunSheShift) & 63u));
-            }
-            // a long run (shlo == 0) among the four?  Rare (more than 32 equal values): its end comes from the head tables
-            if (min(min(rw[0], rw[1]), min(rw[2], rw[3])) < (1u << kRunShloShift)) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const uint32_t w = rw[e];
-                if ((w >> kRunShloShift) == 0u) {
-                  const uint32_t gs = (w & kRunOffMask) >> 3, ls = ((w >> kRunSheShift) & 63u) - 1u;
-                  const uint32_t above = ls == 31u ? 0u : (__ldg(blob.head_bits + gs) >> (ls + 1u));
-                  const uint32_t endpos = above ? gs * 32u + ls + (uint32_t)__ffs(above) : __ldg(blob.next_head + gs + 1);
-                  const uint2 ts = table[gs], tl = table[endpos >> 5];
-                  sum[e] = ts.y + __popc(shl_clamp(ts.x, 32u - ls)) + tl.y + __popc(shl_clamp(tl.x, 32u - (endpos & 31u)));
-                }
-              }
-            }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int32_t d = ((kw >> e) & 1u) ? (int32_t)sum[e] - (int32_t)Ns : 0;
-              d4[e] = d;
-              acc_ss = square_acc(acc_ss, d);
-            }
-          } else {
-            uint32_t s4[4], e4[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) { s4[e] = rw[e] & smask; e4[e] = s4[e] + (rw[e] >> sbits) + 1u; }
-            if (max(max(rw[0], rw[1]), max(rw[2], rw[3])) >= esc_word) {   // rare: a run longer than the packed field
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                if (rw[e] >= esc_word) {
-                  const uint32_t g = s4[e] >> 5, l = s4[e] & 31u;
-                  const uint32_t above = l == 31u ? 0u : (__ldg(blob.head_bits + g) >> (l + 1u));
-                  e4[e] = above ? s4[e] + (uint32_t)__ffs(above) : __ldg(blob.next_head + g + 1);
-                }
-              }
-            }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const uint32_t gs = s4[e] >> 5, ge = e4[e] >> 5;
-              const uint2 ts = table[gs];
-              uint2 te = ts;
-              if (ge != gs) te = table[ge];                      // ~5 % of pairs: the run leaves the 32-group
-              // popc of the low (x & 31) bits: shifting left by 32 - (x & 31) drops the others (PTX shl clamps at 32)
-              const uint32_t lo = ts.y + __popc(shl_clamp(ts.x, 32u - (s4[e] & 31u)));
-              const uint32_t hi = te.y + __popc(shl_clamp(te.x, 32u - (e4[e] & 31u)));
-              const int32_t d = ((kw >> e) & 1u) ? (int32_t)(lo + hi) - (int32_t)Ns : 0;
-              d4[e] = d;
-              acc_ss += (Acc)d * (Acc)d;
-            }
-          }
+          for (int a = 0; a < kFuseMax; ++a) acc[a] = mac4(acc[a], d4, m4[a]);
         }
-        if (kFused) {
-          if (any_kept) {
-#pragma unroll
-            for (int a = 0; a < kFuseMax; ++a) acc[a] = mac4(acc[a], d4, m4[a]);
-          }
-        } else {
-          *reinterpret_cast<int4*>(out_dev + p0) = make_int4(d4[0], d4[1], d4[2], d4[3]);
+      }
+    } else {
+      // each warp takes 256 consecutive pairs per step as two coalesced groups of 128: eight independent
+      // table lookups per thread are in flight, and both groups usually lie in the same RDM row, so a
+      // dropped stimulus' row still skips the work
+      constexpr uint32_t kStep = kRankThreads * 8u;
+      uint32_t p0 = (threadIdx.x >> 5) * 256u + lane * 4u;
+      constexpr uint32_t kPadWord = kCompact ? 32u << kRunShloShift : 0u;     // what the presort stores beyond N
+      uint4 qa_cur = make_uint4(kPadWord, kPadWord, kPadWord, kPadWord), qb_cur = qa_cur;
+      uint32_t ka_cur = 0u, kb_cur = 0u;
+      if (p0 < N) { qa_cur = __ldg(reinterpret_cast<const uint4*>(runs + p0)); ka_cur = __ldg(keptw + (p0 >> 5)); }
+      if (p0 + 128u < N) { qb_cur = __ldg(reinterpret_cast<const uint4*>(runs + p0 + 128u)); kb_cur = __ldg(keptw + ((p0 + 128u) >> 5)); }
+      for (; p0 < (uint32_t)dev_stride; p0 += kStep) {
+        const uint32_t p1 = p0 + 128u;
+        int32_t da[4] = {0, 0, 0, 0}, db[4] = {0, 0, 0, 0};
+        const uint4 qa = qa_cur, qb = qb_cur;
+        const uint32_t ka = p0 < N ? (ka_cur >> (p0 & 31u)) & 0xFu : 0u;
+        const uint32_t kb = p1 < N ? (kb_cur >> (p1 & 31u)) & 0xFu : 0u;
+        {
+          const uint32_t pn = p0 + kStep;
+          if (pn < N) { qa_cur = __ldg(reinterpret_cast<const uint4*>(runs + pn)); ka_cur = __ldg(keptw + (pn >> 5)); }
+          if (pn + 128u < N) { qb_cur = __ldg(reinterpret_cast<const uint4*>(runs + pn + 128u)); kb_cur = __ldg(keptw + ((pn + 128u) >> 5)); }
         }
+        if ((ka | kb) != 0u) {         // run words beyond N are padding words: valid to rank, never kept
+          rank4(qa, ka, da);
+          rank4(qb, kb, db);
+        }
+        *reinterpret_cast<int4*>(out_dev + p0) = make_int4(da[0], da[1], da[2], da[3]);
+        if (p1 < (uint32_t)dev_stride) *reinterpret_cast<int4*>(out_dev + p1) = make_int4(db[0], db[1], db[2], db[3]);
       }
     }
 
     // block reduction: ss (slot kFuseMax) and, when fused, the n_mat dot products
     {
-      double v_ss = warp_sum((double)acc_ss);
+      auto wsum = [](Acc x) -> Red {
+        if constexpr (std::is_integral<Acc>::value) return warp_sum_ll((long long)x);
+        else return warp_sum((double)x);
+      };
+      const Red v_ss = wsum(acc_ss);
       if (lane == 0) s_red[warp][kFuseMax] = v_ss;
       if (kFused) {
 #pragma unroll
         for (int a = 0; a < kFuseMax; ++a) {
           if (a < A.n_mat) {
-            double t;
-            if constexpr (std::is_integral<Acc>::value) t = (double)warp_sum_ll((long long)acc[a]);   // exact
-            else t = warp_sum((double)acc[a]);
+            const Red t = wsum(acc[a]);
             if (lane == 0) s_red[warp][a] = t;
           }
         }
@@ -391,13 +423,13 @@ rank_kernel(const __grid_constant__ RankArgs A) {
     __syncthreads();
     if (threadIdx.x <= kFuseMax) {
       const int slot = threadIdx.x;
-      double tot = 0.0;
+      Red tot_r = 0, ss_r = 0;       // every participating lane needs ss of this item as well
       if (slot == kFuseMax || (kFused && slot < A.n_mat))
-        for (int w = 0; w < kRankWarps; ++w) tot += s_red[w][slot];
+        for (int w = 0; w < kRankWarps; ++w) tot_r += s_red[w][slot];
+      for (int w = 0; w < kRankWarps; ++w) ss_r += s_red[w][kFuseMax];
+      const double tot = (double)tot_r;
+      double ss_item = (double)ss_r;
       const double nan = __longlong_as_double(0x7ff8000000000000LL);
-      // every participating lane needs ss of this item: recompute it locally from slot kFuseMax
-      double ss_item = 0.0;
-      for (int w = 0; w < kRankWarps; ++w) ss_item += s_red[w][kFuseMax];
       if (kUntied)                   // ranks are a permutation of 1..N_r: sum of (2 rank - N_r - 1)^2, exact in int64
         ss_item = (double)(((long long)Ns - 1) * (long long)Ns * ((long long)Ns + 1) / 3);
       if (blob.hdr->has_nan) ss_item = nan;
