@@ -190,8 +190,12 @@ int vr_bootstrap_pearson(const float* const* rdmA_host, int nA,
  * rsa.py:22-40 (SciPy tau-b rescaled to (C - D) / n0) inside compute_rdm_correlation (rsa.py:122)
  * and inside the bootstrap loops when compare_method = kendall (evals.py:229, utils.py:518).
  * out is (R,) fp64; NaN for < 2 kept pairs, a constant vector or a NaN entry.
+ * Replicates are processed in batches of up to 64 (one grid row per replicate); the batch shrinks to
+ * what the workspace holds: vr_kendall_workspace_bytes(n) is the minimum (one replicate at a time),
+ * vr_kendall_batch_workspace_bytes(n, R) the size at which R replicates run in full batches.
  * ---------------------------------------------------------------------------------- */
 size_t vr_kendall_workspace_bytes(int n);
+size_t vr_kendall_batch_workspace_bytes(int n, int R);
 int vr_kendall_tau_a(const float* rdmA, const float* rdmB, int n, int64_t ld,
                      const uint32_t* masks, int R, double* out,
                      void* ws, size_t ws_bytes, vr_stream_t stream);

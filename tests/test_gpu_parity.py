@@ -515,3 +515,92 @@ def test_tied_and_tie_free_vectors_in_one_launch(dev):
             np.testing.assert_array_equal(devv[r][kp] + (Ns + 1), orc.rank2x(v[kp]))
             assert not devv[r][~kp].any()
             assert float(ss[r]) == float((devv[r] ** 2).sum())
+
+
+def test_eval_blocks_match_the_reference_loops(dev):
+    """visreps_b200.evals restates the (region, subject) loops of visreps/evals.py:249-287 and :333-398 as grouped
+    device jobs; the oracle runs the loops as written."""
+    from visreps_b200 import evals as vevals
+    rs = np.random.RandomState(2024)
+    g = lambda *s: torch.from_numpy(rs.standard_normal(s).astype(np.float32))
+    n_train, n_test, n_select, B = 150, 60, 100, 25
+    layers = ["conv1", "conv2", "fc1"]
+    pairs = [("V1", 0), ("V1", 1), ("ventral", 0), ("ventral", 1)]
+    latent_tr, latent_te = g(n_train, 12), g(n_test, 12)
+    mix = {l: g(12, d) for l, d in zip(layers, (300, 80, 40))}
+    noise = {"conv1": 3.0, "conv2": 0.3, "fc1": 1.0}
+    train_acts = {k: {l: (latent_tr @ mix[l] + noise[l] * g(n_train, mix[l].shape[1])).reshape(n_train, -1, 4) for l in layers} for k in pairs}
+    test_feats = {l: (latent_te @ mix[l] + noise[l] * g(n_test, mix[l].shape[1])).reshape(n_test, 4, -1) for l in layers}
+    proj = {k: g(12, 30 + 7 * i) for i, k in enumerate(pairs)}
+    train_neural = {k: latent_tr @ proj[k] + 0.5 * g(n_train, proj[k].shape[1]) for k in pairs}
+    test_neural = {k: latent_te @ proj[k] + 0.5 * g(n_test, proj[k].shape[1]) for k in pairs}
+
+    got = vevals.eval_rsa_scores(train_acts, train_neural, test_feats, test_neural, "spearman", n_select=n_select,
+                                 bootstrap=True, n_bootstrap=B)
+    assert [r["layer"] for r in got] and len(got) == len(pairs)
+    model_rdms = {l: orc.rdm(test_feats[l].flatten(start_dim=1)) for l in layers}
+    for k, r in zip(pairs, got):
+        # phase 1 as written: RandomState(42) per pair, first strict maximum wins
+        sel_idx = np.random.RandomState(42).choice(n_train, size=n_select, replace=False)
+        nrdm = orc.rdm(train_neural[k][sel_idx])
+        best, best_score, want_sel = None, -float("inf"), []
+        for l in layers:
+            s = orc.rdm_compare(orc.rdm(train_acts[k][l][sel_idx].flatten(start_dim=1)), nrdm, correlation="Spearman")
+            want_sel.append(s)
+            if s > best_score:
+                best, best_score = l, s
+        assert r["layer"] == best
+        assert [d["layer"] for d in r["layer_selection_scores"]] == layers
+        np.testing.assert_allclose([d["score"] for d in r["layer_selection_scores"]], want_sel, atol=SCORE_TOL, rtol=0)
+        # scoring block as written: RandomState(42) re-created per pair
+        neural_rdm = orc.rdm(test_neural[k])
+        assert abs(r["score"] - orc.rdm_compare(model_rdms[best], neural_rdm, correlation="Spearman")) <= SCORE_TOL
+        want = orc.bootstrap_compare_with_indices(model_rdms[best], neural_rdm, "spearman", orc.draw_subsamples(n_test, B, 42))
+        np.testing.assert_allclose(r["bootstrap_scores"], want, atol=SCORE_TOL, rtol=0)
+        assert r["ci_low"] == float(np.percentile(r["bootstrap_scores"], 2.5))
+        assert r["ci_high"] == float(np.percentile(r["bootstrap_scores"], 97.5))
+        assert set(r) == {"layer", "compare_method", "score", "ci_low", "ci_high", "analysis", "layer_selection_scores", "bootstrap_scores"}
+        assert isinstance(r["score"], float) and isinstance(r["bootstrap_scores"], list)
+    # without bootstrap: CI fields are None and there is no score list (evals.py:350-352, :388-389)
+    plain = vevals.score_pairs(test_feats, test_neural, {k: "fc1" for k in pairs}, "pearson")
+    assert all(r["ci_low"] is None and r["ci_high"] is None and "bootstrap_scores" not in r and r["layer_selection_scores"] == [] for r in plain)
+    for k, r in zip(pairs, plain):
+        assert abs(r["score"] - orc.rdm_compare(model_rdms["fc1"], orc.rdm(test_neural[k]), correlation="Pearson")) <= SCORE_TOL
+    # n_select >= n_train keeps every stimulus in order (evals.py:261-262)
+    assert np.array_equal(vevals.selection_indices(80, 1000), np.arange(80)) and np.array_equal(vevals.selection_indices(80, None), np.arange(80))
+
+
+def test_kendall_batches_ties_and_small_workspace(dev):
+    """More replicates than one batch (64), heavy ties on one side, and the minimum workspace (one replicate per
+    batch) must all give the oracle's tau-a."""
+    import ctypes as C
+    from visreps_b200 import _lib
+    n, B = 150, 70
+    N = n * (n - 1) // 2
+    rs = np.random.RandomState(99)
+    a = orc.rdm(torch.from_numpy(rs.standard_normal((n, 40)).astype(np.float32)))
+    b = cases.vector_to_rdm(cases.tied_vectors(N, 11, 5)[0], n)
+    c = orc.rdm(torch.from_numpy(rs.standard_normal((n, 25)).astype(np.float32)))
+    idx = orc.draw_subsamples(n, B, 42)
+    for x, y in ((a, b), (a, c), (b, b)):
+        p, lo, hi, scores = vb.bootstrap_rdm_correlation(x, y, "kendall", n_bootstrap=B, seed=42)
+        want = orc.bootstrap_compare_with_indices(x, y, "kendall", idx)
+        np.testing.assert_allclose(scores, want, atol=SCORE_TOL, rtol=0)
+        assert abs(p - orc.rdm_compare(x, y, correlation="Kendall")) <= SCORE_TOL
+    # the C entry point with its minimum workspace: same numbers, one replicate per batch
+    lib = _lib.load()
+    masks = vrsa.build_masks(idx, n, dev, with_full=True)
+    R = int(masks.shape[0])
+    xa, yb = a.to(dev).contiguous(), b.to(dev).contiguous()
+    small = torch.empty(lib.vr_kendall_workspace_bytes(n), dtype=torch.uint8, device=dev)
+    big = torch.empty(lib.vr_kendall_batch_workspace_bytes(n, R), dtype=torch.uint8, device=dev)
+    outs = []
+    for ws in (small, big):
+        out = torch.empty(R, dtype=torch.float64, device=dev)
+        _lib.check(lib.vr_kendall_tau_a(xa.data_ptr(), yb.data_ptr(), n, n, masks.data_ptr(), R, out.data_ptr(),
+                                        ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "vr_kendall_tau_a")
+        outs.append(out.cpu().numpy())
+    np.testing.assert_array_equal(outs[0], outs[1])
+    np.testing.assert_allclose(outs[0][1:], orc.bootstrap_compare_with_indices(a, b, "kendall", idx), atol=SCORE_TOL, rtol=0)
+    assert lib.vr_kendall_tau_a(xa.data_ptr(), yb.data_ptr(), n, n, masks.data_ptr(), R, out.data_ptr(),
+                                small.data_ptr(), small.numel() - 4096, _lib.stream_ptr()) == 2      # VR_ERR_WORKSPACE

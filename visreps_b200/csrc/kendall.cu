@@ -8,11 +8,15 @@
 //
 // Once per RDM pair:   entries are sorted by (x, y) with two stable radix sorts (by y, then by x) that
 //                      carry the canonical pair index.
-// Per replicate:       the (x, y) order of the kept entries is the stable compaction of the full order
+//                      Run starts (lower bounds in the sorted keys) for equal x, equal (x, y), equal y.
+// Per batch of <= 64 replicates (grid.y = replicate, ~15 launches per batch whatever its size):
+//                      the (x, y) order of the kept entries is the stable compaction of the full order
 //                      (same fact the Spearman path uses), so no replicate sorts:
-//                      compact -> tie sums (run lengths) -> D = inversions of the y sequence, counted by a
-//                      bottom-up merge sort in which every element finds its merged position by binary
-//                      search in the sibling run (O(M log^2 M) steps, fully parallel, ~20 launches).
+//                      kept tables {kept word, kept count before} of both orders -> tie sums (a kept entry adds
+//                      the kept entries before it in its run) -> D = inversions of the compacted y sequence,
+//                      counted by a bottom-up merge sort: 2048-entry tiles in shared memory, then global
+//                      levels in which every element finds its merged position by binary search in the
+//                      sibling run.
 #include "common.cuh"
 #include "sort.cuh"
 #include "pairmask.cuh"
@@ -40,101 +44,260 @@ gather_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ ind
   if (k < N) dst[k] = src[index[k]];
 }
 
-// kept flag of sorted position k (pair index order[k]) for one replicate, and block-wise counts for the scan.
-// Single-CTA exclusive scan + stable compaction of up to two value arrays.  N <= ~2^27.
+// Start of the run of equal keys that holds sorted position k: the keys are sorted, so it is a lower bound
+// (lexicographic on (k0, k1) when k1 is given).  Replicate-independent, once per RDM pair.
+__global__ void __launch_bounds__(256)
+run_start_kernel(const uint32_t* __restrict__ k0, const uint32_t* __restrict__ k1, uint32_t N, uint32_t* __restrict__ start) {
+  const uint32_t k = blockIdx.x * 256u + threadIdx.x;
+  if (k >= N) return;
+  const uint32_t a = k0[k], b = k1 ? k1[k] : 0u;
+  uint32_t lo = 0, hi = k;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    const uint32_t am = k0[mid];
+    const bool less = am < a || (k1 && am == a && k1[mid] < b);
+    if (less) lo = mid + 1; else hi = mid;
+  }
+  start[k] = lo;
+}
+
+// ---- per batch of replicates -------------------------------------------------------------------------
+// Kept tables of a sorted order for every replicate of the batch: entry g = {kept word of positions
+// [32g, 32g+32), kept count before the group}, built in three steps (group words + chunk totals, scan of
+// the chunk totals, add the bases).  grid (chunks, replicates, 2 orders); a chunk is 256 groups.
+constexpr uint32_t kChunkGroups = 256;
+
+struct KendallOrders {
+  const uint32_t* order[2];    // pair index at each sorted position: [0] (x, y) order, [1] y order
+};
+
+__global__ void __launch_bounds__(256)
+kept_words_kernel(const KendallOrders ord, const uint32_t* __restrict__ pairbits, uint32_t words, uint32_t N, uint32_t G,
+                  uint2* __restrict__ tables, uint32_t* __restrict__ chunk_tot, uint32_t nchunks) {
+  __shared__ uint32_t s_warp[8];
+  const int r = blockIdx.y, o = blockIdx.z;
+  const uint32_t* __restrict__ order = ord.order[o];
+  const uint32_t* __restrict__ pb = pairbits + (size_t)r * words;
+  uint2* __restrict__ tab = tables + ((size_t)o * gridDim.y + r) * G;
+  const unsigned lane = lane_id();
+  const uint32_t g_base = blockIdx.x * kChunkGroups + (threadIdx.x >> 5) * 32u;     // this warp's 32 groups
+  uint32_t mine = 0, tot = 0;
+  for (uint32_t t = 0; t < 32u; ++t) {
+    const uint32_t k = (g_base + t) * 32u + lane;
+    bool kept = false;
+    if (k < N) { const uint32_t p = order[k]; kept = (pb[p >> 5] >> (p & 31u)) & 1u; }
+    const uint32_t word = __ballot_sync(0xffffffffu, kept);
+    if (t == lane) mine = word;
+    tot += __popc(word);
+  }
+  // exclusive prefix of the 32 group counts of this warp, relative to the warp's start
+  uint32_t c = __popc(mine), incl = c;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (unsigned)d) incl += x; }
+  if (g_base + lane < G) tab[g_base + lane] = make_uint2(mine, incl - c);
+  if (lane == 0) s_warp[threadIdx.x >> 5] = tot;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    for (int w = 0; w < 8; ++w) run += s_warp[w];
+    chunk_tot[((size_t)o * gridDim.y + r) * nchunks + blockIdx.x] = run;
+  }
+}
+
+// One CTA per (replicate, order): exclusive scan of the chunk totals in place; the grand total is the number of kept entries.
 __global__ void __launch_bounds__(1024)
-compact_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ pairbits, uint32_t N,
-               const uint32_t* __restrict__ v0, const uint32_t* __restrict__ v1, uint32_t* __restrict__ o0,
-               uint32_t* __restrict__ o1, uint32_t* __restrict__ count_out) {
+chunk_scan_kernel(uint32_t* __restrict__ chunk_tot, uint32_t nchunks, uint32_t* __restrict__ counts) {
   __shared__ uint32_t part[1024];
-  const uint32_t chunk = (N + 1023u) / 1024u;
-  const uint32_t lo = threadIdx.x * chunk, hi = min(N, lo + chunk);
-  uint32_t c = 0;
-  for (uint32_t k = lo; k < hi; ++k) { const uint32_t p = order[k]; c += (pairbits[p >> 5] >> (p & 31u)) & 1u; }
-  part[threadIdx.x] = c;
+  uint32_t* c = chunk_tot + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * nchunks;
+  const uint32_t per = (nchunks + 1023u) / 1024u;
+  const uint32_t lo = min(nchunks, threadIdx.x * per), hi = min(nchunks, lo + per);
+  uint32_t sum = 0;
+  for (uint32_t i = lo; i < hi; ++i) sum += c[i];
+  part[threadIdx.x] = sum;
   __syncthreads();
   if (threadIdx.x < 32) {
     uint32_t loc[32], run = 0;
     for (int t = 0; t < 32; ++t) { loc[t] = part[threadIdx.x * 32 + t]; run += loc[t]; }
     uint32_t incl = run;
-    for (int o = 1; o < 32; o <<= 1) { uint32_t x = __shfl_up_sync(0xffffffffu, incl, o); if (threadIdx.x >= (unsigned)o) incl += x; }
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, incl, d); if (threadIdx.x >= (unsigned)d) incl += x; }
     uint32_t base = incl - run;
     for (int t = 0; t < 32; ++t) { part[threadIdx.x * 32 + t] = base; base += loc[t]; }
-    if (threadIdx.x == 31) *count_out = incl;
+    if (threadIdx.x == 31) counts[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = incl;
   }
   __syncthreads();
-  uint32_t w = part[threadIdx.x];
-  for (uint32_t k = lo; k < hi; ++k) {
-    const uint32_t p = order[k];
-    if ((pairbits[p >> 5] >> (p & 31u)) & 1u) {
-      o0[w] = v0[k];
-      if (v1) o1[w] = v1[k];
-      ++w;
-    }
+  uint32_t run = part[threadIdx.x];
+  for (uint32_t i = lo; i < hi; ++i) { const uint32_t t = c[i]; c[i] = run; run += t; }
+}
+
+// Adds the chunk and warp bases to the table counts; for the (x, y) order it also writes the kept y keys,
+// compacted, which is the sequence whose inversions are counted.
+__global__ void __launch_bounds__(256)
+kept_finish_kernel(uint2* __restrict__ tables, const uint32_t* __restrict__ chunk_base, uint32_t nchunks, uint32_t G, uint32_t N,
+                   const uint32_t* __restrict__ yseq, uint32_t* __restrict__ cy, int64_t cy_stride) {
+  __shared__ uint32_t s_warp[9];
+  const int r = blockIdx.y, o = blockIdx.z;
+  uint2* __restrict__ tab = tables + ((size_t)o * gridDim.y + r) * G;
+  const unsigned lane = lane_id();
+  const int warp = threadIdx.x >> 5;
+  const uint32_t g = blockIdx.x * kChunkGroups + threadIdx.x;
+  uint2 e = g < G ? tab[g] : make_uint2(0u, 0u);
+  // total of each warp's 32 groups = last lane's count + popc of its word
+  const uint32_t wtot = __shfl_sync(0xffffffffu, e.y + __popc(e.x), 31);
+  if (lane == 0) s_warp[warp + 1] = wtot;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t run = chunk_base[((size_t)o * gridDim.y + r) * nchunks + blockIdx.x];
+    for (int w = 0; w < 8; ++w) { const uint32_t t = s_warp[w + 1]; s_warp[w] = run; run += t; }
+  }
+  __syncthreads();
+  e.y += s_warp[warp];
+  if (g < G) tab[g] = e;
+  if (o == 0 && g < G) {
+    uint32_t* __restrict__ out = cy + (int64_t)r * cy_stride;
+    uint32_t w = e.x, pos = e.y;
+    while (w) { const int b = __ffs(w) - 1; w &= w - 1u; out[pos++] = yseq[g * 32u + b]; }
   }
 }
 
-// sum over runs of equal (k0[, k1]) of c(c-1)/2; the thread at a run head walks its run.
-__global__ void __launch_bounds__(256)
-tie_pairs_kernel(const uint32_t* __restrict__ k0, const uint32_t* __restrict__ k1, const uint32_t* __restrict__ count,
-                 unsigned long long* __restrict__ out) {
-  const uint32_t M = *count;
-  unsigned long long local = 0;
-  for (uint32_t k = blockIdx.x * 256u + threadIdx.x; k < M; k += gridDim.x * 256u) {
-    const bool head = k == 0 || k0[k] != k0[k - 1] || (k1 && k1[k] != k1[k - 1]);
-    if (head) {
-      uint32_t e = k + 1;
-      while (e < M && k0[e] == k0[k] && (!k1 || k1[e] == k1[k])) ++e;
-      const unsigned long long c = e - k;
-      local += c * (c - 1) / 2;
-    }
-  }
-  local = (unsigned long long)warp_sum_ll((long long)local);
-  if (lane_id() == 0 && local) atomicAdd(out, local);
+__device__ __forceinline__ uint32_t kept_before(const uint2* __restrict__ tab, uint32_t x) {
+  const uint2 e = tab[x >> 5];
+  return e.y + __popc(e.x & ((1u << (x & 31u)) - 1u));
 }
 
-// One level of the bottom-up merge: runs of length L are merged pairwise; elements of the right run count the
-// left-run elements strictly greater than themselves (discordant pairs).
+// Tied pairs among the kept entries: sum over runs of c(c-1)/2 = sum over kept entries of the number of kept
+// entries before them in their run.  acc[r]: [0] tx  [1] ty  [2] txy.
 __global__ void __launch_bounds__(256)
-merge_level_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, const uint32_t* __restrict__ count,
-                   uint32_t L, unsigned long long* __restrict__ inversions) {
-  const uint32_t M = *count;
+tie_sums_kernel(const uint2* __restrict__ tables, uint32_t G, uint32_t N, const uint32_t* __restrict__ rs_x,
+                const uint32_t* __restrict__ rs_xy, const uint32_t* __restrict__ rs_y, unsigned long long* __restrict__ acc) {
+  const int r = blockIdx.y;
+  const uint2* __restrict__ txy_tab = tables + (size_t)r * G;
+  const uint2* __restrict__ ty_tab = tables + ((size_t)gridDim.y + r) * G;
+  unsigned long long tx = 0, ty = 0, txy = 0;
+  for (uint32_t k = blockIdx.x * 256u + threadIdx.x; k < N; k += gridDim.x * 256u) {
+    const uint2 e = txy_tab[k >> 5];
+    if ((e.x >> (k & 31u)) & 1u) {
+      const uint32_t here = e.y + __popc(e.x & ((1u << (k & 31u)) - 1u));
+      tx += here - kept_before(txy_tab, rs_x[k]);
+      txy += here - kept_before(txy_tab, rs_xy[k]);
+    }
+    const uint2 f = ty_tab[k >> 5];
+    if ((f.x >> (k & 31u)) & 1u)
+      ty += f.y + __popc(f.x & ((1u << (k & 31u)) - 1u)) - kept_before(ty_tab, rs_y[k]);
+  }
+  tx = (unsigned long long)warp_sum_ll((long long)tx);
+  ty = (unsigned long long)warp_sum_ll((long long)ty);
+  txy = (unsigned long long)warp_sum_ll((long long)txy);
+  if (lane_id() == 0) {
+    if (tx) atomicAdd(acc + (size_t)r * 4 + 0, tx);
+    if (ty) atomicAdd(acc + (size_t)r * 4 + 1, ty);
+    if (txy) atomicAdd(acc + (size_t)r * 4 + 2, txy);
+  }
+}
+
+// One merge step for element k of a sequence of sorted runs of length L: left-run elements go before equal
+// right-run elements; a right-run element counts the left-run elements strictly greater than itself.
+template <typename Src>
+__device__ __forceinline__ uint32_t merge_slot(const Src& in, uint32_t k, uint32_t M, uint32_t L, uint32_t v, uint32_t& greater) {
+  const uint32_t base = k / (2u * L) * (2u * L);
+  const uint32_t a1 = min(M, base + L), b1 = min(M, base + 2u * L);
+  if (k < a1) {
+    uint32_t lo = a1, hi = b1;                      // lower_bound in the right run
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (in[mid] < v) lo = mid + 1; else hi = mid; }
+    greater = 0;
+    return k + (lo - a1);
+  }
+  uint32_t lo = base, hi = a1;                      // upper_bound in the left run
+  while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (in[mid] <= v) lo = mid + 1; else hi = mid; }
+  greater = a1 - lo;
+  return base + (k - a1) + (lo - base);
+}
+
+// Levels 1 .. kTile/2 of the bottom-up merge inside shared memory: every CTA sorts one tile of the kept y
+// sequence and counts the inversions inside it.
+constexpr uint32_t kTile = 2048;
+
+__global__ void __launch_bounds__(256)
+tile_sort_kernel(const uint32_t* __restrict__ cy, uint32_t* __restrict__ out, int64_t stride, const uint32_t* __restrict__ counts,
+                 unsigned long long* __restrict__ acc) {
+  __shared__ uint32_t buf[2][kTile];
+  const int r = blockIdx.y;
+  const uint32_t M = counts[r];
+  const uint32_t base = blockIdx.x * kTile;
+  if (base >= M) return;
+  const uint32_t len = min(kTile, M - base);
+  const uint32_t* __restrict__ in = cy + (int64_t)r * stride + base;
+  for (uint32_t k = threadIdx.x; k < kTile; k += 256u) buf[0][k] = k < len ? in[k] : 0xFFFFFFFFu;
+  __syncthreads();
+  unsigned long long inv = 0;
+  int src = 0;
+  for (uint32_t L = 1; L < kTile; L <<= 1) {
+    const uint32_t* s = buf[src];
+    uint32_t* d = buf[src ^ 1];
+    for (uint32_t k = threadIdx.x; k < kTile; k += 256u) {
+      const uint32_t v = s[k];
+      uint32_t greater;
+      const uint32_t slot = merge_slot(s, k, kTile, L, v, greater);
+      d[slot] = v;
+      inv += greater;
+    }
+    __syncthreads();
+    src ^= 1;
+  }
+  uint32_t* __restrict__ o = out + (int64_t)r * stride + base;
+  for (uint32_t k = threadIdx.x; k < len; k += 256u) o[k] = buf[src][k];
+  inv = (unsigned long long)warp_sum_ll((long long)inv);
+  if (lane_id() == 0 && inv) atomicAdd(acc + (size_t)r * 4 + 3, inv);
+}
+
+// One level of the merge in global memory (runs of length L >= kTile), all replicates of the batch.
+__global__ void __launch_bounds__(256)
+merge_level_kernel(const uint32_t* __restrict__ in_all, uint32_t* __restrict__ out_all, int64_t stride,
+                   const uint32_t* __restrict__ counts, uint32_t L, unsigned long long* __restrict__ acc) {
+  const int r = blockIdx.y;
+  const uint32_t M = counts[r];
+  const uint32_t* __restrict__ in = in_all + (int64_t)r * stride;
+  uint32_t* __restrict__ out = out_all + (int64_t)r * stride;
   unsigned long long local = 0;
   for (uint32_t k = blockIdx.x * 256u + threadIdx.x; k < M; k += gridDim.x * 256u) {
-    const uint32_t base = k / (2u * L) * (2u * L);
-    const uint32_t a1 = min(M, base + L), b1 = min(M, base + 2u * L);
     const uint32_t v = in[k];
-    if (k < a1) {                                   // left run: goes before equal right elements
-      uint32_t lo = a1, hi = b1;                    // lower_bound in the right run
-      while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (in[mid] < v) lo = mid + 1; else hi = mid; }
-      out[k + (lo - a1)] = v;
-    } else {                                        // right run
-      uint32_t lo = base, hi = a1;                  // upper_bound in the left run
-      while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (in[mid] <= v) lo = mid + 1; else hi = mid; }
-      out[base + (k - a1) + (lo - base)] = v;
-      local += a1 - lo;                             // left elements > v
-    }
+    uint32_t greater;
+    const uint32_t slot = merge_slot(in, k, M, L, v, greater);
+    out[slot] = v;
+    local += greater;
   }
   local = (unsigned long long)warp_sum_ll((long long)local);
-  if (lane_id() == 0 && local) atomicAdd(inversions, local);
+  if (lane_id() == 0 && local) atomicAdd(acc + (size_t)r * 4 + 3, local);
 }
 
-// acc: [0] tx  [1] ty  [2] txy  [3] D ; counts: [0] M (x order)  [1] M (y order)
+// acc[r]: [0] tx  [1] ty  [2] txy  [3] D ; counts[r] = kept entries
 __global__ void kendall_finish_kernel(const unsigned long long* __restrict__ acc, const uint32_t* __restrict__ counts,
-                                      const uint32_t* __restrict__ nan_flag, double* __restrict__ out) {
+                                      const uint32_t* __restrict__ nan_flag, int Rb, double* __restrict__ out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= Rb) return;
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
-  const unsigned long long M = counts[0];
-  if (M < 2 || *nan_flag) { *out = nan; return; }
+  const unsigned long long M = counts[r];
+  if (M < 2 || *nan_flag) { out[r] = nan; return; }
   const unsigned long long n0 = M * (M - 1) / 2;
-  const unsigned long long tx = acc[0], ty = acc[1], txy = acc[2], D = acc[3];
-  if (tx == n0 || ty == n0) { *out = nan; return; }            // a constant vector: tau-b undefined (rsa.py:29-30)
+  const unsigned long long tx = acc[r * 4 + 0], ty = acc[r * 4 + 1], txy = acc[r * 4 + 2], D = acc[r * 4 + 3];
+  if (tx == n0 || ty == n0) { out[r] = nan; return; }          // a constant vector: tau-b undefined (rsa.py:29-30)
   const long long cd = (long long)n0 - (long long)tx - (long long)ty + (long long)txy - 2ll * (long long)D;
-  *out = (double)cd / (double)n0;
+  out[r] = (double)cd / (double)n0;
 }
 
-__global__ void zero_u64_kernel(unsigned long long* p, int count) {
-  if ((int)threadIdx.x < count) p[threadIdx.x] = 0ull;
+// workspace: what one RDM pair needs once, and what every replicate of a batch adds
+static size_t kendall_fixed_bytes(int n) {
+  const size_t Np = (size_t)round_up(triu_len(n), 32);
+  // xkey_c, ykey_c, 4 sort buffers, order_y, ysorted, order_xy, xseq, yseq, 3 run-start arrays
+  return 14 * arena_bytes(Np, 4) + arena_bytes(sort_count_elems(triu_len(n), 1), 4) + 4096;
 }
+static size_t kendall_per_replicate_bytes(int n) {
+  const size_t Np = (size_t)round_up(triu_len(n), 32);
+  const size_t G = Np / 32, nchunks = (G + kChunkGroups - 1) / kChunkGroups;
+  // two y sequences (ping-pong), two kept tables, pair bits, two chunk-total rows, accumulators and counts
+  return 2 * Np * 4 + 2 * G * 8 + G * 4 + 2 * nchunks * 4 + 4 * 8 + 2 * 4;
+}
+constexpr size_t kKendallSlack = 8192;       // 256-byte alignment of the per-batch arrays
+constexpr int kKendallMaxBatch = 64;
 
 }  // namespace vr
 
@@ -142,9 +305,12 @@ using namespace vr;
 
 extern "C" size_t vr_kendall_workspace_bytes(int n) {
   if (n < 2) return 256;
-  const size_t Np = (size_t)round_up(triu_len(n), 32);
-  // xkey_c, ykey_c, idx, 4 sort buffers, order_y, order_xy, xseq, yseq, ysorted, 4 compact/merge buffers, pairbits
-  return 16 * arena_bytes(Np, 4) + arena_bytes(sort_count_elems(triu_len(n), 1), 4) + arena_bytes(Np / 32, 4) + 4096;
+  return kendall_fixed_bytes(n) + kendall_per_replicate_bytes(n) + kKendallSlack;
+}
+extern "C" size_t vr_kendall_batch_workspace_bytes(int n, int R) {
+  if (n < 2 || R < 1) return 256;
+  const int rb = R < kKendallMaxBatch ? R : kKendallMaxBatch;
+  return kendall_fixed_bytes(n) + (size_t)rb * kendall_per_replicate_bytes(n) + kKendallSlack;
 }
 
 extern "C" int vr_kendall_tau_a(const float* rdmA, const float* rdmB, int n, int64_t ld, const uint32_t* masks, int R,
@@ -158,7 +324,14 @@ extern "C" int vr_kendall_tau_a(const float* rdmA, const float* rdmB, int n, int
   }
   const int64_t N = triu_len(n);
   const size_t Np = (size_t)round_up(N, 32);
+  const uint32_t G = (uint32_t)(Np / 32), words = G;
+  const uint32_t nchunks = (G + kChunkGroups - 1) / kChunkGroups;
   const int W = vr_mask_words(n);
+  // as many replicates per batch as the workspace holds (every batch is ~15 launches whatever its size)
+  int Rb = (int)((ws_bytes - kendall_fixed_bytes(n) - kKendallSlack) / kendall_per_replicate_bytes(n));
+  if (Rb > kKendallMaxBatch) Rb = kKendallMaxBatch;
+  if (Rb > R) Rb = R;
+  if (Rb < 1) Rb = 1;
   Arena a(ws, ws_bytes);
   uint32_t* xkey_c = a.take<uint32_t>(Np);
   uint32_t* ykey_c = a.take<uint32_t>(Np);
@@ -171,21 +344,25 @@ extern "C" int vr_kendall_tau_a(const float* rdmA, const float* rdmB, int n, int
   uint32_t* order_xy = a.take<uint32_t>(Np);    // pair indices in (x, y) order
   uint32_t* xseq = a.take<uint32_t>(Np);        // x keys in (x, y) order
   uint32_t* yseq = a.take<uint32_t>(Np);        // y keys in (x, y) order
-  uint32_t* cx = a.take<uint32_t>(Np);          // compacted x keys
-  uint32_t* cy = a.take<uint32_t>(Np);          // compacted y keys (x, y order)
-  uint32_t* cy2 = a.take<uint32_t>(Np);         // merge ping-pong
-  uint32_t* cys = a.take<uint32_t>(Np);         // compacted y keys (y order)
+  uint32_t* rs_x = a.take<uint32_t>(Np);        // run starts: equal x / equal (x, y) in (x, y) order, equal y in y order
+  uint32_t* rs_xy = a.take<uint32_t>(Np);
+  uint32_t* rs_y = a.take<uint32_t>(Np);
   uint32_t* counts_sort = a.take<uint32_t>(sort_count_elems(N, 1));
-  uint32_t* pairbits = a.take<uint32_t>(Np / 32);
-  unsigned long long* acc = a.take<unsigned long long>(8);
-  uint32_t* small = a.take<uint32_t>(8);        // [0] M (x order) [1] M (y order) [2] nan flag
+  uint32_t* cy = a.take<uint32_t>((size_t)Rb * Np);       // kept y keys in (x, y) order, per replicate
+  uint32_t* cy2 = a.take<uint32_t>((size_t)Rb * Np);      // merge ping-pong
+  uint2* tables = a.take<uint2>((size_t)2 * Rb * G);
+  uint32_t* pairbits = a.take<uint32_t>((size_t)Rb * words);
+  uint32_t* chunk_tot = a.take<uint32_t>((size_t)2 * Rb * nchunks);
+  unsigned long long* acc = a.take<unsigned long long>((size_t)Rb * 4);
+  uint32_t* counts = a.take<uint32_t>((size_t)2 * Rb);    // kept entries: [0][r] from the (x, y) order, [1][r] from the y order
+  uint32_t* nan_flag = a.take<uint32_t>(8);
   if (!a.ok) { set_error("vr_kendall_tau_a: internal workspace plan overflow"); return VR_ERR_WORKSPACE; }
   ProfScope prof(F_KENDALL, stream);
   const unsigned nblk = (unsigned)((N + 255) / 256);
 
-  VR_CHECK_CUDA(cudaMemsetAsync(small, 0, 8 * sizeof(uint32_t), stream));
+  VR_CHECK_CUDA(cudaMemsetAsync(nan_flag, 0, 8 * sizeof(uint32_t), stream));
   dim3 grid((n + 255) / 256, n);
-  kendall_keys_kernel<<<grid, 256, 0, stream>>>(rdmA, rdmB, n, ld, xkey_c, ykey_c, v0, small + 2);
+  kendall_keys_kernel<<<grid, 256, 0, stream>>>(rdmA, rdmB, n, ld, xkey_c, ykey_c, v0, nan_flag);
   VR_CHECK_LAUNCH();
   // sort by y, carrying the pair index
   VR_CHECK_CUDA(cudaMemcpyAsync(k0, ykey_c, (size_t)N * 4, cudaMemcpyDeviceToDevice, stream));
@@ -202,33 +379,42 @@ extern "C" int vr_kendall_tau_a(const float* rdmA, const float* rdmB, int n, int
   VR_CHECK_CUDA(cudaMemcpyAsync(order_xy, v0, (size_t)N * 4, cudaMemcpyDeviceToDevice, stream));
   gather_kernel<<<nblk, 256, 0, stream>>>(ykey_c, order_xy, (uint32_t)N, yseq);
   VR_CHECK_LAUNCH();
+  run_start_kernel<<<nblk, 256, 0, stream>>>(xseq, nullptr, (uint32_t)N, rs_x);
+  VR_CHECK_LAUNCH();
+  run_start_kernel<<<nblk, 256, 0, stream>>>(xseq, yseq, (uint32_t)N, rs_xy);
+  VR_CHECK_LAUNCH();
+  run_start_kernel<<<nblk, 256, 0, stream>>>(ysorted, nullptr, (uint32_t)N, rs_y);
+  VR_CHECK_LAUNCH();
 
-  const uint32_t words = (uint32_t)(Np / 32);
-  const int mgrid = (int)(nblk < 4 * kNumSMs ? nblk : 4 * kNumSMs);
-  for (int r = 0; r < R; ++r) {
-    dim3 pg((words + 255) / 256 < 64 ? (words + 255) / 256 : 64, 1);
-    pair_mask_kernel<<<pg, 256, (size_t)W * 4, stream>>>(masks + (size_t)r * W, 1, n, W, words, pairbits);
+  KendallOrders ord;
+  ord.order[0] = order_xy;
+  ord.order[1] = order_y;
+  const unsigned mgrid = nblk < 2u * kNumSMs ? nblk : 2u * kNumSMs;
+  const unsigned tiles = (unsigned)((N + kTile - 1) / kTile);
+  for (int r0 = 0; r0 < R; r0 += Rb) {
+    const int rb = R - r0 < Rb ? R - r0 : Rb;
+    VR_CHECK_CUDA(cudaMemsetAsync(acc, 0, (size_t)rb * 4 * sizeof(unsigned long long), stream));
+    dim3 pg((words + 255) / 256 < 64 ? (words + 255) / 256 : 64, rb);
+    pair_mask_kernel<<<pg, 256, (size_t)W * 4, stream>>>(masks + (size_t)r0 * W, rb, n, W, words, pairbits);
     VR_CHECK_LAUNCH();
-    zero_u64_kernel<<<1, 32, 0, stream>>>(acc, 8);
+    kept_words_kernel<<<dim3(nchunks, rb, 2), 256, 0, stream>>>(ord, pairbits, words, (uint32_t)N, G, tables, chunk_tot, nchunks);
     VR_CHECK_LAUNCH();
-    compact_kernel<<<1, 1024, 0, stream>>>(order_xy, pairbits, (uint32_t)N, xseq, yseq, cx, cy, small + 0);
+    chunk_scan_kernel<<<dim3(rb, 2), 1024, 0, stream>>>(chunk_tot, nchunks, counts);
     VR_CHECK_LAUNCH();
-    compact_kernel<<<1, 1024, 0, stream>>>(order_y, pairbits, (uint32_t)N, ysorted, nullptr, cys, nullptr, small + 1);
+    kept_finish_kernel<<<dim3(nchunks, rb, 2), 256, 0, stream>>>(tables, chunk_tot, nchunks, G, (uint32_t)N, yseq, cy, (int64_t)Np);
     VR_CHECK_LAUNCH();
-    tie_pairs_kernel<<<mgrid, 256, 0, stream>>>(cx, nullptr, small + 0, acc + 0);
+    tie_sums_kernel<<<dim3(mgrid, rb), 256, 0, stream>>>(tables, G, (uint32_t)N, rs_x, rs_xy, rs_y, acc);
     VR_CHECK_LAUNCH();
-    tie_pairs_kernel<<<mgrid, 256, 0, stream>>>(cys, nullptr, small + 1, acc + 1);
+    tile_sort_kernel<<<dim3(tiles, rb), 256, 0, stream>>>(cy, cy2, (int64_t)Np, counts, acc);
     VR_CHECK_LAUNCH();
-    tie_pairs_kernel<<<mgrid, 256, 0, stream>>>(cx, cy, small + 0, acc + 2);
-    VR_CHECK_LAUNCH();
-    uint32_t* src = cy;
-    uint32_t* dst = cy2;
-    for (uint64_t L = 1; L < (uint64_t)N; L <<= 1) {     // M <= N: levels beyond M are no-ops that only copy
-      merge_level_kernel<<<mgrid, 256, 0, stream>>>(src, dst, small + 0, (uint32_t)L, acc + 3);
+    uint32_t* src = cy2;
+    uint32_t* dst = cy;
+    for (uint64_t L = kTile; L < (uint64_t)N; L <<= 1) {      // M <= N: levels beyond M only copy
+      merge_level_kernel<<<dim3(mgrid, rb), 256, 0, stream>>>(src, dst, (int64_t)Np, counts, (uint32_t)L, acc);
       VR_CHECK_LAUNCH();
       uint32_t* t = src; src = dst; dst = t;
     }
-    kendall_finish_kernel<<<1, 1, 0, stream>>>(acc, small, small + 2, out + r);
+    kendall_finish_kernel<<<(rb + 63) / 64, 64, 0, stream>>>(acc, counts, nan_flag, rb, out + r0);
     VR_CHECK_LAUNCH();
   }
   return VR_OK;

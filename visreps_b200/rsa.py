@@ -268,7 +268,7 @@ def compare_grouped(model: Sequence[PresortedRDM], neural: Sequence[PresortedRDM
             full = len(ma) == nA and len(mb) == nB
             part = out if full else torch.empty((len(ma), len(mb), R), dtype=torch.float64, device=dev)
             if method == "kendall":
-                ws = _lib.workspace(lib.vr_kendall_workspace_bytes(n), dev)
+                ws = _lib.workspace(lib.vr_kendall_batch_workspace_bytes(n, R), dev)
                 for ia, a in enumerate(ma):
                     for ib, b in enumerate(mb):
                         ra = a.rdm if a.rdm.stride(0) == n else a.rdm.contiguous()
