@@ -33,7 +33,7 @@ namespace vr {
 constexpr int kRankThreadsMat = 1024;   // materialise: 64 registers per thread
 constexpr int kRankThreadsFused = 768;  // fused: 85 registers per thread, all 8 materialised loads in flight
                                         // (512 threads x two groups: 11.2 ms, 1024 threads x two load batches: 11.0 ms, this: 10.1 ms)
-constexpr int kCountThreads = 512;
+constexpr int kCountThreads = 1024;  // 32 warp segments per (vector, 32-replicate batch): 8192 warps fill the machine at NSD shape
 constexpr int kCountWarps = kCountThreads / 32;
 constexpr int kMaxVectors = 64;
 constexpr size_t kRankSmemTableMax = 200 * 1024;   // bytes of shared memory the table may take
@@ -101,8 +101,22 @@ __device__ __forceinline__ uint32_t warp_bit_transpose(uint32_t w, unsigned lane
   return w;
 }
 
-// tables: [vector][replicate][Gs] of {kept word, kept count before the group}.
+// Count tables: {kept word, kept count before the group} per 32 sorted positions, Gs entries per (vector,
+// replicate); a vector's replicates are padded to a multiple of 32 (table_entry_offset).
+//   linear      [replicate][Gs]: what rank_kernel reads in place when the table does not fit shared memory;
+//   interleaved [replicate / 32][Gs / 2][replicate % 32][2]: a lane of count_kernel owns one replicate, so
+//               the 32 lanes' 16-byte pieces of a group pair are one contiguous 512-byte store (the linear
+//               layout scatters them over 32 tables: 64 wavefronts per four groups, the kernel's whole cost);
+//               rank_kernel straightens it out while copying the table into shared memory.
+__host__ __device__ inline int64_t table_vector_stride(int64_t R, uint32_t Gs) { return (R + 31) / 32 * 32 * (int64_t)Gs; }
+template <bool kInterleaved>
+__device__ __forceinline__ int64_t table_entry_offset(int r, uint32_t g, uint32_t Gs) {
+  if (!kInterleaved) return (int64_t)r * Gs + g;
+  return (int64_t)(r >> 5) * 32 * Gs + (int64_t)(g >> 1) * 64 + (r & 31) * 2 + (g & 1u);
+}
+
 // Dynamic shared memory: maskT of the batch, n words.
+template <bool kInterleaved>
 __global__ void __launch_bounds__(kCountThreads)
 count_kernel(const __grid_constant__ BlobList blobs, int n, const uint32_t* __restrict__ maskT, int R,
              uint2* __restrict__ tables, uint32_t Gs, uint32_t* __restrict__ seg_tot) {
@@ -122,7 +136,7 @@ count_kernel(const __grid_constant__ BlobList blobs, int n, const uint32_t* __re
   __syncthreads();
 
   const int rep = batch * 32 + (int)lane;                 // the replicate this lane accumulates
-  uint2* __restrict__ my_table = tables + ((int64_t)v * R + min(rep, R - 1)) * Gs;
+  uint2* __restrict__ vec_table = tables + (int64_t)v * table_vector_stride(R, Gs);
   uint32_t running = 0;
   for (uint32_t g0 = g_lo; g0 < g_hi; g0 += 4u) {          // g_lo is a multiple of 32: 4-group steps stay aligned
     uint32_t wd[4];
@@ -136,10 +150,9 @@ count_kernel(const __grid_constant__ BlobList blobs, int n, const uint32_t* __re
       C[q] = running;
       running += __popc(K[q]);
     }
-    if (rep < R) {
-      uint4* dst = reinterpret_cast<uint4*>(my_table + g0);
-      dst[0] = make_uint4(K[0], C[0], K[1], C[1]);
-      dst[1] = make_uint4(K[2], C[2], K[3], C[3]);
+    if (kInterleaved || rep < R) {     // interleaved: the padding replicates' slots exist and keep the store whole
+      *reinterpret_cast<uint4*>(vec_table + table_entry_offset<kInterleaved>(rep, g0, Gs)) = make_uint4(K[0], C[0], K[1], C[1]);
+      *reinterpret_cast<uint4*>(vec_table + table_entry_offset<kInterleaved>(rep, g0 + 2u, Gs)) = make_uint4(K[2], C[2], K[3], C[3]);
     }
   }
   // counts are relative to the warp's segment; rank_kernel adds the segment bases from seg_tot
@@ -229,7 +242,8 @@ rank_kernel(const __grid_constant__ RankArgs A) {
     const int r = kFused ? (int)(item / n_vec) : (int)(item % R);
     PresortView blob = presort_view(const_cast<void*>(A.blobs.p[v]), n);
     const int64_t tix = (int64_t)(A.table_base + v) * R + r;
-    uint2* __restrict__ g_table = A.tables + tix * Gs;
+    uint2* __restrict__ vec_table = A.tables + (int64_t)(A.table_base + v) * table_vector_stride(R, Gs);
+    uint2* __restrict__ g_table = vec_table + (int64_t)r * Gs;     // linear layout (table read in place)
     if (threadIdx.x == 0) {                                  // exclusive prefix of the segment totals
       uint32_t run = 0;
       for (int w = 0; w < kCountWarps; ++w) { s_base[w] = run; run += A.seg_tot[tix * kCountWarps + w]; }
@@ -243,7 +257,7 @@ rank_kernel(const __grid_constant__ RankArgs A) {
       uint2* dst = kSmemTable ? s_table : g_table;
       for (uint32_t g = threadIdx.x; g < Gs; g += kRankThreads) {
         uint2 e = make_uint2(0u, Ns);
-        if (g < G) { e = g_table[g]; e.y += s_base[g / seg_groups]; }
+        if (g < G) { e = vec_table[table_entry_offset<kSmemTable>(r, g, Gs)]; e.y += s_base[g / seg_groups]; }
         dst[g] = e;
       }
     }
@@ -494,21 +508,27 @@ static int build_rank_context(const uint32_t* masks, int n, int R, void* ctx, cu
 
 // count tables + segment totals of nV vectors x R replicates
 static inline size_t tables_bytes(int n, int nV, int64_t R) {
-  return arena_bytes((size_t)nV * R * table_groups(n), 8) + arena_bytes((size_t)nV * R * kCountWarps, 4);
+  return arena_bytes((size_t)nV * table_vector_stride(R, table_groups(n)), 8) + arena_bytes((size_t)nV * R * kCountWarps, 4);
 }
 static int launch_count(const BlobList& blobs, int nV, int n, const RankContext& ctx, int R, void* ws, size_t ws_bytes,
                         uint2** tables, uint32_t** seg_tot, cudaStream_t stream) {
   const uint32_t Gs = table_groups(n);
   Arena a(ws, ws_bytes);
-  *tables = a.take<uint2>((size_t)nV * R * Gs);
+  *tables = a.take<uint2>((size_t)nV * table_vector_stride(R, Gs));
   *seg_tot = a.take<uint32_t>((size_t)nV * R * kCountWarps);
   if (!a.ok) { set_error("rank workspace too small for the count tables"); return VR_ERR_WORKSPACE; }
   static unsigned long long attr_done = 0;
   const size_t smem = (size_t)n * 4;
-  if (smem > 40 * 1024) VR_CHECK_CUDA(ensure_dynamic_smem(count_kernel, 160 * 1024, &attr_done));
+  static unsigned long long attr_done_i = 0;
+  const bool interleaved = rank_table_in_smem(n);          // rank_kernel copies the table to shared memory
+  if (smem > 40 * 1024) {
+    if (interleaved) VR_CHECK_CUDA(ensure_dynamic_smem(count_kernel<true>, 160 * 1024, &attr_done_i));
+    else VR_CHECK_CUDA(ensure_dynamic_smem(count_kernel<false>, 160 * 1024, &attr_done));
+  }
   ProfScope prof(F_KEPT, stream);
   dim3 grid((R + 31) / 32, nV);
-  count_kernel<<<grid, kCountThreads, smem, stream>>>(blobs, n, ctx.maskT, R, *tables, Gs, *seg_tot);
+  if (interleaved) count_kernel<true><<<grid, kCountThreads, smem, stream>>>(blobs, n, ctx.maskT, R, *tables, Gs, *seg_tot);
+  else count_kernel<false><<<grid, kCountThreads, smem, stream>>>(blobs, n, ctx.maskT, R, *tables, Gs, *seg_tot);
   VR_CHECK_LAUNCH();
   return VR_OK;
 }
@@ -691,7 +711,7 @@ SpearmanPlan spearman_plan(int n, int nA, int nB) {
   const int nF = nA <= nB ? nB : nA;
   const int stage = group > nF ? group : nF;
   SpearmanPlan p;
-  p.fixed = 16 * 256 + (size_t)n * 4 * 2 + 4096;
+  p.fixed = 16 * 256 + (size_t)n * 4 * 2 + 4096 + (size_t)32 * stage * table_groups(n) * 8;   // tables pad replicates to 32
   p.per_rep = (size_t)vr_dev_stride(n) / 8 + (size_t)n / 8 + 8 +                      // context
               (size_t)stage * ((size_t)table_groups(n) * 8 + 4 * kCountWarps) +      // count tables
               (size_t)group * ((size_t)vr_dev_stride(n) * 4 + 8);                    // dev + ss
