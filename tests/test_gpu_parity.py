@@ -604,3 +604,60 @@ def test_kendall_batches_ties_and_small_workspace(dev):
     np.testing.assert_allclose(outs[0][1:], orc.bootstrap_compare_with_indices(a, b, "kendall", idx), atol=SCORE_TOL, rtol=0)
     assert lib.vr_kendall_tau_a(xa.data_ptr(), yb.data_ptr(), n, n, masks.data_ptr(), R, out.data_ptr(),
                                 small.data_ptr(), small.numel() - 4096, _lib.stream_ptr()) == 2      # VR_ERR_WORKSPACE
+
+
+def test_pearson_inclusion_exclusion_paths_and_nan_semantics(dev):
+    """The Pearson bootstrap sums over the DROPPED stimuli (inclusion-exclusion) and falls back to the kept pairs
+    when a mask drops more than 2048 stimuli; a NaN entry makes exactly those replicates NaN that keep its pair."""
+    rs = np.random.RandomState(31)
+    n = 90
+    a = orc.rdm(torch.from_numpy(rs.standard_normal((n, 30)).astype(np.float32)))
+    b = orc.rdm(torch.from_numpy(rs.standard_normal((n, 12)).astype(np.float32)))
+    c = orc.rdm(torch.from_numpy(rs.standard_normal((n, 7)).astype(np.float32)))
+    # arbitrary masks: keep 2 .. n stimuli
+    sets = [np.sort(rs.choice(n, size=k, replace=False)) for k in (2, 3, 17, 45, 80, 89, 90)]
+    W = (n + 31) // 32
+    words = np.zeros((len(sets), W), dtype=np.uint32)
+    for r, ks in enumerate(sets):
+        for i in ks:
+            words[r, i >> 5] |= np.uint32(1) << np.uint32(i & 31)
+    masks = torch.from_numpy(words.view(np.int32)).to(dev)
+    out = vrsa.compare_grouped([vrsa._RawRDM(a.to(dev)), vrsa._RawRDM(c.to(dev))], [vrsa._RawRDM(b.to(dev))], "pearson", masks).cpu().numpy()
+    for r, ks in enumerate(sets):
+        for k, m in enumerate((a, c)):
+            sub = torch.from_numpy(ks)
+            want = orc.rdm_compare(m[sub][:, sub], b[sub][:, sub], correlation="Pearson")
+            got = out[k, 0, r]
+            assert (math.isnan(want) and math.isnan(got)) or abs(got - want) <= SCORE_TOL, (r, k, got, want)
+    # NaN entries: stimulus 5's row/column is NaN in `a`
+    bad = a.clone()
+    bad[5, :] = float("nan"); bad[:, 5] = float("nan"); bad[5, 5] = 0.0
+    keep_all = np.arange(n)
+    without5 = np.array([i for i in range(n) if i not in (5, 40)])
+    words = np.zeros((2, W), dtype=np.uint32)
+    for r, ks in enumerate((keep_all, without5)):
+        for i in ks:
+            words[r, i >> 5] |= np.uint32(1) << np.uint32(i & 31)
+    out = vrsa.compare_grouped([vrsa._RawRDM(bad.to(dev))], [vrsa._RawRDM(b.to(dev))], "pearson",
+                               torch.from_numpy(words.view(np.int32)).to(dev)).cpu().numpy()[0, 0]
+    assert math.isnan(out[0])
+    sub = torch.from_numpy(without5)
+    assert abs(out[1] - orc.rdm_compare(a[sub][:, sub], b[sub][:, sub], correlation="Pearson")) <= SCORE_TOL
+    # more than 2048 dropped stimuli: the direct sum over the kept pairs
+    n2 = 2200
+    x = torch.from_numpy(rs.standard_normal((n2, 16)).astype(np.float32))
+    y = x + torch.from_numpy(rs.standard_normal((n2, 16)).astype(np.float32))
+    ra, rb = vb.compute_rdm(x.to(dev)), vb.compute_rdm(y.to(dev))
+    ks = np.sort(rs.choice(n2, size=120, replace=False))
+    words = np.zeros((2, (n2 + 31) // 32), dtype=np.uint32)
+    for i in ks:
+        words[0, i >> 5] |= np.uint32(1) << np.uint32(i & 31)
+    words[1, :] = 0xFFFFFFFF
+    words[1, -1] = (1 << (n2 % 32)) - 1 if n2 % 32 else 0xFFFFFFFF
+    out = vrsa.compare_grouped([vrsa._RawRDM(ra)], [vrsa._RawRDM(rb)], "pearson", torch.from_numpy(words.view(np.int32)).to(dev)).cpu().numpy()[0, 0]
+    sub = torch.from_numpy(ks).to(dev)
+    iu = np.triu_indices(len(ks), 1)
+    va, vbv = ra[sub][:, sub].cpu().numpy()[iu].astype(np.float64), rb[sub][:, sub].cpu().numpy()[iu].astype(np.float64)
+    assert abs(out[0] - np.corrcoef(va, vbv)[0, 1]) <= SCORE_TOL
+    iu = np.triu_indices(n2, 1)
+    assert abs(out[1] - np.corrcoef(ra.cpu().numpy()[iu].astype(np.float64), rb.cpu().numpy()[iu].astype(np.float64))[0, 1]) <= SCORE_TOL

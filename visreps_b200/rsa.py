@@ -288,11 +288,12 @@ def compare_grouped(model: Sequence[PresortedRDM], neural: Sequence[PresortedRDM
                     rows = [r.contiguous() for r in rows]
                     ld = n
                 pa, pb = _ptr_array(rows[:len(ma)]), _ptr_array(rows[len(ma):])
+                ws = _lib.workspace(lib.vr_bootstrap_pearson_workspace_bytes(n, len(ma), len(mb), R), dev)
                 for r0 in range(0, R, 65535):
                     rc = min(65535, R - r0)
                     sub = part if rc == R else torch.empty((len(ma), len(mb), rc), dtype=torch.float64, device=dev)
                     _lib.check(lib.vr_bootstrap_pearson(pa, len(ma), pb, len(mb), n, ld, masks[r0:r0 + rc].data_ptr(), rc,
-                                                        sub.data_ptr(), None, 0, _lib.stream_ptr()), "vr_bootstrap_pearson")
+                                                        sub.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "vr_bootstrap_pearson")
                     if sub is not part:
                         part[:, :, r0:r0 + rc] = sub
             if not full:
