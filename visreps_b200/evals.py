@@ -101,3 +101,8 @@ def eval_rsa_scores(train_acts_by_pair: Mapping[Hashable, Mapping[str, torch.Ten
     for k in test_neural_by_pair.keys():
         best[k], sel_scores[k] = select_layer(train_acts_by_pair[k], train_neural_by_pair[k], method, n_select)
     return score_pairs(test_features, test_neural_by_pair, best, method, bootstrap, n_bootstrap, sel_scores)
+
+
+def _compare_rdms(rdm1: torch.Tensor, rdm2: torch.Tensor, correlation: str) -> float:
+    """`experiments/binary_pc_rsa/main.py:28-38`: the same comparison with a positional method name."""
+    return rsa.compute_rdm_correlation(rdm1, rdm2, correlation=correlation)
