@@ -170,8 +170,10 @@ int vr_rank_fused(const void* const* blobs_host, int nF, int n, const void* ctx,
  * nB neural RDMs x R masks in one call.  A mask with all n bits set gives the point
  * estimate (evals.py:347).  out is (nA, nB, R) fp64, replicate order = mask order.
  *   Spearman: inputs are presorted blobs (host arrays of device pointers).
- *   Pearson : inputs are the RDMs themselves (n x n fp32, leading dimension ld).
- * Undefined correlations (constant vector, < 2 kept stimuli, NaN input) give NaN.
+ *   Pearson : inputs are the RDMs themselves (n x n fp32, leading dimension ld); only the strict
+ *             upper triangle is read.  The moments of every replicate are taken by inclusion-exclusion
+ *             over its DROPPED stimuli (totals and row sums live in the workspace, which is required).
+ * Undefined correlations (constant vector, < 2 kept stimuli, a NaN among the kept pairs) give NaN.
  * ---------------------------------------------------------------------------------- */
 size_t vr_bootstrap_spearman_workspace_bytes(int n, int nA, int nB, int R);
 int vr_bootstrap_spearman(const void* const* presortedA_host, int nA,
