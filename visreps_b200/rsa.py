@@ -665,9 +665,18 @@ def _spearman_pipeline(inputs_a: Sequence[torch.Tensor], inputs_b: Sequence[torc
     # materialised side, and as many of the fused side's matrices (smallest first) as will have landed
     # by the time the draw is done (host draw ~8.5 ns per index, copies ~50 GB/s).  The compute stream
     # only waits on copy events, never the host.
-    m_items = PresortedRDM.batch([rdm_of(st, slot_m(k)) for k, st in enumerate(staged_m)])
     f_items: Dict[int, PresortedRDM] = {}
-    if fus_on_device:
+    if fus_on_device and len(mats) + len(fus) <= _MAX_GROUP * 2:
+        # everything is here already: one batched presort for both sides (half the sort launches)
+        both = PresortedRDM.batch([rdm_of(st, slot_m(k)) for k, st in enumerate(staged_m)] +
+                                  [rdm_of(staged_f[k], slot_f(k)) for k in range(len(fus))])
+        m_items = both[:len(mats)]
+        f_items = dict(enumerate(both[len(mats):]))
+    else:
+        m_items = PresortedRDM.batch([rdm_of(st, slot_m(k)) for k, st in enumerate(staged_m)])
+    if f_items:
+        pass
+    elif fus_on_device:
         for k, it in enumerate(PresortedRDM.batch([rdm_of(staged_f[k], slot_f(k)) for k in range(len(fus))])):
             f_items[k] = it
     elif index_sets is None:
