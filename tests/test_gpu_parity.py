@@ -661,3 +661,28 @@ def test_pearson_inclusion_exclusion_paths_and_nan_semantics(dev):
     assert abs(out[0] - np.corrcoef(va, vbv)[0, 1]) <= SCORE_TOL
     iu = np.triu_indices(n2, 1)
     assert abs(out[1] - np.corrcoef(ra.cpu().numpy()[iu].astype(np.float64), rb.cpu().numpy()[iu].astype(np.float64))[0, 1]) <= SCORE_TOL
+
+
+def test_rdm_wide_rows_single_pass_centring(dev):
+    """Rows of >= 16384 features are centred in one pass around a sampled shift, with the remainder of the mean
+    removed in the epilogue; offsets, block structure and sparsity must not cost accuracy (1e-5 vs fp64)."""
+    rs = np.random.RandomState(123)
+    n, d = 96, 20000
+    base = rs.standard_normal((n, d)).astype(np.float32)
+    x = base.copy()
+    x[0:16] += 50.0                                            # a large common offset
+    x[16:32, : d // 2] = 0.0                                   # block structure: the sample mean is not the mean
+    x[16:32, d // 2:] = x[16:32, d // 2:] * 3 + 40.0
+    x[32:48] = np.maximum(x[32:48], 0)                         # post-ReLU sparsity
+    x[48:56, ::7] += 1000.0                                    # periodic spikes that alias with a strided sample
+    x[56] = 3.25                                               # a constant row
+    t = torch.from_numpy(x)
+    got = vb.compute_rdm(t.to(dev)).cpu().double().numpy()
+    xd = x.astype(np.float64)
+    xc = xd - xd.mean(1, keepdims=True)
+    sd = np.sqrt((xc ** 2).mean(1) + 1e-12)
+    truth = 1 - np.clip((xc @ xc.T) / d / (sd[:, None] * sd[None, :] + 1e-12), -1, 1)
+    np.fill_diagonal(truth, 0.0)
+    assert np.abs(got - truth).max() <= RDM_TOL
+    assert np.abs(got - orc.rdm(t).double().numpy()).max() <= RDM_TOL
+    assert np.array_equal(got, got.T) and not np.diag(got).any()

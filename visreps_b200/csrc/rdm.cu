@@ -40,42 +40,65 @@ inline RdmPlan rdm_plan(int n, int64_t d) {
 }
 
 // One CTA per (padded) row.  Rows >= n and columns >= d are written as zeros.
+//
+// The row is shifted by a value c close to its mean, split into tf32 hi/lo planes, and the statistics of the
+// shifted values v = x - c are kept: delta = mean(v) (the part of the mean c missed) and the variance
+// mean(v^2) - delta^2.  The epilogue removes d * delta_i * delta_j from the Gram entries, so the result is the
+// covariance of exactly centred rows whatever c was; c only has to be close enough that v carries no large
+// common offset (which would cost tf32 mantissa bits).
+//   kSampledShift = false: c = the row mean (fp64 sum, rounded to fp32): two passes over the row.
+//   kSampledShift = true : c = the mean of 2048 samples strided across the row: ONE pass over the row.  Used for
+//                          wide rows, where the second pass no longer hits L2 and costs a full HBM read.
+constexpr int kShiftSamples = 2048;
+constexpr int64_t kSinglePassMinCols = 16384;
+
+template <bool kSampledShift>
 __global__ void __launch_bounds__(256)
 row_center_kernel(const float* __restrict__ X, int n, int64_t d, int64_t ldx, float correction,
                   float* __restrict__ Z, float* __restrict__ Zlo, int64_t d_pad, float* __restrict__ stdv,
-                  int* __restrict__ zero_rows) {
+                  double* __restrict__ delta, int* __restrict__ zero_rows) {
   __shared__ double s_red[8];
-  __shared__ float s_mean;
+  __shared__ double s_red2[8];
+  __shared__ float s_shift;
   const int row = blockIdx.x;
-  // Z / Zlo receive the tf32 split of the centred row: hi = rn_tf32(z), lo = rn_tf32(z - hi)
-  // (z - hi is exact in fp32).
+  // Z / Zlo receive the tf32 split of the shifted row: hi = rn_tf32(v), lo = rn_tf32(v - hi)
+  // (v - hi is exact in fp32).
   float* z = Z + (int64_t)row * d_pad;
   float* zl = Zlo + (int64_t)row * d_pad;
   if (row >= n) {
     for (int64_t c = threadIdx.x; c < d_pad; c += 256) { z[c] = 0.f; zl[c] = 0.f; }
+    if (threadIdx.x == 0) { stdv[row] = 1.f; delta[row] = 0.0; }
     return;
   }
   const float* x = X + (int64_t)row * ldx;
   // 16-byte path when the row start is aligned: float4 loads / stores, 4 values folded in fp32 before each
-  // fp64 accumulation.  The second pass over the row is served by L2.
+  // fp64 accumulation.
   const bool vec = (reinterpret_cast<uintptr_t>(x) & 15u) == 0;
   const int64_t d4 = vec ? (d & ~(int64_t)3) : 0;           // elements covered by the vector path
   double acc = 0.0;
-  for (int64_t c = (int64_t)threadIdx.x * 4; c < d4; c += 1024) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(x + c));
-    acc += (double)((v.x + v.y) + (v.z + v.w));
+  double count = (double)d;
+  if (kSampledShift) {
+    const int64_t stride = d / kShiftSamples;                 // >= 8 (d >= kSinglePassMinCols)
+    for (int k = threadIdx.x; k < kShiftSamples; k += 256) acc += (double)__ldg(x + (int64_t)k * stride);
+    count = (double)kShiftSamples;
+  } else {
+    for (int64_t c = (int64_t)threadIdx.x * 4; c < d4; c += 1024) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x + c));
+      acc += (double)((v.x + v.y) + (v.z + v.w));
+    }
+    for (int64_t c = d4 + threadIdx.x; c < d; c += 256) acc += (double)x[c];
   }
-  for (int64_t c = d4 + threadIdx.x; c < d; c += 256) acc += (double)x[c];
   acc = warp_sum(acc);
   if (lane_id() == 0) s_red[threadIdx.x >> 5] = acc;
   __syncthreads();
   if (threadIdx.x == 0) {
     double t = 0.0;
     for (int w = 0; w < 8; ++w) t += s_red[w];
-    s_mean = (float)(t / (double)d);
+    const float c = (float)(t / count);
+    s_shift = (c == c && fabsf(c) <= 3.0e38f) ? c : 0.f;
   }
   __syncthreads();
-  const float mean = s_mean;
+  const float shift = s_shift;
   auto split = [](float v, float& hi, float& lo) {
     uint32_t hb, lb;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
@@ -84,10 +107,12 @@ row_center_kernel(const float* __restrict__ X, int n, int64_t d, int64_t ldx, fl
     lo = __uint_as_float(lb);
   };
   acc = 0.0;
+  double acc1 = 0.0;
   for (int64_t c = (int64_t)threadIdx.x * 4; c < d4; c += 1024) {
     const float4 xv = __ldg(reinterpret_cast<const float4*>(x + c));
-    const float v0 = xv.x - mean, v1 = xv.y - mean, v2 = xv.z - mean, v3 = xv.w - mean;
+    const float v0 = xv.x - shift, v1 = xv.y - shift, v2 = xv.z - shift, v3 = xv.w - shift;
     acc += (double)((v0 * v0 + v1 * v1) + (v2 * v2 + v3 * v3));
+    acc1 += (double)((v0 + v1) + (v2 + v3));
     float4 h, l;
     split(v0, h.x, l.x); split(v1, h.y, l.y); split(v2, h.z, l.z); split(v3, h.w, l.w);
     *reinterpret_cast<float4*>(z + c) = h;
@@ -95,29 +120,35 @@ row_center_kernel(const float* __restrict__ X, int n, int64_t d, int64_t ldx, fl
   }
   for (int64_t c = d4 + threadIdx.x; c < d_pad; c += 256) {
     float v = 0.f;
-    if (c < d) { v = x[c] - mean; acc += (double)v * (double)v; }
+    if (c < d) { v = x[c] - shift; acc += (double)v * (double)v; acc1 += (double)v; }
     float hi, lo;
     split(v, hi, lo);
     z[c] = hi;
     zl[c] = lo;
   }
   acc = warp_sum(acc);
+  acc1 = warp_sum(acc1);
   __syncthreads();
-  if (lane_id() == 0) s_red[threadIdx.x >> 5] = acc;
+  if (lane_id() == 0) { s_red[threadIdx.x >> 5] = acc; s_red2[threadIdx.x >> 5] = acc1; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    double t = 0.0;
-    for (int w = 0; w < 8; ++w) t += s_red[w];
-    float sd = (float)sqrt(t / (double)d + (double)correction);
+    double t = 0.0, t1 = 0.0;
+    for (int w = 0; w < 8; ++w) { t += s_red[w]; t1 += s_red2[w]; }
+    const double dl = t1 / (double)d;
+    double var = t / (double)d - dl * dl;
+    if (var < 0.0) var = 0.0;
+    float sd = (float)sqrt(var + (double)correction);
     if (sd < correction * 10.f) { sd = 1.f; if (zero_rows) atomicAdd(zero_rows, 1); }
     stdv[row] = sd;
+    delta[row] = dl;
   }
 }
 
 // One thread per (i <= j).  Mirrors to (j, i).
 __global__ void __launch_bounds__(256)
 rdm_epilogue_kernel(const float* __restrict__ partial, int splits, int n_pad, int n, int64_t d,
-                    const float* __restrict__ stdv, float correction, float* __restrict__ rdm) {
+                    const float* __restrict__ stdv, const double* __restrict__ delta, float correction,
+                    float* __restrict__ rdm) {
   const int j = blockIdx.x * 256 + threadIdx.x;
   const int i = blockIdx.y;
   if (j >= n || j < i) return;
@@ -125,7 +156,7 @@ rdm_epilogue_kernel(const float* __restrict__ partial, int splits, int n_pad, in
   double g = 0.0;
   const int64_t plane = (int64_t)n_pad * n_pad;
   for (int s = 0; s < splits; ++s) g += (double)partial[s * plane + (int64_t)i * n_pad + j];
-  const float cov = (float)(g / (double)d);
+  const float cov = (float)(g / (double)d - delta[i] * delta[j]);     // rows were shifted, not exactly centred
   float corr = cov / (stdv[i] * stdv[j] + correction);
   corr = fminf(fmaxf(corr, -1.f), 1.f);
   const float v = 1.0f - corr;
@@ -140,7 +171,7 @@ using namespace vr;
 extern "C" size_t vr_rdm_workspace_bytes(int n, int64_t d) {
   if (n < 1 || d < 1) return 256;
   RdmPlan p = rdm_plan(n, d);
-  return 2 * arena_bytes((size_t)p.n_pad * p.d_pad, 4) + arena_bytes(p.n_pad, 4) +
+  return 2 * arena_bytes((size_t)p.n_pad * p.d_pad, 4) + arena_bytes(p.n_pad, 4) + arena_bytes(p.n_pad, 8) +
          arena_bytes((size_t)p.tc_splits * p.n_pad * p.n_pad, 4) + 256;
 }
 
@@ -159,12 +190,16 @@ extern "C" int vr_rdm_pearson_f32(const float* X, int n, int64_t d, int64_t ldx,
   float* Zhi = a.take<float>((size_t)p.n_pad * p.d_pad);
   float* Zlo = a.take<float>((size_t)p.n_pad * p.d_pad);
   float* stdv = a.take<float>(p.n_pad);
+  double* delta = a.take<double>(p.n_pad);
   const int splits = p.tc_splits;
   float* partial = a.take<float>((size_t)p.tc_splits * p.n_pad * p.n_pad);
   if (zero_var_rows) VR_CHECK_CUDA(cudaMemsetAsync(zero_var_rows, 0, sizeof(int), stream));
   {
     ProfScope prof(F_RDM_CENTER, stream);
-    row_center_kernel<<<p.n_pad, 256, 0, stream>>>(X, n, d, ldx, correction, Zhi, Zlo, p.d_pad, stdv, zero_var_rows);
+    if (d >= kSinglePassMinCols)
+      row_center_kernel<true><<<p.n_pad, 256, 0, stream>>>(X, n, d, ldx, correction, Zhi, Zlo, p.d_pad, stdv, delta, zero_var_rows);
+    else
+      row_center_kernel<false><<<p.n_pad, 256, 0, stream>>>(X, n, d, ldx, correction, Zhi, Zlo, p.d_pad, stdv, delta, zero_var_rows);
     VR_CHECK_LAUNCH();
   }
   {
@@ -184,7 +219,7 @@ extern "C" int vr_rdm_pearson_f32(const float* X, int n, int64_t d, int64_t ldx,
   }
   dim3 eg((n + 255) / 256, n);
   ProfScope prof(F_RDM_EPILOGUE, stream);
-  rdm_epilogue_kernel<<<eg, 256, 0, stream>>>(partial, splits, p.n_pad, n, d, stdv, correction, rdm);
+  rdm_epilogue_kernel<<<eg, 256, 0, stream>>>(partial, splits, p.n_pad, n, d, stdv, delta, correction, rdm);
   VR_CHECK_LAUNCH();
   return VR_OK;
 }
