@@ -108,8 +108,7 @@ row_center_kernel(const float* __restrict__ X, int n, int64_t d, int64_t ldx, fl
   };
   acc = 0.0;
   double acc1 = 0.0;
-  for (int64_t c = (int64_t)threadIdx.x * 4; c < d4; c += 1024) {
-    const float4 xv = __ldg(reinterpret_cast<const float4*>(x + c));
+  auto emit4 = [&](const float4 xv, int64_t c) {
     const float v0 = xv.x - shift, v1 = xv.y - shift, v2 = xv.z - shift, v3 = xv.w - shift;
     acc += (double)((v0 * v0 + v1 * v1) + (v2 * v2 + v3 * v3));
     acc1 += (double)((v0 + v1) + (v2 + v3));
@@ -117,7 +116,16 @@ row_center_kernel(const float* __restrict__ X, int n, int64_t d, int64_t ldx, fl
     split(v0, h.x, l.x); split(v1, h.y, l.y); split(v2, h.z, l.z); split(v3, h.w, l.w);
     *reinterpret_cast<float4*>(z + c) = h;
     *reinterpret_cast<float4*>(zl + c) = l;
+  };
+  int64_t c = (int64_t)threadIdx.x * 4;
+  for (; c + 3072 < d4; c += 4096) {                     // four independent 16-byte loads in flight per thread
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(x + c));
+    const float4 a1 = __ldg(reinterpret_cast<const float4*>(x + c + 1024));
+    const float4 a2 = __ldg(reinterpret_cast<const float4*>(x + c + 2048));
+    const float4 a3 = __ldg(reinterpret_cast<const float4*>(x + c + 3072));
+    emit4(a0, c); emit4(a1, c + 1024); emit4(a2, c + 2048); emit4(a3, c + 3072);
   }
+  for (; c < d4; c += 1024) emit4(__ldg(reinterpret_cast<const float4*>(x + c)), c);
   for (int64_t c = d4 + threadIdx.x; c < d_pad; c += 256) {
     float v = 0.f;
     if (c < d) { v = x[c] - shift; acc += (double)v * (double)v; acc1 += (double)v; }
