@@ -202,6 +202,21 @@ int vr_kendall_tau_a(const float* rdmA, const float* rdmB, int n, int64_t ld,
                      const uint32_t* masks, int R, double* out,
                      void* ws, size_t ws_bytes, vr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * Bootstrap of the encoding score: replaces the loop at
+ * visreps/analysis/encoding_score.py:228-240,
+ *     scores[i] = correlation_score(Y_test[boot_idx], pred_test[boot_idx]).mean()
+ * with himalaya's correlation_score = per-column Pearson r (population z-scores).  y_true / y_pred are
+ * (n, V) fp32 row-major on the device; mask r keeps the rows of draw r (mask of all ones = the point
+ * estimate, encoding_score.py:61).  mean_out is (R,) fp64: the mean over the V columns; per_column
+ * (nullable) receives the (R, V) fp32 column scores.  A column without variance among the kept rows makes
+ * its replicate NaN.
+ * ---------------------------------------------------------------------------------- */
+size_t vr_bootstrap_column_corr_workspace_bytes(int n, int V, int R);
+int vr_bootstrap_column_corr_f32(const float* y_true, const float* y_pred, int n, int V,
+                                 int64_t ld_true, int64_t ld_pred, const uint32_t* masks, int R,
+                                 double* mean_out, float* per_column, void* ws, size_t ws_bytes, vr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

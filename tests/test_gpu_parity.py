@@ -686,3 +686,32 @@ def test_rdm_wide_rows_single_pass_centring(dev):
     assert np.abs(got - truth).max() <= RDM_TOL
     assert np.abs(got - orc.rdm(t).double().numpy()).max() <= RDM_TOL
     assert np.array_equal(got, got.T) and not np.diag(got).any()
+
+
+def test_encoding_score_bootstrap_matches_oracle(dev):
+    """the bootstrap over cached predictions (encoding_score.py:228-240) on the device."""
+    from oracle import encoding_oracle as enc
+    from visreps_b200 import encoding as venc
+    rs = np.random.RandomState(8)
+    n, V, B = 220, 300, 40
+    y = rs.standard_normal((n, V)).astype(np.float32) * rs.uniform(0.5, 4.0, V).astype(np.float32) + rs.uniform(-3, 3, V).astype(np.float32)
+    p = (0.5 * y + rs.standard_normal((n, V)) * 2.0).astype(np.float32)
+    rng_o, rng_g = np.random.RandomState(42), np.random.RandomState(42)
+    rng_o.permutation(1000); rng_g.permutation(1000)           # the train split drawn first (encoding_score.py:131)
+    want = enc.bootstrap_encoding(y, p, n_bootstrap=B, rng=rng_o)
+    got = venc.bootstrap_encoding_score(torch.from_numpy(y), torch.from_numpy(p), n_bootstrap=B, rng=rng_g)
+    assert abs(got[0] - want[0]) <= SCORE_TOL
+    np.testing.assert_allclose(got[3], want[3], atol=SCORE_TOL, rtol=0)
+    assert abs(got[1] - want[1]) <= SCORE_TOL and abs(got[2] - want[2]) <= SCORE_TOL
+    assert rng_o.randint(1 << 30) == rng_g.randint(1 << 30)    # generators left in step
+    assert isinstance(got[3], list) and len(got[3]) == B
+    cols = venc.correlation_score(torch.from_numpy(y).to(dev), torch.from_numpy(p).to(dev)).cpu().numpy()
+    np.testing.assert_allclose(cols, enc.correlation_score(y, p), atol=SCORE_TOL, rtol=0)
+    # a column without variance among the kept rows makes the replicate NaN, like the division by a zero std
+    y2 = y.copy(); y2[:, 3] = 1.5
+    point, lo, hi, scores = venc.bootstrap_encoding_score(torch.from_numpy(y2), torch.from_numpy(p), n_bootstrap=3)
+    assert math.isnan(point) and all(math.isnan(s) for s in scores)
+    # strided inputs and many dropped rows (direct sum over the kept rows)
+    wide = torch.from_numpy(np.concatenate([y, p], axis=1)).to(dev)
+    a, b = wide[:, :V], wide[:, V:]
+    np.testing.assert_allclose(venc.correlation_score(a, b).cpu().numpy(), cols, atol=1e-7, rtol=0)

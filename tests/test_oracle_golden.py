@@ -114,3 +114,24 @@ def test_kendall_hand_counts():
     t, _ = orc.kendall_tau_a(np.array([1., 2., 3.]), np.array([3., 1., 2.]))
     assert t == pytest.approx(-1 / 3)
     assert np.isnan(orc.kendall_tau_a(np.array([1.]), np.array([1.]))[0])
+
+
+def test_encoding_oracle_correlation_score_is_columnwise_pearson():
+    """oracle/encoding_oracle.py restates himalaya's correlation_score (absent here): per column it must be
+    scipy's Pearson r, and the bootstrap must consume the generator like the reference loop."""
+    import scipy.stats
+    from oracle import encoding_oracle as enc
+    rs = np.random.RandomState(5)
+    y = rs.standard_normal((60, 9)).astype(np.float32)
+    p = (0.6 * y + rs.standard_normal((60, 9))).astype(np.float32)
+    got = enc.correlation_score(y, p)
+    want = [scipy.stats.pearsonr(y[:, v].astype(np.float64), p[:, v].astype(np.float64))[0] for v in range(9)]
+    np.testing.assert_allclose(got, want, atol=2e-6)
+    rng = np.random.RandomState(42)
+    rng.permutation(200)                                       # encoding_score.py:131 consumes the generator first
+    point, lo, hi, scores = enc.bootstrap_encoding(y, p, n_bootstrap=7, rng=rng)
+    ref = np.random.RandomState(42)
+    ref.permutation(200)
+    idx0 = ref.choice(60, size=54, replace=False)
+    assert scores[0] == float(enc.correlation_score(y[idx0], p[idx0]).mean())
+    assert lo <= np.median(scores) <= hi and abs(point - np.mean(want)) < 1e-5

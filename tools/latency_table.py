@@ -31,3 +31,7 @@ tm("evals.select_layer(8 layers, one ROI, n_select=1000)", lambda: vevals.select
 tr = vb.AlignmentData({k: v[:800] for k, v in acts.items()}, Y[0][:800], [str(i) for i in range(800)])
 te = vb.AlignmentData({k: v[800:] for k, v in acts.items()}, Y[0][800:], [str(i) for i in range(800, 1000)])
 tm("compute_rsa(800 train / 200 test, 8 layers, 1000 replicates)", lambda: vb.compute_rsa({"compare_method": "spearman"}, tr, te, n_bootstrap=1000), reps=3)
+from visreps_b200 import encoding as venc
+yt = Y[7]                                                   # (1000, 7600) "ventral" responses as targets
+yp = 0.5 * yt + torch.randn_like(yt)
+tm("encoding.bootstrap_encoding_score(1000 x 7600 predictions, 1000 replicates)", lambda: venc.bootstrap_encoding_score(yt, yp, n_bootstrap=1000), reps=3)

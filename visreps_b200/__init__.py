@@ -19,6 +19,7 @@ from .rsa import (  # noqa: F401
 from .alignment import AlignmentData, compute_traintest_alignment, _align_stimulus_level  # noqa: F401
 from .install import install, uninstall  # noqa: F401
 from . import evals  # noqa: F401
+from . import encoding  # noqa: F401
 
 __all__ = ["compute_rdm", "compute_rdm_correlation", "compute_rsa", "bootstrap_rdm_correlation",
            "bootstrap_rdm_correlation_grouped", "rsa_grouped", "AlignmentData", "compute_traintest_alignment", "install", "uninstall"]

@@ -53,6 +53,8 @@ SIGNATURES = {
     "vr_rank_fused": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _i64, _i64, _vp, _sz, _vp]),
     "vr_bootstrap_spearman_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "vr_bootstrap_spearman": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _vp, _vp, _sz, _vp]),
+    "vr_bootstrap_column_corr_workspace_bytes": (_sz, [_i, _i, _i]),
+    "vr_bootstrap_column_corr_f32": (_i, [_vp, _vp, _i, _i, _i64, _i64, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "vr_kendall_workspace_bytes": (_sz, [_i]),
     "vr_kendall_batch_workspace_bytes": (_sz, [_i, _i]),
     "vr_kendall_tau_a": (_i, [_vp, _vp, _i, _i64, _vp, _i, _vp, _vp, _sz, _vp]),

@@ -17,7 +17,7 @@ void set_error(const char* fmt, ...) {
 
 // ---- stage profiler ---------------------------------------------------------------------
 static const char* kFamilyNames[F_NUM_FAMILIES] = {"masks", "presort", "count", "rank", "rank_fused", "pearson", "kendall",
-                                            "rdm_center", "rdm_syrk", "rdm_epilogue", "row_rank"};
+                                            "rdm_center", "rdm_syrk", "rdm_epilogue", "row_rank", "column_corr"};
 struct ProfRec { int fam; cudaEvent_t a, b; };
 static std::mutex g_prof_mu;
 static bool g_prof_on = false;

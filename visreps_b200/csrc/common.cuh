@@ -19,7 +19,7 @@ void count_launch(unsigned n = 1);
 // start/stop event pair; stop() synchronises them and returns per-family device time and
 // kernel-launch counts.  bench.py uses it to time the dominant kernel inside the timed region.
 enum Family {
-  F_MASKS = 0, F_PRESORT, F_KEPT, F_RANK, F_RANK_FUSED, F_PEARSON, F_KENDALL, F_RDM_CENTER, F_RDM_SYRK, F_RDM_EPILOGUE, F_ROWRANK,
+  F_MASKS = 0, F_PRESORT, F_KEPT, F_RANK, F_RANK_FUSED, F_PEARSON, F_KENDALL, F_RDM_CENTER, F_RDM_SYRK, F_RDM_EPILOGUE, F_ROWRANK, F_COLCORR,
   F_NUM_FAMILIES
 };
 struct ProfScope {
