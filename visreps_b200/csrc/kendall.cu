@@ -395,7 +395,7 @@ extern "C" int vr_kendall_tau_a(const float* rdmA, const float* rdmB, int n, int
     const int rb = R - r0 < Rb ? R - r0 : Rb;
     VR_CHECK_CUDA(cudaMemsetAsync(acc, 0, (size_t)rb * 4 * sizeof(unsigned long long), stream));
     dim3 pg((words + 255) / 256 < 64 ? (words + 255) / 256 : 64, rb);
-    pair_mask_kernel<<<pg, 256, (size_t)W * 4, stream>>>(masks + (size_t)r0 * W, rb, n, W, words, pairbits);
+    pair_mask_kernel<<<pg, 256, (size_t)(W + 1) * 4, stream>>>(masks + (size_t)r0 * W, rb, n, W, words, pairbits);
     VR_CHECK_LAUNCH();
     kept_words_kernel<<<dim3(nchunks, rb, 2), 256, 0, stream>>>(ord, pairbits, words, (uint32_t)N, G, tables, chunk_tot, nchunks);
     VR_CHECK_LAUNCH();

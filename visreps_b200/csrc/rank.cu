@@ -497,7 +497,7 @@ static int build_rank_context(const uint32_t* masks, int n, int R, void* ctx, cu
   for (int r0 = 0; r0 < R; r0 += 65535) {   // grid.y limit
     const int rc = R - r0 < 65535 ? R - r0 : 65535;
     dim3 grid((words + 255) / 256 < 64 ? (words + 255) / 256 : 64, rc);
-    pair_mask_kernel<<<grid, 256, (size_t)W * 4, stream>>>(masks + (size_t)r0 * W, rc, n, W, words,
+    pair_mask_kernel<<<grid, 256, (size_t)(W + 1) * 4, stream>>>(masks + (size_t)r0 * W, rc, n, W, words,
                                                            c.pairbits + (size_t)r0 * words);
     VR_CHECK_LAUNCH();
   }
