@@ -30,7 +30,9 @@ inline RdmPlan rdm_plan(int n, int64_t d) {
   p.kb_total = (int)(p.d_pad / tc::kBK);
   const int64_t tiles128 = (int64_t)p.nb128 * (p.nb128 + 1) / 2;
   // ~6 CTAs per SM in total: diagonal tiles move half the bytes, so finer work units balance better (measured)
-  int64_t want_splits = (6 * kNumSMs + tiles128 - 1) / tiles128;
+  // (rounded DOWN: one CTA per SM is resident, so 36 tiles x 25 splits = 900 CTAs would run a seventh, almost
+  // empty wave on 148 SMs; 24 splits = 864 CTAs finish in six)
+  int64_t want_splits = (6 * kNumSMs) / tiles128;
   int64_t max_splits = (p.kb_total + 7) / 8;               // at least 8 K-blocks (256 columns) per CTA
   if (want_splits > max_splits) want_splits = max_splits;
   if (want_splits < 1) want_splits = 1;
