@@ -196,9 +196,10 @@ struct RankArgs {
   int64_t out_stride_m;
 };
 
-template <bool kSmemTable, bool kFused, typename Acc, bool kCompact, bool kUntied>
+template <bool kSmemTable, bool kFused, typename Acc, bool kCompact, bool kUntied, int kNMat>
 __global__ void __launch_bounds__(kFused ? kRankThreadsFused : kRankThreadsMat, 1)
 rank_kernel(const __grid_constant__ RankArgs A) {
+  static_assert(kNMat >= 1 && kNMat <= kFuseMax, "materialised vectors multiplied per pass");
   static_assert(kCompact || !kUntied, "the tie-free sweep reads compact run words");
   constexpr int kRankThreads = kFused ? kRankThreadsFused : kRankThreadsMat;
   constexpr int kRankWarps = kRankThreads / 32;
@@ -269,17 +270,17 @@ rank_kernel(const __grid_constant__ RankArgs A) {
     // materialised vectors as int4 streams; 32-bit offsets (host guarantees n_mat * R * dev_stride < 2^34)
     const int4* __restrict__ mat4 = reinterpret_cast<const int4*>(mat);
     const uint32_t mat_step4 = (uint32_t)(((int64_t)R * dev_stride) >> 2);
-    uint32_t moff[kFuseMax];                                 // vectors past n_mat alias the last one (results unused)
+    uint32_t moff[kNMat];                                    // vectors past n_mat alias the last one (results unused)
 #pragma unroll
-    for (int a = 0; a < kFuseMax; ++a) moff[a] = kFused ? (uint32_t)min(a, A.n_mat - 1) * mat_step4 + threadIdx.x : 0u;
+    for (int a = 0; a < kNMat; ++a) moff[a] = kFused ? (uint32_t)min(a, A.n_mat - 1) * mat_step4 + threadIdx.x : 0u;
     const uint32_t* __restrict__ runs = blob.runs;
     const uint32_t* __restrict__ keptw = A.pairbits + (int64_t)r * (dev_stride >> 5);
     // sum of squares in fp64: exact while a thread's share stays below 2^53 (it does whenever Acc is integral:
     // <= 1365 pairs of |d| <= 2.1e6), and its I2F + DFMA run on the XU / fp64 pipes the sweep leaves idle
     double acc_ss = 0.0;
-    Acc acc[kFuseMax];
+    Acc acc[kNMat];
 #pragma unroll
-    for (int a = 0; a < kFuseMax; ++a) acc[a] = 0;
+    for (int a = 0; a < kNMat; ++a) acc[a] = 0;
 
     // A vector without ties has run length 1 everywhere, so C(s) + C(e) = 2 C(s) + 1 for every kept pair:
     // one table entry, one shift, one popc -- and its sum of squares is the closed form N_r (N_r^2 - 1) / 3.
@@ -372,10 +373,10 @@ rank_kernel(const __grid_constant__ RankArgs A) {
         const uint4 q = q_cur;
         const uint32_t kw = kw_cur >> (p0 & 31u);              // 4 kept bits (p0 is a multiple of 4)
         const bool any_kept = p0 < N && (kw & 0xFu) != 0u;      // a dropped stimulus' row: all four pairs are out
-        int4 m4[kFuseMax];
+        int4 m4[kNMat];
         if (any_kept) {   // all materialised vectors are requested before the ranking work, which hides their latency
 #pragma unroll
-          for (int a = 0; a < kFuseMax; ++a) m4[a] = __ldg(mat4 + (moff[a] + ((p0 >> 2) - threadIdx.x)));
+          for (int a = 0; a < kNMat; ++a) m4[a] = __ldg(mat4 + (moff[a] + ((p0 >> 2) - threadIdx.x)));
         }
         {
           const uint32_t pn = p0 + kRankThreads * 4u;
@@ -384,7 +385,7 @@ rank_kernel(const __grid_constant__ RankArgs A) {
         if (any_kept) {
           rank4(q, kw, d4);
 #pragma unroll
-          for (int a = 0; a < kFuseMax; ++a) acc[a] = mac4(acc[a], d4, m4[a]);
+          for (int a = 0; a < kNMat; ++a) acc[a] = mac4(acc[a], d4, m4[a]);
         }
       }
     } else {
@@ -428,7 +429,7 @@ rank_kernel(const __grid_constant__ RankArgs A) {
       if (lane == 0) s_red[warp][kFuseMax] = v_ss;
       if (kFused) {
 #pragma unroll
-        for (int a = 0; a < kFuseMax; ++a) {
+        for (int a = 0; a < kNMat; ++a) {
           if (a < A.n_mat) {
             const Red t = wsum(acc[a]);
             if (lane == 0) s_red[warp][a] = t;
@@ -535,14 +536,22 @@ static int launch_count(const BlobList& blobs, int nV, int n, const RankContext&
   return VR_OK;
 }
 
-template <bool kSmem, bool kFused, typename Acc, bool kCompact, bool kUntied>
-static int launch_rank_kind(const RankArgs& args, int grid, size_t smem, cudaStream_t stream) {
+template <bool kSmem, bool kFused, typename Acc, bool kCompact, bool kUntied, int kNMat>
+static int launch_rank_inst(const RankArgs& args, int grid, size_t smem, cudaStream_t stream) {
   static unsigned long long attr_done = 0;
-  auto kernel = rank_kernel<kSmem, kFused, Acc, kCompact, kUntied>;
+  auto kernel = rank_kernel<kSmem, kFused, Acc, kCompact, kUntied, kNMat>;
   if (kSmem) VR_CHECK_CUDA(ensure_dynamic_smem(kernel, (int)(kRankSmemTableMax + 8192), &attr_done));
   kernel<<<grid, kFused ? kRankThreadsFused : kRankThreadsMat, smem, stream>>>(args);
   VR_CHECK_LAUNCH();
   return VR_OK;
+}
+// The fused sweep is instantiated for 1, 4 and 8 materialised vectors: a single-pair bootstrap or a job with one
+// neural RDM (THINGS behaviour) would otherwise load and multiply seven aliases of its only partner.
+template <bool kSmem, bool kFused, typename Acc, bool kCompact, bool kUntied>
+static int launch_rank_kind(const RankArgs& args, int grid, size_t smem, cudaStream_t stream) {
+  if (kFused && args.n_mat <= 1) return launch_rank_inst<kSmem, kFused, Acc, kCompact, kUntied, kFused ? 1 : kFuseMax>(args, grid, smem, stream);
+  if (kFused && args.n_mat <= 4) return launch_rank_inst<kSmem, kFused, Acc, kCompact, kUntied, kFused ? 4 : kFuseMax>(args, grid, smem, stream);
+  return launch_rank_inst<kSmem, kFused, Acc, kCompact, kUntied, kFuseMax>(args, grid, smem, stream);
 }
 // Whether a vector has ties is known only on the device (presort header), so both sweeps are launched and each
 // takes the vectors of its kind; the one with nothing to do returns after reading the headers.
