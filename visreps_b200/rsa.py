@@ -69,6 +69,16 @@ class PresortedRDM:
         if not _defer:
             PresortedRDM._sort_batch([self])
 
+    @classmethod
+    def from_blob(cls, blob: torch.Tensor, n: int, rdm: Optional[torch.Tensor] = None) -> "PresortedRDM":
+        """Adopt a blob presorted elsewhere (another rank): `vr_presort_bytes(n)` bytes on this device."""
+        lib = _lib.load()
+        if blob.dtype != torch.uint8 or blob.numel() != lib.vr_presort_bytes(n) or not blob.is_cuda or not blob.is_contiguous():
+            raise ValueError("blob must be a contiguous CUDA uint8 tensor of vr_presort_bytes(n) bytes")
+        self = cls.__new__(cls)
+        self.rdm, self.n, self.blob = rdm, int(n), blob
+        return self
+
     @staticmethod
     def _sort_batch(items: "Sequence[PresortedRDM]") -> None:
         lib = _lib.load()
