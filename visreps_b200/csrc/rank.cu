@@ -19,7 +19,8 @@
 //   and appends {kept word, count} to the replicate's table (8 B per 32 pairs).
 // rank_kernel (canonical order): one CTA per (vector, replicate).  The replicate's table is
 //   copied to shared memory (global when it does not fit); for every pair the precomputed run
-//   bounds (one packed word, coalesced) give C(s) and C(e) with two table reads + popc.
+//   word (coalesced) gives C(s) and C(e) from one table entry (a predicated second read when the run
+//   ends in the next 32-group) + two popc, without a data-dependent branch.
 //   Reads and the dev write are coalesced; the only random accesses hit the table.
 //   The side of the comparison with fewer vectors is materialised (dev vectors in HBM); the items of
 //   the other side multiply their dev values with those vectors on the fly (fused) and emit rho.

@@ -6,7 +6,9 @@
 //     slice of the tile and visits it in order, so ranking inside a digit is stable;
 //   - equal digits inside a 32-element row are resolved with __match_any_sync + popc;
 //   - per-(segment, digit, tile) counts are scanned digit-major, which yields each tile's
-//     global base per digit.
+//     global base per digit;
+//   - the scatter stages the tile in shared memory in digit order and writes it out from there, so
+//     every digit's run leaves as consecutive addresses.
 // HBM traffic per pass: 2 reads + 1 write of the 8-byte pairs (24 B/element).
 #pragma once
 #include "common.cuh"
@@ -86,7 +88,12 @@ tile_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __rest
                     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                     int64_t len, int64_t seg_stride, int shift,
                     const uint32_t* __restrict__ bases, int tiles) {
-  __shared__ uint32_t cnt[kSortWarps][kRadix];
+  __shared__ uint32_t cnt[kSortWarps][kRadix];     // per-warp digit counts -> tile-local start of (warp, digit)
+  __shared__ uint32_t dstart[kRadix];              // tile-local start of each digit
+  __shared__ uint32_t gbase[kRadix];               // global position of the tile's first element of each digit
+  __shared__ uint32_t skey[kSortTile];             // the tile, locally sorted by digit (stable)
+  __shared__ uint32_t sval[kSortTile];
+  __shared__ uint32_t wtot[kSortWarps];
   const int tile = blockIdx.x, seg = blockIdx.y;
   const int warp = threadIdx.x >> 5;
   const unsigned lane = lane_id();
@@ -96,7 +103,8 @@ tile_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __rest
   const int64_t seg_off = (int64_t)seg * seg_stride;
   const uint32_t* kin = keys_in + seg_off;
   const uint32_t* vin = vals_in + seg_off;
-  const int64_t base = (int64_t)tile * kSortTile + (int64_t)warp * (kSortItems * 32);
+  const int64_t tile_base = (int64_t)tile * kSortTile;
+  const int64_t base = tile_base + (int64_t)warp * (kSortItems * 32);
 
   uint32_t key[kSortItems], val[kSortItems], rank[kSortItems];
 #pragma unroll
@@ -123,27 +131,56 @@ tile_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __rest
     __syncwarp();
   }
   __syncthreads();
-  {  // per digit: turn per-warp counts into per-warp bases (global)
+  // per digit (one thread each): the tile's count, and the warps' counts turned into offsets inside the digit
+  uint32_t dcount;
+  {
     const int digit = threadIdx.x;
-    uint32_t run = bases[((size_t)seg * kRadix + digit) * tiles + tile];
+    uint32_t run = 0;
 #pragma unroll
     for (int w = 0; w < kSortWarps; ++w) {
       uint32_t t = cnt[w][digit];
       cnt[w][digit] = run;
       run += t;
     }
+    dcount = run;
+    gbase[digit] = bases[((size_t)seg * kRadix + digit) * tiles + tile];
+  }
+  // exclusive scan of the 256 digit counts -> dstart
+  {
+    uint32_t incl = dcount;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += t; }
+    if (lane == 31) wtot[warp] = incl;
+    __syncthreads();
+    uint32_t before = 0;
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) before += w < warp ? wtot[w] : 0u;
+    dstart[threadIdx.x] = before + incl - dcount;
   }
   __syncthreads();
-  uint32_t* kout = keys_out + seg_off;
-  uint32_t* vout = vals_out + seg_off;
+  // stage the tile in digit order, then write it out: consecutive threads write consecutive addresses inside every
+  // digit's run instead of 32 scattered 8-byte pieces per warp
 #pragma unroll
   for (int r = 0; r < kSortItems; ++r) {
     int64_t idx = base + r * 32 + lane;
     if (idx < len) {
-      uint32_t pos = cnt[warp][(key[r] >> shift) & 0xFFu] + rank[r];
-      kout[pos] = key[r];
-      vout[pos] = val[r];
+      const uint32_t d = (key[r] >> shift) & 0xFFu;
+      const uint32_t p = dstart[d] + cnt[warp][d] + rank[r];
+      skey[p] = key[r];
+      sval[p] = val[r];
     }
+  }
+  __syncthreads();
+  uint32_t* kout = keys_out + seg_off;
+  uint32_t* vout = vals_out + seg_off;
+  const int64_t remaining = len - tile_base;
+  const uint32_t valid = (uint32_t)(remaining < kSortTile ? remaining : kSortTile);
+  for (uint32_t p = threadIdx.x; p < valid; p += kSortThreads) {
+    const uint32_t k = skey[p];
+    const uint32_t d = (k >> shift) & 0xFFu;
+    const uint32_t pos = gbase[d] + (p - dstart[d]);
+    kout[pos] = k;
+    vout[pos] = sval[p];
   }
 }
 
