@@ -27,7 +27,10 @@ pa = t("presort(model)", lambda: vrsa.PresortedRDM(a))
 pb = t("presort(neural)", lambda: vrsa.PresortedRDM(b))
 idx = vrsa.draw_index_sets(n, B, 42)
 masks = vrsa.build_masks(idx, n, dev, with_full=True)
+from visreps_b200 import _lib
+_lib.profile_start()
 out = t(f"spearman: point + {B} replicates", lambda: vrsa.compare_grouped([pa], [pb], "spearman", masks))
+print("   stages:", {k: round(v["ms"], 2) for k, v in _lib.profile_stop().items() if v["ms"] > 0})
 self_ = t("spearman self-comparison", lambda: vrsa.compare_grouped([pa], [pa], "spearman", masks))
 print("scores (first 6)", out[0, 0, :6].cpu().numpy())
 assert np.allclose(self_.cpu().numpy(), 1.0, atol=1e-12)

@@ -36,6 +36,7 @@ constexpr int kRankThreadsFused = 768;  // fused: 85 registers per thread, all 8
                                         // (512 threads x two groups: 11.2 ms, 1024 threads x two load batches: 11.0 ms, this: 10.1 ms)
 constexpr int kCountThreads = 1024;  // 32 warp segments per (vector, 32-replicate batch): 8192 warps fill the machine at NSD shape
 constexpr int kCountWarps = kCountThreads / 32;
+constexpr int kCountCtasMax = 16;       // CTAs sharing one (vector, 32-replicate batch) when there are few of them
 constexpr int kMaxVectors = 64;
 constexpr size_t kRankSmemTableMax = 200 * 1024;   // bytes of shared memory the table may take
 
@@ -128,8 +129,10 @@ count_kernel(const __grid_constant__ BlobList blobs, int n, const uint32_t* __re
   const uint32_t N = (uint32_t)triu_len(n);
   const uint32_t G = (N + 31u) / 32u;
   const uint32_t SG = (G + 31u) / 32u;
-  const uint32_t sg_per_warp = (SG + kCountWarps - 1) / kCountWarps;
-  const uint32_t g_lo = min(G, warp * sg_per_warp * 32u);
+  const uint32_t n_seg = kCountWarps * gridDim.z;           // one segment per warp; gridDim.z CTAs share a (vector, batch)
+  const uint32_t seg = blockIdx.z * kCountWarps + warp;
+  const uint32_t sg_per_warp = (SG + n_seg - 1) / n_seg;
+  const uint32_t g_lo = min(G, seg * sg_per_warp * 32u);
   const uint32_t g_hi = min(G, g_lo + sg_per_warp * 32u);
   PresortView blob = presort_view(const_cast<void*>(blobs.p[v]), n);
   const uint32_t* __restrict__ stream = blob.stream;
@@ -157,7 +160,7 @@ count_kernel(const __grid_constant__ BlobList blobs, int n, const uint32_t* __re
     }
   }
   // counts are relative to the warp's segment; rank_kernel adds the segment bases from seg_tot
-  if (rep < R) seg_tot[((int64_t)v * R + rep) * kCountWarps + warp] = running;
+  if (rep < R) seg_tot[((int64_t)v * R + rep) * n_seg + seg] = running;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -195,7 +198,38 @@ struct RankArgs {
   double* out;               // out[f * out_stride_f + m * out_stride_m + r]
   int64_t out_stride_f;
   int64_t out_stride_m;
+  // global-table path (table too large for shared memory): an item is swept by `slices` CTAs at a time
+  int slices;                // canonical range cut into this many slices of slice_len pairs
+  uint32_t slice_len;
+  unsigned long long* partial;   // [n_vectors][R][slices][kFuseMax + 1] raw 64-bit partial sums (int64 or fp64)
+  uint32_t* ns;              // [n_vectors][R] kept pairs, written by table_finish_kernel
+  int n_seg;                 // count segments per (vector, replicate): kCountWarps x CTAs per batch
 };
+
+// Global-table path, step 1: add the segment bases to every table in place, write the sentinel entries and the
+// number of kept pairs.  grid (chunks of 1024 entries, vectors * R).
+__global__ void __launch_bounds__(256)
+table_finish_kernel(uint2* __restrict__ tables, int table_base, const uint32_t* __restrict__ seg_tot, int n_seg, int R, uint32_t G,
+                    uint32_t Gs, uint32_t seg_groups, uint32_t* __restrict__ ns, int64_t item0) {
+  __shared__ uint32_t s_base[kCountWarps * kCountCtasMax + 1];
+  const int64_t item = item0 + blockIdx.y;
+  const int v = (int)(item / R), r = (int)(item % R);
+  const int64_t tix = (int64_t)(table_base + v) * R + r;
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    for (int w = 0; w < n_seg; ++w) { s_base[w] = run; run += seg_tot[tix * n_seg + w]; }
+    s_base[n_seg] = run;
+    if (blockIdx.x == 0) ns[(int64_t)v * R + r] = run;
+  }
+  __syncthreads();
+  uint2* __restrict__ tab = tables + (int64_t)(table_base + v) * table_vector_stride(R, Gs) + (int64_t)r * Gs;
+  const uint32_t Ns = s_base[n_seg];
+  for (uint32_t g = blockIdx.x * 1024u + threadIdx.x; g < min(Gs, (blockIdx.x + 1u) * 1024u); g += 256u) {
+    uint2 e = make_uint2(0u, Ns);
+    if (g < G) { e = tab[g]; e.y += s_base[g / seg_groups]; }
+    tab[g] = e;
+  }
+}
 
 template <bool kSmemTable, bool kFused, typename Acc, bool kCompact, bool kUntied, int kNMat>
 __global__ void __launch_bounds__(kFused ? kRankThreadsFused : kRankThreadsMat, 1)
@@ -237,33 +271,43 @@ rank_kernel(const __grid_constant__ RankArgs A) {
   __syncthreads();
   const int n_vec = s_nvec;
 
+  // Shared-memory table: one CTA per item.  Global table: an item is cut into A.slices slices and consecutive CTAs
+  // take consecutive slices, so that the CTAs in flight share a few tables (L2 / L1 resident) instead of 148.
+  const int slices = kSmemTable ? 1 : A.slices;
   const int64_t items = (int64_t)n_vec * R;
-  for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+  const int64_t units = items * slices;
+  for (int64_t unit = blockIdx.x; unit < units; unit += gridDim.x) {
+    const int64_t item = unit / slices;
+    const int slice = (int)(unit % slices);
     // materialise: vector-major (CTAs share the vector's `runs` stream); fused: replicate-major
     const int v = s_vec[kFused ? (int)(item % n_vec) : (int)(item / R)];
     const int r = kFused ? (int)(item / n_vec) : (int)(item % R);
+    const uint32_t lo = kSmemTable ? 0u : (uint32_t)slice * A.slice_len;
+    const uint32_t hi = kSmemTable ? (uint32_t)dev_stride : (uint32_t)min((int64_t)dev_stride, (int64_t)lo + A.slice_len);
     PresortView blob = presort_view(const_cast<void*>(A.blobs.p[v]), n);
     const int64_t tix = (int64_t)(A.table_base + v) * R + r;
     uint2* __restrict__ vec_table = A.tables + (int64_t)(A.table_base + v) * table_vector_stride(R, Gs);
     uint2* __restrict__ g_table = vec_table + (int64_t)r * Gs;     // linear layout (table read in place)
-    if (threadIdx.x == 0) {                                  // exclusive prefix of the segment totals
-      uint32_t run = 0;
-      for (int w = 0; w < kCountWarps; ++w) { s_base[w] = run; run += A.seg_tot[tix * kCountWarps + w]; }
-      s_base[kCountWarps] = run;
-    }
-    __syncthreads();
-    const uint32_t Ns = s_base[kCountWarps];
-    // bring the table in (shared memory) or finish it in place (global), adding the segment bases;
-    // entries >= G become the sentinel {0, N_r} so that C(N) needs no special case
-    {
-      uint2* dst = kSmemTable ? s_table : g_table;
+    uint32_t Ns;
+    if constexpr (kSmemTable) {
+      if (threadIdx.x == 0) {                                // exclusive prefix of the segment totals
+        uint32_t run = 0;
+        for (int w = 0; w < kCountWarps; ++w) { s_base[w] = run; run += A.seg_tot[tix * kCountWarps + w]; }
+        s_base[kCountWarps] = run;
+      }
+      __syncthreads();
+      Ns = s_base[kCountWarps];
+      // bring the table into shared memory, adding the segment bases; entries >= G become the sentinel
+      // {0, N_r} so that C(N) needs no special case
       for (uint32_t g = threadIdx.x; g < Gs; g += kRankThreads) {
         uint2 e = make_uint2(0u, Ns);
-        if (g < G) { e = vec_table[table_entry_offset<kSmemTable>(r, g, Gs)]; e.y += s_base[g / seg_groups]; }
-        dst[g] = e;
+        if (g < G) { e = vec_table[table_entry_offset<true>(r, g, Gs)]; e.y += s_base[g / seg_groups]; }
+        s_table[g] = e;
       }
+      __syncthreads();
+    } else {
+      Ns = __ldg(A.ns + (int64_t)v * R + r);                 // the table was finished in place by table_finish_kernel
     }
-    __syncthreads();
     const uint2* __restrict__ table = kSmemTable ? s_table : g_table;
 
     int32_t* __restrict__ out_dev = kFused ? nullptr : A.dev + ((int64_t)v * R + r) * dev_stride;
@@ -365,11 +409,12 @@ rank_kernel(const __grid_constant__ RankArgs A) {
 
     // software pipeline: the run words and kept bits of the NEXT step are in flight while this one is ranked
     if constexpr (kFused) {
-      uint32_t p0 = threadIdx.x * 4u;
+      uint32_t p0 = lo + threadIdx.x * 4u;
+      const uint32_t n_hi = min(N, hi);
       uint4 q_cur = make_uint4(0u, 0u, 0u, 0u);
       uint32_t kw_cur = 0u;
-      if (p0 < N) { q_cur = __ldg(reinterpret_cast<const uint4*>(runs + p0)); kw_cur = __ldg(keptw + (p0 >> 5)); }
-      for (; p0 < (uint32_t)dev_stride; p0 += kRankThreads * 4u) {
+      if (p0 < n_hi) { q_cur = __ldg(reinterpret_cast<const uint4*>(runs + p0)); kw_cur = __ldg(keptw + (p0 >> 5)); }
+      for (; p0 < hi; p0 += kRankThreads * 4u) {
         int32_t d4[4] = {0, 0, 0, 0};
         const uint4 q = q_cur;
         const uint32_t kw = kw_cur >> (p0 & 31u);              // 4 kept bits (p0 is a multiple of 4)
@@ -381,7 +426,7 @@ rank_kernel(const __grid_constant__ RankArgs A) {
         }
         {
           const uint32_t pn = p0 + kRankThreads * 4u;
-          if (pn < N) { q_cur = __ldg(reinterpret_cast<const uint4*>(runs + pn)); kw_cur = __ldg(keptw + (pn >> 5)); }
+          if (pn < n_hi) { q_cur = __ldg(reinterpret_cast<const uint4*>(runs + pn)); kw_cur = __ldg(keptw + (pn >> 5)); }
         }
         if (any_kept) {
           rank4(q, kw, d4);
@@ -394,29 +439,30 @@ rank_kernel(const __grid_constant__ RankArgs A) {
       // table lookups per thread are in flight, and both groups usually lie in the same RDM row, so a
       // dropped stimulus' row still skips the work
       constexpr uint32_t kStep = kRankThreads * 8u;
-      uint32_t p0 = (threadIdx.x >> 5) * 256u + lane * 4u;
+      uint32_t p0 = lo + (threadIdx.x >> 5) * 256u + lane * 4u;
+      const uint32_t n_hi = min(N, hi);
       constexpr uint32_t kPadWord = kCompact ? 32u << kRunShloShift : 0u;     // what the presort stores beyond N
       uint4 qa_cur = make_uint4(kPadWord, kPadWord, kPadWord, kPadWord), qb_cur = qa_cur;
       uint32_t ka_cur = 0u, kb_cur = 0u;
-      if (p0 < N) { qa_cur = __ldg(reinterpret_cast<const uint4*>(runs + p0)); ka_cur = __ldg(keptw + (p0 >> 5)); }
-      if (p0 + 128u < N) { qb_cur = __ldg(reinterpret_cast<const uint4*>(runs + p0 + 128u)); kb_cur = __ldg(keptw + ((p0 + 128u) >> 5)); }
-      for (; p0 < (uint32_t)dev_stride; p0 += kStep) {
+      if (p0 < n_hi) { qa_cur = __ldg(reinterpret_cast<const uint4*>(runs + p0)); ka_cur = __ldg(keptw + (p0 >> 5)); }
+      if (p0 + 128u < n_hi) { qb_cur = __ldg(reinterpret_cast<const uint4*>(runs + p0 + 128u)); kb_cur = __ldg(keptw + ((p0 + 128u) >> 5)); }
+      for (; p0 < hi; p0 += kStep) {
         const uint32_t p1 = p0 + 128u;
         int32_t da[4] = {0, 0, 0, 0}, db[4] = {0, 0, 0, 0};
         const uint4 qa = qa_cur, qb = qb_cur;
-        const uint32_t ka = p0 < N ? (ka_cur >> (p0 & 31u)) & 0xFu : 0u;
-        const uint32_t kb = p1 < N ? (kb_cur >> (p1 & 31u)) & 0xFu : 0u;
+        const uint32_t ka = p0 < n_hi ? (ka_cur >> (p0 & 31u)) & 0xFu : 0u;
+        const uint32_t kb = p1 < n_hi ? (kb_cur >> (p1 & 31u)) & 0xFu : 0u;
         {
           const uint32_t pn = p0 + kStep;
-          if (pn < N) { qa_cur = __ldg(reinterpret_cast<const uint4*>(runs + pn)); ka_cur = __ldg(keptw + (pn >> 5)); }
-          if (pn + 128u < N) { qb_cur = __ldg(reinterpret_cast<const uint4*>(runs + pn + 128u)); kb_cur = __ldg(keptw + ((pn + 128u) >> 5)); }
+          if (pn < n_hi) { qa_cur = __ldg(reinterpret_cast<const uint4*>(runs + pn)); ka_cur = __ldg(keptw + (pn >> 5)); }
+          if (pn + 128u < n_hi) { qb_cur = __ldg(reinterpret_cast<const uint4*>(runs + pn + 128u)); kb_cur = __ldg(keptw + ((pn + 128u) >> 5)); }
         }
         if ((ka | kb) != 0u) {         // run words beyond N are padding words: valid to rank, never kept
           rank4(qa, ka, da);
           rank4(qb, kb, db);
         }
         *reinterpret_cast<int4*>(out_dev + p0) = make_int4(da[0], da[1], da[2], da[3]);
-        if (p1 < (uint32_t)dev_stride) *reinterpret_cast<int4*>(out_dev + p1) = make_int4(db[0], db[1], db[2], db[3]);
+        if (p1 < hi) *reinterpret_cast<int4*>(out_dev + p1) = make_int4(db[0], db[1], db[2], db[3]);
       }
     }
 
@@ -439,7 +485,18 @@ rank_kernel(const __grid_constant__ RankArgs A) {
       }
     }
     __syncthreads();
-    if (threadIdx.x <= kFuseMax) {
+    if (!kSmemTable) {               // a slice only contributes partial sums; rank_finalize_kernel adds them up in order
+      if (threadIdx.x <= kFuseMax) {
+        const int slot = threadIdx.x;
+        Red tot_r = 0;
+        if (slot == kFuseMax || (kFused && slot < A.n_mat))
+          for (int w = 0; w < kRankWarps; ++w) tot_r += s_red[w][slot];
+        unsigned long long raw;
+        if constexpr (std::is_integral<Acc>::value) raw = (unsigned long long)tot_r;
+        else raw = (unsigned long long)__double_as_longlong((double)tot_r);
+        A.partial[((((int64_t)v * R + r) * slices) + slice) * (kFuseMax + 1) + slot] = raw;
+      }
+    } else if (threadIdx.x <= kFuseMax) {
       const int slot = threadIdx.x;
       Red tot_r = 0, ss_r = 0;       // every participating lane needs ss of this item as well
       if (slot == kFuseMax || (kFused && slot < A.n_mat))
@@ -464,6 +521,45 @@ rank_kernel(const __grid_constant__ RankArgs A) {
       }
     }
     __syncthreads();  // table, s_mask and s_red are reused by the next item
+  }
+}
+
+// Global-table path, last step: one warp per item adds the slices' partial sums in slice order and writes what the
+// single-CTA path writes at the end of an item.  grid = items of the launch (all vectors, tie-free or not).
+template <bool kFused, bool kIntegral>
+__global__ void __launch_bounds__(32)
+rank_finalize_kernel(const __grid_constant__ RankArgs A) {
+  const int v = blockIdx.x / A.R, r = blockIdx.x % A.R;
+  const int slot = threadIdx.x;
+  const uint32_t N = (uint32_t)triu_len(A.n);
+  const PresortHeader* hdr = static_cast<const PresortHeader*>(A.blobs.p[v]);
+  double mine = 0.0;
+  if (slot <= kFuseMax) {
+    const unsigned long long* p = A.partial + (((int64_t)v * A.R + r) * A.slices) * (kFuseMax + 1) + slot;
+    if (kIntegral) {
+      long long t = 0;
+      for (int s = 0; s < A.slices; ++s) t += (long long)p[(int64_t)s * (kFuseMax + 1)];
+      mine = (double)t;
+    } else {
+      for (int s = 0; s < A.slices; ++s) mine += __longlong_as_double((long long)p[(int64_t)s * (kFuseMax + 1)]);
+    }
+  }
+  double ss_item = __shfl_sync(0xffffffffu, mine, kFuseMax);
+  const uint32_t Ns = A.ns[(int64_t)v * A.R + r];
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  if (run_compact(N) && hdr->n_runs == N)      // tie-free vector: the sweep did not accumulate squares (closed form)
+    ss_item = (double)(((unsigned long long)Ns - 1ull) * Ns * ((unsigned long long)Ns + 1ull) / 3ull);
+  if (hdr->has_nan) ss_item = nan;
+  if (!kFused) {
+    if (slot == kFuseMax) {
+      A.ss[(int64_t)v * A.R + r] = ss_item;
+      if (A.nkept) A.nkept[(int64_t)v * A.R + r] = (int64_t)Ns;
+    }
+  } else if (slot < A.n_mat) {
+    const double ss_m = A.mat_ss[(int64_t)slot * A.R + r];
+    double rho = mine / (sqrt(ss_m) * sqrt(ss_item));
+    if (!(ss_m > 0.0) || !(ss_item > 0.0)) rho = nan;
+    A.out[(int64_t)v * A.out_stride_f + (int64_t)slot * A.out_stride_m + r] = rho;
   }
 }
 
@@ -511,15 +607,49 @@ static int build_rank_context(const uint32_t* masks, int n, int R, void* ctx, cu
 }
 
 // count tables + segment totals of nV vectors x R replicates
+// Global-table path: slices of the canonical range swept by different CTAs.  A slice is a multiple of both sweeps'
+// step (768 * 4 and 1024 * 8 pairs) and long enough (>= ~100k pairs) that the per-slice reduction stays cheap; at most
+// one slice per SM, so that a table of the stress shape (12.5 MB) is shared by the whole machine.
+struct SlicePlan { int slices; uint32_t slice_len; };
+static inline SlicePlan rank_slice_plan(int n) {
+  const int64_t stride = vr_dev_stride(n);
+  if (rank_table_in_smem(n)) return {1, (uint32_t)stride};
+  const int64_t unit = 24576;                                // lcm(768 * 4, 1024 * 8)
+  int64_t target = stride / (unit * 4);
+  if (target < 1) target = 1;
+  if (target > kNumSMs) target = kNumSMs;
+  const int64_t len = round_up((stride + target - 1) / target, unit);
+  return {(int)((stride + len - 1) / len), (uint32_t)len};
+}
+// Large tables with few (vector, batch) pairs -- the stress shape with a handful of masks -- would leave the count
+// to one or two CTAs; the group range is then cut over up to kCountCtasMax CTAs (more segments per table).
+static inline int count_ctas(int n, int nV, int64_t R) {
+  if (rank_table_in_smem(n)) return 1;
+  const int64_t ctas = (int64_t)nV * ((R + 31) / 32);
+  int64_t z = kNumSMs / (ctas > 0 ? ctas : 1);
+  if (z < 1) z = 1;
+  if (z > kCountCtasMax) z = kCountCtasMax;
+  return (int)z;
+}
 static inline size_t tables_bytes(int n, int nV, int64_t R) {
-  return arena_bytes((size_t)nV * table_vector_stride(R, table_groups(n)), 8) + arena_bytes((size_t)nV * R * kCountWarps, 4);
+  size_t b = arena_bytes((size_t)nV * table_vector_stride(R, table_groups(n)), 8) +
+             arena_bytes((size_t)nV * R * kCountWarps * kCountCtasMax, 4);
+  if (!rank_table_in_smem(n))
+    b += arena_bytes((size_t)nV * R * rank_slice_plan(n).slices * (kFuseMax + 1), 8) + arena_bytes((size_t)nV * R, 4);
+  return b;
 }
 static int launch_count(const BlobList& blobs, int nV, int n, const RankContext& ctx, int R, void* ws, size_t ws_bytes,
-                        uint2** tables, uint32_t** seg_tot, cudaStream_t stream) {
+                        uint2** tables, uint32_t** seg_tot, unsigned long long** partial, uint32_t** ns, cudaStream_t stream) {
   const uint32_t Gs = table_groups(n);
   Arena a(ws, ws_bytes);
   *tables = a.take<uint2>((size_t)nV * table_vector_stride(R, Gs));
-  *seg_tot = a.take<uint32_t>((size_t)nV * R * kCountWarps);
+  *seg_tot = a.take<uint32_t>((size_t)nV * R * kCountWarps * kCountCtasMax);
+  *partial = nullptr;
+  *ns = nullptr;
+  if (!rank_table_in_smem(n)) {
+    *partial = a.take<unsigned long long>((size_t)nV * R * rank_slice_plan(n).slices * (kFuseMax + 1));
+    *ns = a.take<uint32_t>((size_t)nV * R);
+  }
   if (!a.ok) { set_error("rank workspace too small for the count tables"); return VR_ERR_WORKSPACE; }
   static unsigned long long attr_done = 0;
   const size_t smem = (size_t)n * 4;
@@ -530,7 +660,7 @@ static int launch_count(const BlobList& blobs, int nV, int n, const RankContext&
     else VR_CHECK_CUDA(ensure_dynamic_smem(count_kernel<false>, 160 * 1024, &attr_done));
   }
   ProfScope prof(F_KEPT, stream);
-  dim3 grid((R + 31) / 32, nV);
+  dim3 grid((R + 31) / 32, nV, count_ctas(n, nV, R));
   if (interleaved) count_kernel<true><<<grid, kCountThreads, smem, stream>>>(blobs, n, ctx.maskT, R, *tables, Gs, *seg_tot);
   else count_kernel<false><<<grid, kCountThreads, smem, stream>>>(blobs, n, ctx.maskT, R, *tables, Gs, *seg_tot);
   VR_CHECK_LAUNCH();
@@ -572,16 +702,33 @@ static int launch_rank_side(const RankArgs& args, cudaStream_t stream) {
   const bool in_smem = rank_table_in_smem(n);
   const size_t smem = rank_smem_bytes(n, in_smem);
   const int64_t items = (int64_t)args.n_vectors * args.R;
-  const int grid = (int)(items < kNumSMs ? items : kNumSMs);
+  const int64_t units = items * args.slices;
+  const int grid = (int)(units < kNumSMs ? units : kNumSMs);
+  if (!in_smem) {                                            // global tables: finish them in place first
+    const uint32_t G = presort_groups(n);
+    const uint32_t seg_groups = ((((G + 31u) / 32u) + args.n_seg - 1) / args.n_seg) * 32u;
+    for (int64_t i0 = 0; i0 < items; i0 += 65535) {
+      const int cnt = (int)(items - i0 < 65535 ? items - i0 : 65535);
+      dim3 fg((args.Gs + 1023u) / 1024u, cnt);
+      table_finish_kernel<<<fg, 256, 0, stream>>>(args.tables, args.table_base, args.seg_tot, args.n_seg, args.R, G, args.Gs, seg_groups, args.ns, i0);
+      VR_CHECK_LAUNCH();
+    }
+  }
   // Integer accumulation is exact to the end while N^3 < 2^60.  Beyond that the sums are folded into fp64 every
   // four pairs; int64 would still fit up to N ~ 3e6, but measured at n = 1854 the fp64 variant is 7 % faster
   // (its conversions and adds run on the otherwise idle fp64 / XU pipes instead of the ALU pipe).
   const bool exact = N <= (1ll << 20);
   const bool compact = run_compact((uint32_t)N);
   if (in_smem) return launch_rank_variant<true, kFused, long long, true>(args, grid, smem, stream);   // N <= ~816k
-  if (exact) return launch_rank_variant<false, kFused, long long, true>(args, grid, smem, stream);
-  if (compact) return launch_rank_variant<false, kFused, double, true>(args, grid, smem, stream);
-  return launch_rank_variant<false, kFused, double, false>(args, grid, smem, stream);
+  int st;
+  if (exact) st = launch_rank_variant<false, kFused, long long, true>(args, grid, smem, stream);
+  else if (compact) st = launch_rank_variant<false, kFused, double, true>(args, grid, smem, stream);
+  else st = launch_rank_variant<false, kFused, double, false>(args, grid, smem, stream);
+  if (st != VR_OK) return st;
+  if (exact) rank_finalize_kernel<kFused, true><<<(unsigned)items, 32, 0, stream>>>(args);
+  else rank_finalize_kernel<kFused, false><<<(unsigned)items, 32, 0, stream>>>(args);
+  VR_CHECK_LAUNCH();
+  return VR_OK;
 }
 
 static int launch_rank(const RankArgs& args, bool fused, cudaStream_t stream) {
@@ -600,8 +747,11 @@ static int rank_stage(const void* const* blobs_host, int nV, int n, const RankCo
   }
   uint2* tables = nullptr;
   uint32_t* seg_tot = nullptr;
-  int st = launch_count(args.blobs, nV, n, ctx, R, ws, ws_bytes, &tables, &seg_tot, stream);
+  int st = launch_count(args.blobs, nV, n, ctx, R, ws, ws_bytes, &tables, &seg_tot, &args.partial, &args.ns, stream);
   if (st != VR_OK) return st;
+  const SlicePlan sp = rank_slice_plan(n);
+  args.slices = sp.slices; args.slice_len = sp.slice_len;
+  args.n_seg = kCountWarps * count_ctas(n, nV, R);
   args.n_vectors = nV; args.n = n; args.pairbits = ctx.pairbits; args.R = R; args.tables = tables; args.table_base = 0;
   args.Gs = table_groups(n); args.seg_tot = seg_tot; args.dev_stride = vr_dev_stride(n);
   args.dev = dev; args.ss = ss; args.nkept = nkept;
@@ -728,7 +878,8 @@ SpearmanPlan spearman_plan(int n, int nA, int nB) {
   SpearmanPlan p;
   p.fixed = 16 * 256 + (size_t)n * 4 * 2 + 4096 + (size_t)32 * stage * table_groups(n) * 8;   // tables pad replicates to 32
   p.per_rep = (size_t)vr_dev_stride(n) / 8 + (size_t)n / 8 + 8 +                      // context
-              (size_t)stage * ((size_t)table_groups(n) * 8 + 4 * kCountWarps) +      // count tables
+              (size_t)stage * ((size_t)table_groups(n) * 8 + 4 * kCountWarps * kCountCtasMax +
+                               (rank_table_in_smem(n) ? 0 : (size_t)rank_slice_plan(n).slices * (kFuseMax + 1) * 8 + 4)) +   // count tables (+ slice partials)
               (size_t)group * ((size_t)vr_dev_stride(n) * 4 + 8);                    // dev + ss
   return p;
 }
