@@ -9,11 +9,13 @@
 // The SYRK is the tcgen05 / TMEM / TMA kernel of syrk_tc.cuh (3xTF32, fp32-accurate).
 #include "common.cuh"
 #include "syrk_tc.cuh"
+#include "syrk_tc2.cuh"
 
 namespace vr {
 
 struct RdmPlan {
-  int n_pad;        // multiple of 128 (tensor tile rows)
+  bool pair;        // 256 x 256 pair tiles on CTA pairs (syrk_tc2.cuh) instead of 128 x 128 tiles on single CTAs
+  int n_pad;        // multiple of 128 (tensor tile rows), of 256 with pair tiles
   int64_t d_pad;    // multiple of 32 (one TMA box row)
   int nb128;        // 128-row blocks
   int kb_total;     // 32-column K blocks
@@ -23,12 +25,17 @@ struct RdmPlan {
 
 inline RdmPlan rdm_plan(int n, int64_t d) {
   RdmPlan p;
-  p.n_pad = (int)round_up(n, 128);
+  static const int pair_mode = [] { const char* e = getenv("VR_SYRK_PAIR"); return e ? atoi(e) : 1; }();
+  // pair tiles from four 128-row blocks on, and for K ranges long enough to fill whole waves of CTA pairs with
+  // at least ~100 K-blocks each (short rows are launch- and wave-bound: the single-CTA kernel has more, smaller units)
+  p.pair = pair_mode != 0 && n > 384 && d >= 16384;
+  p.n_pad = (int)round_up(n, p.pair ? 256 : 128);
   p.d_pad = round_up(d, 32);
   // K splits only to fill and balance the machine; each CTA chains its whole K range in-kernel
   p.nb128 = p.n_pad / tc::kBM;
   p.kb_total = (int)(p.d_pad / tc::kBK);
-  const int64_t tiles128 = (int64_t)p.nb128 * (p.nb128 + 1) / 2;
+  const int nb2 = p.n_pad / tc2::kPM;
+  const int64_t tiles128 = p.pair ? (int64_t)nb2 * (nb2 + 1) : (int64_t)p.nb128 * (p.nb128 + 1) / 2;   // CTAs per K split
   // ~6 CTAs per SM in total: diagonal tiles move half the bytes, so finer work units balance better (measured)
   // (rounded DOWN: one CTA per SM is resident, so 36 tiles x 25 splits = 900 CTAs would run a seventh, almost
   // empty wave on 148 SMs; 24 splits = 864 CTAs finish in six)
@@ -218,13 +225,22 @@ extern "C" int vr_rdm_pearson_f32(const float* X, int n, int64_t d, int64_t ldx,
     if (rc != VR_OK) return rc;
     rc = tc::make_plane_map(&map_lo, Zlo, p.n_pad, p.d_pad);
     if (rc != VR_OK) return rc;
-    static unsigned long long attr_done = 0;
-    VR_CHECK_CUDA(ensure_dynamic_smem(tc::syrk_tc_kernel, (int)tc::kSmemBytes, &attr_done));
     ProfScope prof(F_RDM_SYRK, stream);
-    const int super = tc::kSuper;
-    dim3 grid(tc::grid_slots(p.nb128, super), p.tc_splits);
-    tc::syrk_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, stream>>>(map_hi, map_lo, p.nb128, p.kb_total, p.kb_per_split,
-                                                                     partial, p.n_pad, super);
+    if (p.pair) {
+      static unsigned long long attr_done2 = 0;
+      VR_CHECK_CUDA(ensure_dynamic_smem(tc2::syrk_tc2_kernel, (int)tc2::kSmemBytes2, &attr_done2));
+      const int nb2 = p.n_pad / tc2::kPM;
+      dim3 grid(nb2 * (nb2 + 1), p.tc_splits);             // 2 CTAs per upper-triangular pair tile
+      tc2::syrk_tc2_kernel<<<grid, tc2::kThreads2, tc2::kSmemBytes2, stream>>>(map_hi, map_lo, nb2, p.kb_total, p.kb_per_split,
+                                                                             partial, p.n_pad);
+    } else {
+      static unsigned long long attr_done = 0;
+      VR_CHECK_CUDA(ensure_dynamic_smem(tc::syrk_tc_kernel, (int)tc::kSmemBytes, &attr_done));
+      const int super = tc::kSuper;
+      dim3 grid(tc::grid_slots(p.nb128, super), p.tc_splits);
+      tc::syrk_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, stream>>>(map_hi, map_lo, p.nb128, p.kb_total, p.kb_per_split,
+                                                                       partial, p.n_pad, super);
+    }
     VR_CHECK_LAUNCH();
   }
   dim3 eg((n + 255) / 256, n);
