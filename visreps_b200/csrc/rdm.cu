@@ -36,10 +36,11 @@ inline RdmPlan rdm_plan(int n, int64_t d) {
   p.kb_total = (int)(p.d_pad / tc::kBK);
   const int nb2 = p.n_pad / tc2::kPM;
   const int64_t tiles128 = p.pair ? (int64_t)nb2 * (nb2 + 1) : (int64_t)p.nb128 * (p.nb128 + 1) / 2;   // CTAs per K split
-  // ~6 CTAs per SM in total: diagonal tiles move half the bytes, so finer work units balance better (measured)
-  // (rounded DOWN: one CTA per SM is resident, so 36 tiles x 25 splits = 900 CTAs would run a seventh, almost
-  // empty wave on 148 SMs; 24 splits = 864 CTAs finish in six)
-  int64_t want_splits = (6 * kNumSMs) / tiles128;
+  // One wave: tiles x splits <= number of SMs (one CTA is resident per SM).  Longer K chains per CTA mean fewer
+  // pipeline fills, fewer partial planes for the epilogue to add, and no partially filled last wave; measured at the
+  // NSD shape with the pair-tile kernel: 1 wave 2.40 + 0.19 ms (SYRK + epilogue), 3 waves 2.46 + 0.24, 6 waves 2.67 + 0.29.
+  static const int waves = [] { const char* e = getenv("VR_SYRK_WAVES"); return e ? atoi(e) : 1; }();
+  int64_t want_splits = ((int64_t)waves * kNumSMs) / tiles128;
   int64_t max_splits = (p.kb_total + 7) / 8;               // at least 8 K-blocks (256 columns) per CTA
   if (want_splits > max_splits) want_splits = max_splits;
   if (want_splits < 1) want_splits = 1;
