@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define VR_ABI_VERSION 1
+#define VR_ABI_VERSION 2
 #define VR_MAX_STIMULI 32767
 
 enum {

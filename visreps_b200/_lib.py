@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libvisreps_b200.so")
 
 VR_OK, VR_ERR_INVALID, VR_ERR_WORKSPACE, VR_ERR_CUDA, VR_ERR_UNSUPPORTED = range(5)
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # name -> (restype, argtypes); mirrors include/visreps_b200.h one to one
 _vp, _i, _i64, _sz, _f = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_float
