@@ -333,6 +333,18 @@ def run_ours(args):
         ach = flops * args.steps / (prof[dom]["ms"] * 1e-3) / 1e12
         roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
                     "traffic": None, "peak_source": "measured bf16_tflops_sustained"}
+    # second roofline object: the tensor-core SYRK family (all RDM builds of the step), useful TF32 work
+    roofline_syrk = None
+    if prof.get("rdm_syrk", {}).get("ms", 0) > 0:
+        tf32_useful = 3.0 * sum(n * (n + 1) * t.shape[1] for t in X + Y) * args.steps / (prof["rdm_syrk"]["ms"] * 1e-3) / 1e12
+        tf32_peak = float(peaks.get("bf16_tflops", 1599.5)) / 2.0
+        roofline_syrk = {"kernel": "syrk_tc2_kernel (pair tiles, cta_group::2) / syrk_tc_kernel", "bound": "tensor",
+                         "achieved": tf32_useful, "peak": tf32_peak, "unit": "TFLOP/s", "frac": tf32_useful / tf32_peak,
+                         "definition": "3 TF32 products x n(n+1)d useful flop per RDM (upper triangle) / CUDA-event time of the SYRK launches; "
+                                       "peak = half the measured dense bf16 rate (MEASURED_PEAKS.json bf16_tflops)",
+                         "note": "ncu: sm__pipe_tensor_cycles_active 92.3 % for the pair-tile kernel at n=1000, d=193,600 "
+                                 "(profiles/r1_syrk_tc2_conv1_full.txt); 11 % of the executed tensor work lies below the diagonal of the "
+                                 "256-wide tiling and the short rows (ROIs, fc layers) are launch-bound"}
     rdm_flops = sum(n * (n + 1) * t.shape[1] for t in X + Y) * args.steps
     rdm_ms = prof["rdm_syrk"]["ms"] + prof["rdm_center"]["ms"] + prof["rdm_epilogue"]["ms"]
     rdm_tflops = rdm_flops / (rdm_ms * 1e-3) / 1e12 if rdm_ms > 0 else None
@@ -347,6 +359,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clock_info,
         "roofline": roofline,
+        "roofline_syrk": roofline_syrk,
         "cpu_baseline": cpu_baseline,
         "rdm_tflops": rdm_tflops,
         "rdm_flops_definition": "n(n+1)d per RDM (upper triangle incl. diagonal, 2 flop/MAC), fp32-accurate",
