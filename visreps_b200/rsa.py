@@ -636,7 +636,12 @@ def _spearman_pipeline(inputs_a: Sequence[torch.Tensor], inputs_b: Sequence[torc
     mat_is_a = nA < nB                                   # ties: the neural side is materialised
     mats = list(inputs_a if mat_is_a else inputs_b)
     fus = list(inputs_b if mat_is_a else inputs_a)
+    # Copy order: smallest first (the GPU gets work at once), but the third-largest matrix LAST: what is exposed after
+    # the final copy is that matrix's RDM build plus its ranking, and the ranking costs the same for every matrix, so
+    # the last one should be cheap to build -- yet large enough that the two biggest builds are over by then.
     order = sorted(range(len(fus)), key=lambda k: fus[k].numel())     # smallest copy first
+    if len(order) >= 4 and any(f.device != dev for f in fus):
+        order.append(order.pop(-3))
     # size the scratch for the largest matrix now, so no allocation (and no implicit sync) happens mid-pipeline
     _lib.workspace(max(lib.vr_rdm_workspace_bytes(n, int(np.prod(x.shape[1:]))) for x in mats + fus), dev)
     compute = torch.cuda.current_stream()
