@@ -127,3 +127,30 @@ def test_percentile_ci_is_numpy_percentile(b):
     assert np.array_equal(want[0], lo, equal_nan=True) and np.array_equal(want[1], hi, equal_nan=True)
     lo1, hi1 = percentile_ci(x[2, 3])
     assert float(lo1) == np.percentile(x[2, 3], 2.5) and float(hi1) == np.percentile(x[2, 3], 97.5)
+
+
+def test_install_rebinds_a_visreps_like_module_tree(monkeypatch):
+    """install() patches the names the reference binds (evals.py:25, alignment.py:8) on whichever modules exist,
+    leaves experiment scripts alone unless they are already imported, and uninstall() restores everything."""
+    import sys, types
+    import visreps_b200 as vb
+    from visreps_b200 import evals as vevals, rsa as vrsa
+    sentinel = object()
+    mods = {}
+    for name, syms in {"visreps": (), "visreps.analysis": (), "visreps.analysis.rsa": ("compute_rdm", "compute_rdm_correlation", "compute_rsa", "_rank"),
+                       "visreps.evals": ("compute_rdm", "compute_rdm_correlation", "unrelated"),
+                       "visreps.analysis.alignment": ("compute_rsa",),
+                       "experiments": (), "experiments.binary_pc_rsa": (), "experiments.binary_pc_rsa.main": ("compute_rdm", "_compare_rdms")}.items():
+        m = types.ModuleType(name)
+        for s in syms:
+            setattr(m, s, sentinel)
+        mods[name] = m
+        monkeypatch.setitem(sys.modules, name, m)
+    done = vb.install()
+    assert ("visreps.evals", "compute_rdm") in done and ("visreps.analysis.alignment", "compute_rsa") in done
+    assert mods["visreps.evals"].compute_rdm is vrsa.compute_rdm and mods["visreps.evals"].unrelated is sentinel
+    assert mods["visreps.analysis.rsa"]._rank is vrsa._rank
+    assert mods["experiments.binary_pc_rsa.main"]._compare_rdms is vevals._compare_rdms
+    assert not any(m == "experiments.reconstruction_analysis.run_reconstruction" for m, _ in done)   # not imported: not touched
+    vb.uninstall()
+    assert mods["visreps.evals"].compute_rdm is sentinel and mods["experiments.binary_pc_rsa.main"]._compare_rdms is sentinel

@@ -15,17 +15,27 @@ _TARGETS = {
     "visreps.analysis.rsa": ("compute_rdm", "compute_rdm_correlation", "compute_rsa", "_rank", "_concept_average_exact"),
     "visreps.evals": ("compute_rdm", "compute_rdm_correlation"),
     "visreps.analysis.alignment": ("compute_rsa",),
+    # secondary callers: scripts, patched only if they are already imported
+    "experiments.reconstruction_analysis.run_reconstruction": ("compute_rdm", "compute_rdm_correlation", "bootstrap_rdm_correlation"),
+    "experiments.binary_pc_rsa.main": ("compute_rdm", "_compare_rdms"),
 }
+_SCRIPTS = ("experiments.reconstruction_analysis.run_reconstruction", "experiments.binary_pc_rsa.main")
 _saved = {}
+
+
+def _ours(sym: str):
+    from . import rsa, evals
+    return getattr(evals, sym) if sym == "_compare_rdms" else getattr(rsa, sym)
 
 
 def install(strict: bool = False):
     """Patch the reference modules in place; returns the list of (module, symbol) rebound."""
-    from . import rsa as ours
     done = []
     for mod_name, symbols in _TARGETS.items():
         mod = sys.modules.get(mod_name)
         if mod is None:
+            if mod_name in _SCRIPTS:      # never import (i.e. run) an experiment script just to patch it
+                continue
             try:
                 mod = importlib.import_module(mod_name)
             except Exception:
@@ -35,7 +45,7 @@ def install(strict: bool = False):
         for sym in symbols:
             if hasattr(mod, sym):
                 _saved.setdefault((mod_name, sym), getattr(mod, sym))
-                setattr(mod, sym, getattr(ours, sym))
+                setattr(mod, sym, _ours(sym))
                 done.append((mod_name, sym))
     return done
 
