@@ -154,3 +154,46 @@ def test_install_rebinds_a_visreps_like_module_tree(monkeypatch):
     assert not any(m == "experiments.reconstruction_analysis.run_reconstruction" for m, _ in done)   # not imported: not touched
     vb.uninstall()
     assert mods["visreps.evals"].compute_rdm is sentinel and mods["experiments.binary_pc_rsa.main"]._compare_rdms is sentinel
+
+
+def test_evals_blocks_assemble_reference_rows_from_a_grouped_job(monkeypatch):
+    """visreps_b200.evals host logic (no GPU): layers are re-extracted in sorted order (evals.py:309), every pair reads
+    the column of its own best layer, rows keep the caller's (region, subject) order and the reference's keys, and the
+    selection takes the first strict maximum (evals.py:270-273)."""
+    import torch
+    from visreps_b200 import evals as vevals, rsa as vrsa
+    calls = []
+
+    def fake_grouped(feats, neur, method, bootstrap=True, n_bootstrap=1000, seed=42, **kw):
+        calls.append((len(feats), len(neur), method, bootstrap, n_bootstrap, seed))
+        nA, nB = len(feats), len(neur)
+        point = np.array([[10.0 * i + j for j in range(nB)] for i in range(nA)])
+        out = {"point": point}
+        if bootstrap:
+            out["scores"] = point[:, :, None] + np.arange(n_bootstrap)[None, None, :] / 100.0
+            out["ci_low"], out["ci_high"] = vrsa.percentile_ci(out["scores"])
+        return out
+
+    monkeypatch.setattr(vrsa, "rsa_grouped", fake_grouped)
+    feats = {"fc1": torch.zeros(6, 3), "conv2": torch.zeros(6, 2, 2), "conv1": torch.zeros(6, 5)}
+    neural = {("V1", 0): torch.zeros(6, 4), ("V1", 1): torch.zeros(6, 4), ("PPA", 0): torch.zeros(6, 2)}
+    best = {("V1", 0): "fc1", ("V1", 1): "conv1", ("PPA", 0): "fc1"}
+    rows = vevals.score_pairs(feats, neural, best, "Spearman", bootstrap=True, n_bootstrap=5,
+                              selection_scores={k: [{"layer": "x", "score": 0.0}] for k in neural})
+    assert calls[-1] == (2, 3, "spearman", True, 5, 42)              # only the distinct best layers, sorted: conv1, fc1
+    assert [r["layer"] for r in rows] == ["fc1", "conv1", "fc1"]
+    assert [r["score"] for r in rows] == [10.0, 1.0, 12.0]           # (fc1 = row 1, pair 0), (conv1 = row 0, pair 1), (fc1, pair 2)
+    assert rows[0]["bootstrap_scores"] == [10.0, 10.01, 10.02, 10.03, 10.04] and rows[0]["compare_method"] == "spearman"
+    assert rows[1]["ci_low"] == float(np.percentile(rows[1]["bootstrap_scores"], 2.5)) and rows[1]["analysis"] == "rsa"
+    assert rows[2]["layer_selection_scores"] == [{"layer": "x", "score": 0.0}]
+    plain = vevals.score_pairs(feats, neural, best, "pearson")
+    assert all(r["ci_low"] is None and "bootstrap_scores" not in r and r["layer_selection_scores"] == [] for r in plain)
+
+    def fake_select(feats, neur, method, bootstrap=True, **kw):
+        return {"point": np.array([[0.2], [float("nan")], [0.7], [0.7]])}
+
+    monkeypatch.setattr(vrsa, "rsa_grouped", fake_select)
+    acts = {k: torch.zeros(12, 3) for k in ("a", "b", "c", "d")}
+    best_layer, scores = vevals.select_layer(acts, torch.zeros(12, 2), "spearman", n_select=1000)
+    assert best_layer == "c" and [s["layer"] for s in scores] == ["a", "b", "c", "d"] and np.isnan(scores[1]["score"])
+    assert list(vevals.selection_indices(2000, 1000)[:3]) == list(np.random.RandomState(42).choice(2000, size=1000, replace=False)[:3])
