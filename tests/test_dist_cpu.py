@@ -44,6 +44,12 @@ def _worker(rank, world, port, total, out):
         lo, hi = vdist.shard_bounds(total, rank, world)
         local = torch.arange(lo, hi, dtype=torch.float64).repeat(2, 1)
         order = vdist.gather_replicate_scores(local, total)
+        # the blob exchange of the sharded RDM build: ragged row blocks of bytes, rank order preserved
+        counts = [vdist.shard_bounds(5, r, world)[1] - vdist.shard_bounds(5, r, world)[0] for r in range(world)]
+        a, b = vdist.shard_bounds(5, rank, world)
+        mine = torch.stack([torch.full((16,), 10 * k + 1, dtype=torch.uint8) for k in range(a, b)]) if b > a else torch.empty((0, 16), dtype=torch.uint8)
+        rows = vdist._allgather_rows(mine, counts)
+        assert rows.shape == (5, 16) and [int(rows[k, 0]) for k in range(5)] == [1, 11, 21, 31, 41]
         if rank == 0:
             np.save(out, np.concatenate([res["scores"].ravel(), order.numpy().ravel()]))
     finally:
