@@ -33,7 +33,7 @@ namespace vr {
 
 constexpr int kRankThreadsMat = 1024;   // materialise: 64 registers per thread
 constexpr int kRankThreadsFused = 768;  // fused: 85 registers per thread, all 8 materialised loads in flight
-                                        // (512 threads x two groups: 11.2 ms, 1024 threads x two load batches: 11.0 ms, this: 10.1 ms)
+                                        // (512 threads x two groups: 11.2 ms, 1024 threads x two load batches: 11.0 ms, 896 threads: 12.9 ms, this: 9.9 ms)
 constexpr int kCountThreads = 1024;  // 32 warp segments per (vector, 32-replicate batch): 8192 warps fill the machine at NSD shape
 constexpr int kCountWarps = kCountThreads / 32;
 constexpr int kCountCtasMax = 16;       // CTAs sharing one (vector, 32-replicate batch) when there are few of them
