@@ -260,6 +260,10 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
+    # ---- parity gates (SURVEY 8d / BASELINE.md 3.6), part of the cpu_baseline leg: the oracle is the checker only
+    if cpu_baseline is not None:
+        cpu_baseline["parity_gates"] = parity_gates(vb, X, Y, res, B, dev)
+
     # a step's host work (index draws, percentiles) overlaps device work; the step time is the max
     # of the device-event time and the wall time between the two synchronised barriers
     t_step_ms = max(ms_dev, wall_dev) / args.steps
@@ -335,8 +339,9 @@ def run_ours(args):
                     "traffic": None, "peak_source": "measured bf16_tflops_sustained"}
     # second roofline object: the tensor-core SYRK family (all RDM builds of the step), useful TF32 work
     roofline_syrk = None
-    if prof.get("rdm_syrk", {}).get("ms", 0) > 0:
-        tf32_useful = 3.0 * sum(n * (n + 1) * t.shape[1] for t in X + Y) * args.steps / (prof["rdm_syrk"]["ms"] * 1e-3) / 1e12
+    syrk_ms = prof.get("rdm_syrk", {}).get("ms", 0) + prof.get("rdm_syrk_pair", {}).get("ms", 0)
+    if syrk_ms > 0:
+        tf32_useful = 3.0 * sum(n * (n + 1) * t.shape[1] for t in X + Y) * args.steps / (syrk_ms * 1e-3) / 1e12
         tf32_peak = float(peaks.get("bf16_tflops", 1599.5)) / 2.0
         roofline_syrk = {"kernel": "syrk_tc2_kernel (pair tiles, cta_group::2) / syrk_tc_kernel", "bound": "tensor",
                          "achieved": tf32_useful, "peak": tf32_peak, "unit": "TFLOP/s", "frac": tf32_useful / tf32_peak,
@@ -346,7 +351,7 @@ def run_ours(args):
                                  "(profiles/r1_syrk_tc2_conv1_full.txt); 11 % of the executed tensor work lies below the diagonal of the "
                                  "256-wide tiling and the short rows (ROIs, fc layers) are launch-bound"}
     rdm_flops = sum(n * (n + 1) * t.shape[1] for t in X + Y) * args.steps
-    rdm_ms = prof["rdm_syrk"]["ms"] + prof["rdm_center"]["ms"] + prof["rdm_epilogue"]["ms"]
+    rdm_ms = syrk_ms + prof["rdm_center"]["ms"] + prof["rdm_epilogue"]["ms"]
     rdm_tflops = rdm_flops / (rdm_ms * 1e-3) / 1e12 if rdm_ms > 0 else None
 
     line = {
@@ -371,6 +376,34 @@ def run_ours(args):
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def parity_gates(vb, X, Y, res, B, dev):
+    """The gates SURVEY 8d asks to print with every benchmark, on this run's own inputs (CPU oracle = checker):
+    RDM max-abs vs the port on one wide layer, ranks bit-exact, point + first two replicates vs the port."""
+    from oracle import rsa_oracle as orc
+    from visreps_b200 import rsa as vrsa
+    li = min(3, len(X) - 1)                                   # conv4 (43,264 features) at the full shape
+    n = int(X[li].shape[0])
+    a_gpu, b_gpu = vb.compute_rdm(X[li]), vb.compute_rdm(Y[0])
+    t0 = time.perf_counter()
+    a_ref = orc.rdm(X[li].cpu())
+    t_rdm = time.perf_counter() - t0
+    rdm_err = float((a_gpu.cpu() - a_ref).abs().max())
+    masks = vrsa.build_masks(None, n, dev, with_full=True)
+    devv, _, _ = vrsa.subsample_rank(a_gpu, masks)
+    N = n * (n - 1) // 2
+    ranks_ok = bool(np.array_equal(devv[0].cpu().numpy().astype(np.int64) + (N + 1), orc.rank2x(orc.triu_vector(a_gpu))))
+    idx = orc.draw_subsamples(n, 2, 42) if B >= 2 else None
+    point_ref = orc.rdm_compare(a_gpu.cpu(), b_gpu.cpu(), correlation="Spearman")
+    gates = {"layer": li, "rdm_max_abs_vs_port": rdm_err, "rdm_ok": rdm_err <= 1e-5, "ranks_bit_exact": ranks_ok,
+             "point_abs_diff": abs(float(res["point"][li, 0]) - point_ref), "port_rdm_seconds": t_rdm}
+    if idx is not None:
+        want = orc.bootstrap_compare_with_indices(a_gpu.cpu(), b_gpu.cpu(), "spearman", idx)
+        gates["replicates_max_abs_diff"] = float(np.abs(res["scores"][li, 0, :2] - np.asarray(want)).max())
+    gates["scores_ok"] = max(gates["point_abs_diff"], gates.get("replicates_max_abs_diff", 0.0)) <= 1e-5
+    assert gates["rdm_ok"] and gates["ranks_bit_exact"] and gates["scores_ok"], gates
+    return gates
 
 
 def _claim_stdout():

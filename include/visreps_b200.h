@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define VR_ABI_VERSION 2
+#define VR_ABI_VERSION 3
 #define VR_MAX_STIMULI 32767
 
 enum {
@@ -50,6 +50,13 @@ int vr_abi_version(void);
 const char* vr_last_error_string(void);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 unsigned long long vr_launch_count(void);
+
+/* Tuning options, for A/B measurements and for tests that must drive one specific kernel (no reference
+ * counterpart).  "syrk_pair": 1 (default) = 256 x 256 pair tiles on CTA pairs for long rows, 0 = single-CTA
+ * 128 x 128 tiles only.  "syrk_waves": CTA waves the SYRK's K splits are sized for (default 1).
+ * Initial values come from the environment (VR_SYRK_PAIR, VR_SYRK_WAVES). */
+int vr_set_option(const char* name, int value);
+int vr_get_option(const char* name, int* value);
 
 /* Built-in stage profiler (no reference counterpart; the reference has no tracing, SURVEY.md
  * section 5).  Between start and stop every stage of the library brackets its launches with CUDA

@@ -18,11 +18,30 @@ y = synth.roi_responses(z, 2000, 500)
 a = t("compute_rdm(model) [cold: allocates scratch]", lambda: vb.compute_rdm(x))
 a = t("compute_rdm(model)", lambda: vb.compute_rdm(x))
 print(f"   -> {n*(n+1)*d/1e12:.2f} algorithmic TFLOP")
-del x
-b = t("compute_rdm(neural, V=2000)", lambda: vb.compute_rdm(y))
 assert torch.equal(a, a.T) and float(a.diagonal().abs().max()) == 0.0
-# spot-check RDM rows against fp64 on the device
-xs = synth.layer_features(z[:64], d, 11).double()
+# spot-check 64 RDM rows (spread over the matrix) against the same formula in fp64 on the device (column chunks)
+def fp64_rows(x, rows):
+    nn, dd = x.shape
+    s1 = torch.zeros(nn, dtype=torch.float64, device=dev); s2 = torch.zeros_like(s1)
+    g = torch.zeros((len(rows), nn), dtype=torch.float64, device=dev)
+    for c0 in range(0, dd, 16384):
+        blk = x[:, c0:c0 + 16384].double()
+        s1 += blk.sum(1); s2 += (blk * blk).sum(1); g += blk[rows] @ blk.T
+    mean = s1 / dd
+    cov = g / dd - mean[rows][:, None] * mean[None, :]
+    sd = (s2 / dd - mean * mean).clamp_(min=0).add(1e-12).sqrt()
+    sd[sd < 1e-11] = 1.0
+    r = (cov / (sd[rows][:, None] * sd[None, :] + 1e-12)).clamp_(-1, 1)
+    out = 1.0 - r
+    out[torch.arange(len(rows), device=dev), rows] = 0.0
+    return out
+rows = torch.linspace(0, n - 1, 64, device=dev).long()
+truth = t("fp64 truth of 64 RDM rows", lambda: fp64_rows(x, rows))
+err = float((a[rows].double() - truth).abs().max())
+print(f"   RDM max-abs error vs fp64 on 64 rows x {n} columns: {err:.3e}")
+assert err <= 1e-5, err
+del x, truth
+b = t("compute_rdm(neural, V=2000)", lambda: vb.compute_rdm(y))
 pa = t("presort(model)", lambda: vrsa.PresortedRDM(a))
 pb = t("presort(neural)", lambda: vrsa.PresortedRDM(b))
 idx = vrsa.draw_index_sets(n, B, 42)

@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libvisreps_b200.so")
 
 VR_OK, VR_ERR_INVALID, VR_ERR_WORKSPACE, VR_ERR_CUDA, VR_ERR_UNSUPPORTED = range(5)
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # name -> (restype, argtypes); mirrors include/visreps_b200.h one to one
 _vp, _i, _i64, _sz, _f = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_float
@@ -24,6 +24,8 @@ SIGNATURES = {
     "vr_abi_version": (_i, []),
     "vr_last_error_string": (C.c_char_p, []),
     "vr_launch_count": (C.c_ulonglong, []),
+    "vr_set_option": (_i, [C.c_char_p, _i]),
+    "vr_get_option": (_i, [C.c_char_p, C.POINTER(C.c_int)]),
     "vr_profile_family_count": (_i, []),
     "vr_profile_family_name": (C.c_char_p, [_i]),
     "vr_profile_start": (_i, []),
@@ -128,6 +130,16 @@ def workspace(nbytes: int, device: torch.device, slot: str = "main") -> torch.Te
 
 def release_workspaces() -> None:
     _workspaces.clear()
+
+
+def set_option(name: str, value: int) -> None:
+    check(load().vr_set_option(name.encode(), int(value)), "vr_set_option")
+
+
+def get_option(name: str) -> int:
+    v = C.c_int(0)
+    check(load().vr_get_option(name.encode(), C.byref(v)), "vr_get_option")
+    return int(v.value)
 
 
 def launch_count() -> int:

@@ -1,6 +1,8 @@
 // Library-level entry points: ABI version, thread-local error text, launch counter.
 #include "common.cuh"
 #include <atomic>
+#include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <vector>
 
@@ -15,9 +17,15 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// ---- tuning options ---------------------------------------------------------------------
+static std::atomic<int> g_syrk_pair{[] { const char* e = getenv("VR_SYRK_PAIR"); return e ? atoi(e) : 1; }()};
+static std::atomic<int> g_syrk_waves{[] { const char* e = getenv("VR_SYRK_WAVES"); return e ? atoi(e) : 1; }()};
+int option_syrk_pair() { return g_syrk_pair.load(std::memory_order_relaxed); }
+int option_syrk_waves() { int w = g_syrk_waves.load(std::memory_order_relaxed); return w < 1 ? 1 : w; }
+
 // ---- stage profiler ---------------------------------------------------------------------
 static const char* kFamilyNames[F_NUM_FAMILIES] = {"masks", "presort", "count", "rank", "rank_fused", "pearson", "kendall",
-                                            "rdm_center", "rdm_syrk", "rdm_epilogue", "row_rank", "column_corr"};
+                                            "rdm_center", "rdm_syrk", "rdm_syrk_pair", "rdm_epilogue", "row_rank", "column_corr"};
 struct ProfRec { int fam; cudaEvent_t a, b; };
 static std::mutex g_prof_mu;
 static bool g_prof_on = false;
@@ -94,6 +102,21 @@ extern "C" int vr_profile_stop(double* ms, unsigned long long* scopes, unsigned 
   }
   vr::g_prof.clear();
   return rc;
+}
+
+extern "C" int vr_set_option(const char* name, int value) {
+  VR_REQUIRE(name, "vr_set_option: null name");
+  if (!strcmp(name, "syrk_pair")) { vr::g_syrk_pair.store(value); return VR_OK; }
+  if (!strcmp(name, "syrk_waves")) { VR_REQUIRE(value >= 1 && value <= 64, "vr_set_option: syrk_waves=%d outside [1, 64]", value); vr::g_syrk_waves.store(value); return VR_OK; }
+  vr::set_error("vr_set_option: unknown option '%s'", name);
+  return VR_ERR_INVALID;
+}
+extern "C" int vr_get_option(const char* name, int* value) {
+  VR_REQUIRE(name && value, "vr_get_option: null pointer");
+  if (!strcmp(name, "syrk_pair")) { *value = vr::option_syrk_pair(); return VR_OK; }
+  if (!strcmp(name, "syrk_waves")) { *value = vr::option_syrk_waves(); return VR_OK; }
+  vr::set_error("vr_get_option: unknown option '%s'", name);
+  return VR_ERR_INVALID;
 }
 
 extern "C" int vr_abi_version(void) { return VR_ABI_VERSION; }

@@ -13,13 +13,16 @@ namespace vr {
 // ---- error plumbing ------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 void count_launch(unsigned n = 1);
+// Tuning options (vr_set_option; initial values from VR_SYRK_PAIR / VR_SYRK_WAVES, for A/B measurements and tests).
+int option_syrk_pair();
+int option_syrk_waves();
 
 // ---- built-in stage profiler (CUDA events on the launching stream) ---------------------
 // Off by default.  Between vr_profile_start() and vr_profile_stop() every ProfScope records a
 // start/stop event pair; stop() synchronises them and returns per-family device time and
 // kernel-launch counts.  bench.py uses it to time the dominant kernel inside the timed region.
 enum Family {
-  F_MASKS = 0, F_PRESORT, F_KEPT, F_RANK, F_RANK_FUSED, F_PEARSON, F_KENDALL, F_RDM_CENTER, F_RDM_SYRK, F_RDM_EPILOGUE, F_ROWRANK, F_COLCORR,
+  F_MASKS = 0, F_PRESORT, F_KEPT, F_RANK, F_RANK_FUSED, F_PEARSON, F_KENDALL, F_RDM_CENTER, F_RDM_SYRK, F_RDM_SYRK_PAIR, F_RDM_EPILOGUE, F_ROWRANK, F_COLCORR,
   F_NUM_FAMILIES
 };
 struct ProfScope {

@@ -25,7 +25,7 @@ struct RdmPlan {
 
 inline RdmPlan rdm_plan(int n, int64_t d) {
   RdmPlan p;
-  static const int pair_mode = [] { const char* e = getenv("VR_SYRK_PAIR"); return e ? atoi(e) : 1; }();
+  const int pair_mode = option_syrk_pair();
   // pair tiles from four 128-row blocks on, and for K ranges long enough to fill whole waves of CTA pairs with
   // at least ~100 K-blocks each (short rows are launch- and wave-bound: the single-CTA kernel has more, smaller units)
   p.pair = pair_mode != 0 && n > 384 && d >= 16384;
@@ -39,7 +39,7 @@ inline RdmPlan rdm_plan(int n, int64_t d) {
   // One wave: tiles x splits <= number of SMs (one CTA is resident per SM).  Longer K chains per CTA mean fewer
   // pipeline fills, fewer partial planes for the epilogue to add, and no partially filled last wave; measured at the
   // NSD shape with the pair-tile kernel: 1 wave 2.40 + 0.19 ms (SYRK + epilogue), 3 waves 2.46 + 0.24, 6 waves 2.67 + 0.29.
-  static const int waves = [] { const char* e = getenv("VR_SYRK_WAVES"); return e ? atoi(e) : 1; }();
+  const int waves = option_syrk_waves();
   int64_t want_splits = ((int64_t)waves * kNumSMs) / tiles128;
   int64_t max_splits = (p.kb_total + 7) / 8;               // at least 8 K-blocks (256 columns) per CTA
   if (want_splits > max_splits) want_splits = max_splits;
@@ -226,7 +226,7 @@ extern "C" int vr_rdm_pearson_f32(const float* X, int n, int64_t d, int64_t ldx,
     if (rc != VR_OK) return rc;
     rc = tc::make_plane_map(&map_lo, Zlo, p.n_pad, p.d_pad);
     if (rc != VR_OK) return rc;
-    ProfScope prof(F_RDM_SYRK, stream);
+    ProfScope prof(p.pair ? F_RDM_SYRK_PAIR : F_RDM_SYRK, stream);
     if (p.pair) {
       static unsigned long long attr_done2 = 0;
       VR_CHECK_CUDA(ensure_dynamic_smem(tc2::syrk_tc2_kernel, (int)tc2::kSmemBytes2, &attr_done2));

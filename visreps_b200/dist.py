@@ -67,15 +67,16 @@ def rsa_grouped_sharded(model_features: Sequence[torch.Tensor], neural_responses
     With `shard_rdms` (NCCL, Spearman) the replicate-independent work is sharded too, so that it does not cap the
     scaling: rank r builds and presorts only its share of the RDMs, and one all-gather over NVLink hands every
     rank all presorted blobs (8 bytes per RDM pair, 14 MB at n = 1854) before the replicates are ranked.
-    `compute` is injectable for tests (and selects the replicate-only sharding).
+    `compute` is injectable for tests (and selects the replicate-only sharding).  `shard_rdms="force"` takes the
+    sharded-build branch at any world size (a one-rank NCCL group exercises the blob exchange on one GPU).
     """
     from . import rsa
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     lo, hi = shard_bounds(n_bootstrap, rank, world)
     method = method.lower()
-    sharded_build = (compute is None and shard_rdms and world > 1 and method == "spearman"
-                     and dist.get_backend(group) == "nccl")
+    sharded_build = (compute is None and bool(shard_rdms) and (world > 1 or shard_rdms == "force") and method == "spearman"
+                     and dist.is_initialized() and dist.get_backend(group) == "nccl")
     if not sharded_build:
         compute = compute or rsa.rsa_grouped
         res = compute(model_features, neural_responses, method, bootstrap=True, n_bootstrap=n_bootstrap, seed=seed,

@@ -846,6 +846,10 @@ def _pipeline_fits(n: int, nA: int, nB: int, R: int, dev: torch.device) -> bool:
     replicate-chunked one-call path when that would not fit comfortably."""
     lib = _lib.load()
     n_mat = min(nA, nB)
+    # vr_rank_fused addresses a materialised group (<= vr_rank_fuse_max() vectors x R replicates) with 32-bit int4
+    # offsets: 2^34 elements.  Beyond that the one-call path chunks the replicates itself.
+    if min(n_mat, lib.vr_rank_fuse_max()) * R * lib.vr_dev_stride(n) >= (1 << 34):
+        return False
     need = n_mat * R * (lib.vr_dev_stride(n) * 4 + 8) + lib.vr_rank_context_bytes(n, R) + \
         lib.vr_rank_workspace_bytes(n, max(min(n_mat, lib.vr_rank_fuse_max()), max(nA, nB)), R)
     key = (n, nA, nB, R, dev.index)
