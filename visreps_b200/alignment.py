@@ -39,6 +39,9 @@ def compute_traintest_alignment(cfg, train: AlignmentData, test: AlignmentData, 
                                 re_extract_fn=None) -> List[dict]:
     """Dispatch on cfg['analysis']; only 'rsa' is served by this package."""
     analysis = cfg.get("analysis", "rsa").lower()
+    if analysis == "encoding_score" and cfg.get("neural_dataset", "").lower() == "things-behavior":
+        raise ValueError("Encoding score is not supported for things-behavior (behavioral embeddings "
+                         "have no voxels to predict). Use analysis=rsa instead.")     # alignment.py:91-95
     if analysis == "rsa":
         return compute_rsa(cfg, train, test, n_select=cfg.get("n_select", None), bootstrap=cfg.get("bootstrap", True),
                            n_bootstrap=cfg.get("n_bootstrap", 1000), verbose=verbose, re_extract_fn=re_extract_fn)
