@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--n-bootstrap", type=int, default=1000)
     ap.add_argument("--small", action="store_true", help="shrunken layer widths (smoke runs only; not a valid bench)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling THINGS-shape job (BASELINE config 3)")
+    ap.add_argument("--strong-steps", type=int, default=5)
     return ap.parse_args()
 
 
@@ -86,12 +88,15 @@ def run_reference_arm(args):
     t_rdm = smp.time_rdms()                      # measured once (seconds-long); reused by every step
     for _ in range(args.warmup):
         smp.step(t_rdm)
-    vals, jobs = [], []
+    vals, jobs, per = [], [], []
     for _ in range(args.steps):
         r = smp.step(t_rdm)
         vals.append(r["value"])
         jobs.append(r["job_seconds"])
+        per.append(r["per_compare_s_per_core"])
+    as_written = smp.as_written(t_rdm)
     smp.close()
+    per_core = float(np.mean(per))
     v = float(np.mean(vals))
     line = {
         "metric": METRIC, "value": v, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
@@ -99,7 +104,8 @@ def run_reference_arm(args):
         "vs_baseline": None, "dtype": "f32 RDM (CPU sgemm) / f64 Spearman (SciPy)", "data": "synthetic",
         "config": config_dict(args, layers, rois, world),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": smp.cores, "kind": "port", "sample": smp.sample_description(),
-                         "t_rdm_s": t_rdm},
+                         "t_rdm_s": t_rdm, "s_per_replicate_per_core": per_core, "replicates_per_s_per_core": 1.0 / per_core,
+                         "as_written": as_written},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "ms_per_step is the whole-job time scaled from the bounded sample; a CPU job does not speed up with --gpus",
@@ -168,7 +174,9 @@ def run_ours(args):
         r = smp.step()
         cpu_baseline = {"value": r["value"], "unit": UNIT, "cores": smp.cores, "kind": "port",
                         "sample": smp.sample_description(), "t_rdm_s": r["t_rdm"],
-                        "s_per_replicate_per_core": r["per_compare_s_per_core"]}
+                        "s_per_replicate_per_core": r["per_compare_s_per_core"],
+                        "replicates_per_s_per_core": 1.0 / r["per_compare_s_per_core"],
+                        "as_written": smp.as_written(r["t_rdm"])}
         smp.close()
         torch.set_num_threads(max(1, min(8, smp.cores)))
 
@@ -181,11 +189,14 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
+    tf32_peak_info = measure_tf32_peak(dev) if (rank == 0 and not args.small) else None
     feats, neur = synth.nsd_workload(args.n, dev, seed=rank, layers=layers, rois=rois)
     X = [x for _, x in feats]
     Y = [y for _, y in neur]
     nA, nB, B = len(X), len(Y), args.n_bootstrap
     in_bytes = sum(t.numel() * 4 for t in X + Y)
+    neural_bytes = sum(t.numel() * 4 for t in Y)
+    flops_step = sum(args.n * (args.n + 1) * t.shape[1] for t in X + Y)
     gathered = torch.empty((world, nA, nB, B + 1), dtype=torch.float64, device=dev) if world > 1 else None
 
     def step_device():
@@ -254,6 +265,47 @@ def run_ours(args):
     ms_e2e, wall_e2e, _, _, res_e2e = timed(step_e2e, args.steps)
     assert np.array_equal(res["scores"], res_e2e["scores"]), "host-input and device-input runs disagree"
     assert np.isfinite(res["scores"]).all() and np.isfinite(res["point"]).all()
+
+    # ---- end to end with a device-resident producer (visreps_b200.producer / install(device_producer=True)): the model
+    # activations never leave the GPU (models/utils.py:344,391 bypassed); the neural responses still come from host
+    # memory (the loaders of dataloaders/neural.py return numpy arrays) and the results still go back to the host.
+    def step_e2e_device_producer():
+        return step_device_host(X, Yh)
+
+    step_e2e_device_producer()
+    ms_dp, wall_dp, _, _, res_dp = timed(step_e2e_device_producer, args.steps)
+    assert np.array_equal(res["scores"], res_dp["scores"])
+    del Xh
+
+    # ---- strong scaling (BASELINE config 3): THINGS shape, 1854 concepts, behavioural RDM (d = 66) vs 8 layers,
+    # B replicates of ONE job sharded over the ranks (dist.rsa_grouped_sharded: sharded RDM builds + presorts, blob
+    # all-gather over NVLink, replicate shards, one all-gather of the scores in replicate order)
+    strong = None
+    if not args.no_strong and not args.small:
+        from visreps_b200 import dist as vdist
+        del X, Y, feats, neur
+        torch.cuda.empty_cache()
+        n3 = 1854
+        z3 = synth.latent(n3, dev, 1)                                # same seeds on every rank: identical inputs
+        feats3 = [synth.layer_features(z3, d, 10 + i) for i, d in enumerate(layers.values())]
+        g3 = torch.Generator(device=dev).manual_seed(7)
+        beh = torch.relu(z3 @ torch.randn(synth.LATENT, 66, device=dev, generator=g3))
+
+        def step_strong():
+            if world > 1:
+                return vdist.rsa_grouped_sharded(feats3, [beh], "spearman", n_bootstrap=B, seed=42)
+            return vb.rsa_grouped(feats3, [beh], "spearman", bootstrap=True, n_bootstrap=B, seed=42)
+
+        for _ in range(2):
+            step_strong()
+        ms_s, wall_s, _, _, res_s = timed(step_strong, args.strong_steps)
+        t_s = max(ms_s, wall_s) / args.strong_steps
+        checksum = float(np.sum(res_s["scores"])) + float(np.sum(res_s["point"]))
+        strong = {"workload": f"THINGS shape (BASELINE config 3): n={n3}, behavioural RDM d=66 x {len(feats3)} layers, {B} replicates of ONE job",
+                  "scaling": "strong", "n_gpus": world, "ms_per_step": t_s, "value": len(feats3) * B / (t_s * 1e-3), "unit": UNIT,
+                  "steps": args.strong_steps, "score_checksum": checksum,
+                  "note": "score_checksum must be identical at every N (replicates keep their draw order, sums are exact integers)"}
+        del feats3, beh
 
     if rank != 0:
         if world > 1:
@@ -332,7 +384,7 @@ def run_ours(args):
             roofline["dram_GBps"] = roofline["traffic"] / (per_launch_ms * 1e-3) / 1e9
             roofline["dram_frac"] = roofline["dram_GBps"] / hbm_peak
     elif dom == "rdm_syrk":
-        flops = sum(n * (n + 1) * t.shape[1] for t in X + Y)
+        flops = flops_step
         tf_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
         ach = flops * args.steps / (prof[dom]["ms"] * 1e-3) / 1e12
         roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
@@ -341,16 +393,19 @@ def run_ours(args):
     roofline_syrk = None
     syrk_ms = prof.get("rdm_syrk", {}).get("ms", 0) + prof.get("rdm_syrk_pair", {}).get("ms", 0)
     if syrk_ms > 0:
-        tf32_useful = 3.0 * sum(n * (n + 1) * t.shape[1] for t in X + Y) * args.steps / (syrk_ms * 1e-3) / 1e12
-        tf32_peak = float(peaks.get("bf16_tflops", 1599.5)) / 2.0
+        tf32_useful = 3.0 * flops_step * args.steps / (syrk_ms * 1e-3) / 1e12
+        if tf32_peak_info:
+            tf32_peak, tf32_src = tf32_peak_info["burst_tflops"], "measured in this run: torch.matmul fp32 with TF32 tensor cores (cuBLAS), 8192^3, best of 10"
+        else:
+            tf32_peak, tf32_src = float(peaks.get("bf16_tflops", 1599.5)) / 2.0, "half the measured dense bf16 rate (MEASURED_PEAKS.json bf16_tflops)"
         roofline_syrk = {"kernel": "syrk_tc2_kernel (pair tiles, cta_group::2) / syrk_tc_kernel", "bound": "tensor",
                          "achieved": tf32_useful, "peak": tf32_peak, "unit": "TFLOP/s", "frac": tf32_useful / tf32_peak,
-                         "definition": "3 TF32 products x n(n+1)d useful flop per RDM (upper triangle) / CUDA-event time of the SYRK launches; "
-                                       "peak = half the measured dense bf16 rate (MEASURED_PEAKS.json bf16_tflops)",
+                         "definition": "3 TF32 products x n(n+1)d useful flop per RDM (upper triangle) / CUDA-event time of the SYRK launches",
+                         "peak_source": tf32_src,
                          "note": "ncu: sm__pipe_tensor_cycles_active 92.3 % for the pair-tile kernel at n=1000, d=193,600 "
                                  "(profiles/r1_syrk_tc2_conv1_full.txt); 11 % of the executed tensor work lies below the diagonal of the "
                                  "256-wide tiling and the short rows (ROIs, fc layers) are launch-bound"}
-    rdm_flops = sum(n * (n + 1) * t.shape[1] for t in X + Y) * args.steps
+    rdm_flops = flops_step * args.steps
     rdm_ms = syrk_ms + prof["rdm_center"]["ms"] + prof["rdm_epilogue"]["ms"]
     rdm_tflops = rdm_flops / (rdm_ms * 1e-3) / 1e12 if rdm_ms > 0 else None
 
@@ -361,6 +416,14 @@ def run_ours(args):
         "config": config_dict(args, layers, rois, world),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(in_bytes + B * ((n + 31) // 32) * 4),
                 "d2h_bytes_per_step": int(nA * nB * (B + 1) * 8 + (nA + nB) * 4), "ms_per_step": t_e2e_ms},
+        "e2e_device_producer": {"value": units / (max(ms_dp, wall_dp) / args.steps * 1e-3), "unit": UNIT,
+                                "ms_per_step": max(ms_dp, wall_dp) / args.steps,
+                                "h2d_bytes_per_step": int(neural_bytes + B * ((n + 31) // 32) * 4),
+                                "d2h_bytes_per_step": int(nA * nB * (B + 1) * 8 + (nA + nB) * 4),
+                                "definition": "model activations handed over on the device (visreps_b200.producer), neural responses "
+                                              "from pinned host memory, results back to the host"},
+        "strong_scaling": strong,
+        "tf32_peak": tf32_peak_info,
         "gpu_launches": int(launches),
         "clocks": clock_info,
         "roofline": roofline,
@@ -376,6 +439,38 @@ def run_ours(args):
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_tf32_peak(dev):
+    """Dense TF32 tensor-core peak of this box ('peak(TF32) to be measured the same way' as the bf16 peak in
+    MEASURED_PEAKS.json): cuBLAS through torch.matmul on fp32 operands with TF32 enabled, 8192^3, CUDA events; best of 10
+    (burst) and back to back for ~1.5 s (sustained).  Library GEMM used as the yardstick only."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        m = 8192
+        a = torch.randn(m, m, device=dev)
+        b = torch.randn(m, m, device=dev)
+        c = torch.empty(m, m, device=dev)
+        for _ in range(3):
+            torch.matmul(a, b, out=c)
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch.matmul(a, b, out=c); e1.record(); e1.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        reps = max(10, int(1500.0 / best))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            torch.matmul(a, b, out=c)
+        e1.record(); e1.synchronize()
+        flop = 2.0 * m ** 3
+        return {"burst_tflops": flop / (best * 1e-3) / 1e12, "sustained_tflops": flop * reps / (e0.elapsed_time(e1) * 1e-3) / 1e12,
+                "how": "torch.matmul fp32 operands, allow_tf32=True (cuBLAS TF32 tensor cores), 8192^3, CUDA events"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
 
 
 def parity_gates(vb, X, Y, res, B, dev):

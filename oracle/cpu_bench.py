@@ -45,7 +45,7 @@ class ReferenceSampler:
     """Builds the workload's inputs on the CPU once, forks a worker pool, times bounded samples."""
 
     def __init__(self, n: int, layer_dims: Dict[str, int], roi_dims: Dict[str, int], n_bootstrap: int,
-                 cores: int | None = None, reps_per_worker: int = 2, seed: int = 0):
+                 cores: int | None = None, reps_per_worker: int = 8, seed: int = 0):
         from visreps_b200 import synth  # data generator only (no CUDA, no kernels)
         self.n, self.n_bootstrap = n, n_bootstrap
         self.cores = cores or usable_cores()
@@ -91,6 +91,23 @@ class ReferenceSampler:
         t0 = time.perf_counter()
         self.pool.map(_worker, jobs)
         return time.perf_counter() - t0
+
+    def time_serial(self, reps: int = 8) -> float:
+        """Seconds per replicate of the loop AS WRITTEN (visreps/evals.py:361-369): one Python process, replicates one
+        after the other, BLAS threads = cores, SciPy ranking single-threaded."""
+        torch.set_num_threads(self.cores)
+        a, b, idx = _shared["a"], _shared["b"], _shared["idx"]
+        t0 = time.perf_counter()
+        orc.bootstrap_compare_with_indices(a, b, "spearman", idx[:reps])
+        return (time.perf_counter() - t0) / reps
+
+    def as_written(self, t_rdm: float, reps: int = 8) -> Dict[str, float]:
+        """The serial reference job (BASELINE.md 3.4 'reference as written'), scaled from `reps` replicates."""
+        per = self.time_serial(reps)
+        n_pairs = len(self.layer_dims) * len(self.roi_dims)
+        job = t_rdm + n_pairs * (self.n_bootstrap + 1) * per
+        return {"value": n_pairs * self.n_bootstrap / job, "job_seconds": job, "s_per_replicate": per, "replicates_timed": reps,
+                "cores": 1, "note": "serial Python loop as in evals.py:361-369 (SciPy ranking is single-threaded); RDM builds use all cores"}
 
     def step(self, t_rdm: float | None = None) -> Dict[str, float]:
         """One bounded sample -> estimated whole-job seconds and replicate-compares/s."""
