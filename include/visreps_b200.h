@@ -82,6 +82,24 @@ int vr_rdm_pearson_f32(const float* X, int n, int64_t d, int64_t ldx, float corr
                        float* rdm, int* zero_var_rows,
                        void* ws, size_t ws_bytes, vr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * The same RDM in stages, for rows whose FEATURES are split over several devices (K-split multi-GPU SYRK,
+ * the 10,000 x 193,600 stress shape).  Every rank holds a column shard X_r (n, d_r):
+ *   1. vr_rdm_moments_f32          per-row sum and sum of squares of the shard (fp64)   -> all-reduce (2n doubles)
+ *   2. vr_rdm_shift_from_moments   c_i = fp32(sum_i / d_total), the shift every rank subtracts
+ *   3. vr_rdm_gram_f32             G_r[i][j] = sum_k (x_ik - c_i)(x_jk - c_j) over the shard, j >= i (zero below the
+ *                                  diagonal), tensor-core SYRK, K splits summed in fp64, fp32 out -> all-reduce (n x n)
+ *   4. vr_rdm_finish_f32           rsa.py:80-92 from the reduced Gram and the whole-row moments: mean, std (+guard),
+ *                                  cov = G/d - delta_i delta_j, /(std_i std_j + c), clamp, 1 - r, mirror, diag 0.
+ * The Gram is reduced BEFORE the non-linear epilogue.  vr_rdm_gram_f32 needs vr_rdm_workspace_bytes(n, d_r).
+ * ---------------------------------------------------------------------------------- */
+int vr_rdm_moments_f32(const float* X, int n, int64_t d, int64_t ldx, double* sum, double* sumsq, vr_stream_t stream);
+int vr_rdm_shift_from_moments(const double* sum, int n, int64_t d_total, float* shift, vr_stream_t stream);
+int vr_rdm_gram_f32(const float* X, int n, int64_t d, int64_t ldx, const float* shift, float* gram, int64_t ldg,
+                    void* ws, size_t ws_bytes, vr_stream_t stream);
+int vr_rdm_finish_f32(const float* gram, int64_t ldg, int n, int64_t d_total, const double* sum, const double* sumsq,
+                      const float* shift, float correction, float* rdm, int* zero_var_rows, vr_stream_t stream);
+
 /* Row-wise 0-based ordinal ranks: replaces _rank(), rsa.py:50-52 (double argsort; ties
  * are split by position, lower index first).  out is (n, d) fp32, contiguous. */
 size_t vr_rank_rows_workspace_bytes(int n, int64_t d);
@@ -170,6 +188,29 @@ int vr_rank_fused(const void* const* blobs_host, int nF, int n, const void* ctx,
                   const int32_t* mat_dev, const double* mat_ss, int nM,
                   double* out, int64_t out_stride_fused, int64_t out_stride_mat,
                   void* ws, size_t ws_bytes, vr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Spearman job: the same grouped comparison with one warp per (canonical pair, 32 replicates) -- csrc/sweep.cu.
+ * Replaces evals.py:361-369 for any number of RDMs that share the R masks of a job (evals.py:356).
+ *   vr_spearman_job_init   masks -> per-batch transposed masks and N_r inside the opaque job buffer
+ *                          (vr_spearman_job_bytes(n, slots, R) bytes; `slots` = RDMs the job can hold)
+ *   vr_spearman_job_add    count tables (rows of {kept word, 2 C - N_r + 1} per 32 sorted positions and replicate) and tie
+ *                          sums of `count` presorted RDMs into slots slot0 .. slot0 + count - 1; may be called as the RDMs
+ *                          become available (the host pipeline overlaps it with host->device copies)
+ *   vr_spearman_job_sweep  rho for every (A vector, B vector, replicate):
+ *                          out[a * strideA + b * strideB + r], fp64, replicate order = mask order
+ * blobs*_host / slots*_host are HOST arrays (device blob pointers, slot numbers); n, R and slots must be the values the
+ * job was initialised with.  Sums are exact integers while N^3 < 9e18 (N <= ~2 M pairs), fp64 beyond.
+ * ---------------------------------------------------------------------------------- */
+size_t vr_spearman_job_bytes(int n, int slots, int R);
+int vr_spearman_job_init(const uint32_t* masks, int n, int R, int slots, void* job, size_t job_bytes, vr_stream_t stream);
+int vr_spearman_job_add(void* job, int n, int R, int slots, const void* const* blobs_host, int count, int slot0, vr_stream_t stream);
+size_t vr_spearman_sweep_workspace_bytes(int n, int nA, int nB, int R);
+int vr_spearman_job_sweep(void* job, int n, int R, int slots,
+                          const void* const* blobsA_host, const int* slotsA_host, int nA,
+                          const void* const* blobsB_host, const int* slotsB_host, int nB,
+                          double* out, int64_t strideA, int64_t strideB,
+                          void* ws, size_t ws_bytes, vr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Grouped bootstrap comparison: replaces the loop at evals.py:361-369 (and its copies at

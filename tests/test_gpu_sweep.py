@@ -1,0 +1,144 @@
+"""The row-sweep Spearman engine (csrc/sweep.cu: one warp per canonical pair x 32 replicates) against the oracle and against
+the legacy engine (csrc/rank.cu), which the bit-exact rank tests pin: same integers in, same scores out."""
+import numpy as np
+import pytest
+import torch
+
+import visreps_b200 as vb
+from visreps_b200 import _lib, rsa as vrsa
+from oracle import cases, rsa_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda", 0)
+
+
+def _both_engines(A, B, masks):
+    out = {}
+    for engine in ("sweep", "legacy"):
+        old = vrsa.SPEARMAN_ENGINE
+        vrsa.SPEARMAN_ENGINE = engine
+        try:
+            out[engine] = vrsa.compare_grouped(A, B, "spearman", masks).cpu().numpy()
+        finally:
+            vrsa.SPEARMAN_ENGINE = old
+    return out["sweep"], out["legacy"]
+
+
+def _rdm_from_vector(v, n, dev):
+    return cases.vector_to_rdm(np.asarray(v, dtype=np.float32), n).to(dev)
+
+
+@pytest.mark.parametrize("n,levels,R", [(40, 5, 7), (130, 300, 33), (300, 40, 64), (700, 100000, 70)])
+def test_sweep_equals_legacy_and_oracle_with_ties(n, levels, R, dev):
+    """Tie structures from 'almost everything tied' to 'almost nothing tied'; replicate counts around the 32-lane batches."""
+    N = n * (n - 1) // 2
+    a, b = cases.tied_vectors(N, levels, 900 + n)
+    rs = np.random.RandomState(n)
+    c = rs.standard_normal(N).astype(np.float32)
+    A = vrsa.PresortedRDM.batch([_rdm_from_vector(a, n, dev), _rdm_from_vector(c, n, dev), _rdm_from_vector(np.round(c, 1), n, dev)])
+    B = vrsa.PresortedRDM.batch([_rdm_from_vector(b, n, dev), _rdm_from_vector(-c + 0.01 * a, n, dev)])
+    idx = vrsa.draw_index_sets(n, R - 1, 42)
+    masks = vrsa.build_masks(idx, n, dev, with_full=True)
+    sweep, legacy = _both_engines(A, B, masks)
+    assert sweep.shape == (3, 2, R)
+    np.testing.assert_array_equal(sweep, legacy)                      # exact integer sums on both sides: bit-identical
+    for r in (0, 1, R - 1):                                           # point estimate and two replicates against SciPy
+        sub = np.arange(n) if r == 0 else np.sort(idx[r - 1])
+        for i, va in enumerate((a, c, np.round(c, 1))):
+            ra = cases.vector_to_rdm(np.asarray(va, dtype=np.float32), n)[sub][:, sub]
+            rb = cases.vector_to_rdm(b, n)[sub][:, sub]
+            want = orc.rdm_compare(ra, rb, correlation="Spearman")
+            assert abs(sweep[i, 0, r] - want) <= 1e-9
+
+
+def test_sweep_run_shapes_long_runs_cross_group_and_constant(dev):
+    """Runs that end in the next 32-group, runs longer than a group, one run spanning the whole vector, runs at the very end."""
+    n = 66
+    N = n * (n - 1) // 2                                              # 2145 = 67 groups + 1 position
+    base = np.arange(N, dtype=np.float32)
+    v1 = base.copy(); v1[20:45] = 20.0; v1[60:70] = 60.0; v1[100:400] = 100.0; v1[N - 3:] = float(N)      # cross, long, tail runs
+    v2 = np.floor(base / 31.0).astype(np.float32)                      # every run crosses a group boundary somewhere
+    v3 = np.full(N, 3.0, dtype=np.float32)                             # constant: correlation undefined -> NaN
+    v4 = base[::-1].copy()
+    rs = np.random.RandomState(1)
+    perm = rs.permutation(N)
+    vecs = [v1[perm], v2[perm], v3, v4[perm]]
+    A = vrsa.PresortedRDM.batch([_rdm_from_vector(v, n, dev) for v in vecs])
+    masks = vrsa.build_masks(vrsa.draw_index_sets(n, 40, 7), n, dev, with_full=True)
+    sweep, legacy = _both_engines(A, A, masks)
+    assert np.array_equal(sweep, legacy, equal_nan=True)
+    assert np.isnan(sweep[2]).all() and np.isnan(sweep[:, 2]).all()
+    for k in (0, 1, 3):
+        np.testing.assert_allclose(sweep[k, k], 1.0, atol=1e-12, rtol=0)
+    want = orc.rdm_compare(cases.vector_to_rdm(vecs[0], n), cases.vector_to_rdm(vecs[1], n), correlation="Spearman")
+    assert abs(sweep[0, 1, 0] - want) <= 1e-9 and sweep[0, 1, 0] == sweep[1, 0, 0]
+
+
+def test_sweep_tiles_and_group_sizes_agree(dev):
+    """Any tiling of the (A, B) grid (options sweep_tile_a / sweep_tile_b, padded instantiations for 3, 5, 6, 7 vectors) gives
+    the same bits; more than eight vectors per side are tiled by the library."""
+    x, y = cases.pair_inputs("p220")
+    n = x.shape[0]
+    rs = np.random.RandomState(3)
+    feats = [x[:, rs.permutation(x.shape[1])[:40 + 3 * k]] for k in range(11)]
+    neur = [y[:, rs.permutation(y.shape[1])[:30 + 5 * k]] for k in range(5)]
+    A = vrsa.PresortedRDM.batch([vb.compute_rdm(f.to(dev)) for f in feats])
+    B = vrsa.PresortedRDM.batch([vb.compute_rdm(f.to(dev)) for f in neur])
+    masks = vrsa.build_masks(vrsa.draw_index_sets(n, 45, 42), n, dev, with_full=True)
+    ref, legacy = _both_engines(A, B, masks)
+    np.testing.assert_array_equal(ref, legacy)
+    try:
+        for ta, tb in ((1, 1), (3, 5), (8, 2), (5, 8), (7, 3)):
+            _lib.set_option("sweep_tile_a", ta)
+            _lib.set_option("sweep_tile_b", tb)
+            got = vrsa.compare_grouped(A, B, "spearman", masks).cpu().numpy()
+            np.testing.assert_array_equal(got, ref)
+    finally:
+        _lib.set_option("sweep_tile_a", 8)
+        _lib.set_option("sweep_tile_b", 8)
+    with pytest.raises(ValueError):
+        _lib.set_option("sweep_tile_a", 9)
+
+
+def test_sweep_large_n_general_run_words_and_fp64_sums(dev):
+    """n = 2100: N = 2,203,950 pairs is past the compact run words (n <= 2048) and past exact int64 totals; the sweep then
+    sums in fp64 in a fixed order.  Checked against the legacy engine (its own fp64 path) and SciPy on the point estimate."""
+    n = 2100
+    rs = np.random.RandomState(5)
+    z = rs.standard_normal((n, 12)).astype(np.float32)
+    x = torch.from_numpy(np.maximum(z @ rs.standard_normal((12, 60)).astype(np.float32) + rs.standard_normal((n, 60)).astype(np.float32), 0))
+    y = torch.from_numpy(np.round(z @ rs.standard_normal((12, 9)).astype(np.float32), 1))           # coarse values: many ties
+    A = vrsa.PresortedRDM.batch([vb.compute_rdm(x.to(dev))])
+    B = vrsa.PresortedRDM.batch([vb.compute_rdm(y.to(dev))])
+    masks = vrsa.build_masks(vrsa.draw_index_sets(n, 3, 42), n, dev, with_full=True)
+    sweep, legacy = _both_engines(A, B, masks)
+    np.testing.assert_allclose(sweep, legacy, atol=1e-12, rtol=0)
+    again = vrsa.compare_grouped(A, B, "spearman", masks).cpu().numpy()
+    np.testing.assert_array_equal(sweep, again)                        # deterministic
+    want = orc.rdm_compare(A[0].rdm.cpu(), B[0].rdm.cpu(), correlation="Spearman")
+    assert abs(sweep[0, 0, 0] - want) <= 1e-9
+
+
+def test_sweep_job_is_incremental(dev):
+    """Vectors added to a job one by one, in any order, and swept in groups give the scores of the one-shot call."""
+    x, y = cases.pair_inputs("p64")
+    n = x.shape[0]
+    rdms = [vb.compute_rdm(x[:, k::3].to(dev)) for k in range(3)] + [vb.compute_rdm(y[:, k::2].to(dev)) for k in range(2)]
+    items = vrsa.PresortedRDM.batch(rdms)
+    masks = vrsa.build_masks(vrsa.draw_index_sets(n, 20, 42), n, dev, with_full=True)
+    R = int(masks.shape[0])
+    want = vrsa.compare_grouped(items[:3], items[3:], "spearman", masks)
+    job = vrsa.SpearmanJob(masks, n, 5)
+    job.add([items[4]], 4)
+    job.add([items[3]], 3)
+    out = torch.full((3, 2, R), float("nan"), dtype=torch.float64, device=dev)
+    for k in (2, 0, 1):
+        job.add([items[k]], k)
+        job.sweep([k], [3, 4], out.view(-1), k * 2 * R, 2 * R, R)
+    assert torch.equal(out, want)
+    with pytest.raises(ValueError):
+        job.add([vrsa.PresortedRDM(vb.compute_rdm(torch.randn(n + 1, 8, device=dev)))], 0)

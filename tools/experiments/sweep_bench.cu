@@ -146,6 +146,256 @@ sweep_kernel(const Desc* __restrict__ desc, int N, int G, const uint2* __restric
     }
 }
 
+
+// ---- v3: descriptors (4 B: row << 5 | bit) staged through a per-warp shared-memory ring with cp.async, table rows of the NEXT
+// pair in flight while the current one is multiplied (two-stage software pipeline), fp64 accumulators.
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int kWarps>
+__global__ void __launch_bounds__(kWarps * 32, 1)
+sweep3_kernel(const uint32_t* __restrict__ desc4 /*[N][NV]*/, int N, int G, const uint2* __restrict__ tables, int batches,
+              const uint32_t* __restrict__ nkept, const uint32_t* __restrict__ pairs_canon, const uint32_t* __restrict__ maskT, int n,
+              int splits, unsigned long long* __restrict__ out) {
+  __shared__ __align__(16) uint32_t ring[kWarps][2][NV / 4][32][4];    // [buffer][quad][pair in block][4 descriptors]
+  __shared__ uint32_t kring[kWarps][2][32];                            // kept words of the block's pairs
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x / splits, s = blockIdx.x % splits;
+  const int per = (N + splits - 1) / splits;
+  const int c_lo = s * per, c_hi = min(N, c_lo + per);
+  const int wper = ((c_hi - c_lo) + kWarps - 1) / kWarps;
+  const int p_lo = c_lo + warp * wper, p_hi = min(c_hi, p_lo + wper);
+  const char* base = reinterpret_cast<const char*>(tables) + (size_t)b * ((size_t)NV * G * 256) + lane * 8;
+  const uint32_t* mt = maskT + (size_t)b * n;
+  double acc[NA][NB];
+#pragma unroll
+  for (int a = 0; a < NA; ++a)
+#pragma unroll
+    for (int c = 0; c < NB; ++c) acc[a][c] = 0.0;
+
+  auto stage_block = [&](int p0, int buf) {      // descriptors + kept words of pairs p0 .. p0+31 -> ring[buf]
+    const int q = min(p0 + lane, N - 1);
+    const uint4* src = reinterpret_cast<const uint4*>(desc4 + (size_t)q * NV);
+#pragma unroll
+    for (int k = 0; k < NV / 4; ++k) cp_async16(&ring[warp][buf][k][lane][0], src + k);
+    cp_async_commit();
+    const uint32_t pw = __ldg(pairs_canon + q);
+    kring[warp][buf][lane] = __ldg(mt + (pw >> 16)) & __ldg(mt + (pw & 0xFFFF));
+  };
+  uint2 e_next[NV];
+  uint32_t bit_next[NV];
+  auto issue = [&](int buf, int k) {              // table rows of pair k of the block in ring[buf]
+#pragma unroll
+    for (int q4 = 0; q4 < NV / 4; ++q4) {
+      const uint4 d = *reinterpret_cast<const uint4*>(&ring[warp][buf][q4][k][0]);
+      const uint32_t dd[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        e_next[q4 * 4 + j] = ldg64(base + ((size_t)(dd[j] & ~31u) << 3));
+        bit_next[q4 * 4 + j] = dd[j];
+      }
+    }
+  };
+  if (p_lo < p_hi) {
+    stage_block(p_lo, 0);
+    cp_async_wait_all();
+    __syncwarp();
+    issue(0, 0);
+  }
+  int buf = 0;
+  for (int p0 = p_lo; p0 < p_hi; p0 += 32, buf ^= 1) {
+    const int cnt = min(32, p_hi - p0);
+    if (p0 + 32 < p_hi) stage_block(p0 + 32, buf ^ 1);
+    for (int k = 0; k < cnt; ++k) {
+      uint2 e[NV];
+      uint32_t bit[NV];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) { e[v] = e_next[v]; bit[v] = bit_next[v]; }
+      const uint32_t kw = kring[warp][buf][k];
+      if (k + 1 < cnt) issue(buf, k + 1);
+      else if (p0 + 32 < p_hi) { cp_async_wait_all(); __syncwarp(); issue(buf ^ 1, 0); }
+      const bool keep = (kw >> lane) & 1u;
+      double dd[NV];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const uint32_t low = e[v].x & ((1u << (bit[v] & 31u)) - 1u);
+        uint32_t d = 2u * (e[v].y + __popc(low)) + 1u;
+        if (v < NA) d = keep ? d : 0u;
+        dd[v] = u2d(d);
+      }
+#pragma unroll
+      for (int a = 0; a < NA; ++a)
+#pragma unroll
+        for (int c = 0; c < NB; ++c) acc[a][c] = fma(dd[a], dd[NA + c], acc[a][c]);
+    }
+  }
+  __shared__ unsigned long long red[kWarps][32];
+  const unsigned long long nr = nkept[(size_t)b * 32 + lane];
+  const unsigned long long share = (warp == 0 && s == 0) ? nr * nr * nr : 0ull;
+#pragma unroll
+  for (int a = 0; a < NA; ++a)
+#pragma unroll
+    for (int c = 0; c < NB; ++c) {
+      red[warp][lane] = (unsigned long long)acc[a][c] - share;
+      __syncthreads();
+      if (warp == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < kWarps; ++w) t += red[w][lane];
+        atomicAdd(out + ((size_t)(a * NB + c) * batches + b) * 32 + lane, t);
+      }
+      __syncthreads();
+    }
+}
+
+
+// ---- v5: table rows fetched with cp.async straight into a per-warp shared-memory ring, kDepth pairs ahead (no registers
+// held while the rows are in flight); tables carry cnt2 = 2*C(32g) - N_r + 2^31 so that dev + 2^31 = cnt2 + 2*popc is the low
+// word of an exactly representable double; fp64 accumulators.
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+template <int N_> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+
+template <int kWarps, int kDepth>
+__global__ void __launch_bounds__(kWarps * 32, 1)
+sweep5_kernel(const uint32_t* __restrict__ desc4 /*[N][NV]*/, int N, int G, const uint2* __restrict__ tables2, int batches,
+              const uint32_t* __restrict__ pairs_canon, const uint32_t* __restrict__ maskT, int n,
+              int splits, double* __restrict__ out /*[NA][NB][batches*32]*/) {
+  extern __shared__ __align__(16) unsigned char smem5[];
+  uint2 (*rows)[kDepth][NV][32] = reinterpret_cast<uint2 (*)[kDepth][NV][32]>(smem5);                       // [warp][slot][v][lane]
+  uint32_t (*ring)[2][NV / 4][32][4] = reinterpret_cast<uint32_t (*)[2][NV / 4][32][4]>(smem5 + (size_t)kWarps * kDepth * NV * 256);
+  uint32_t (*kring)[2][32] = reinterpret_cast<uint32_t (*)[2][32]>(smem5 + (size_t)kWarps * kDepth * NV * 256 + (size_t)kWarps * 2 * NV * 128);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x / splits, s = blockIdx.x % splits;
+  const int per = (N + splits - 1) / splits;
+  const int c_lo = s * per, c_hi = min(N, c_lo + per);
+  const int wper = ((c_hi - c_lo) + kWarps - 1) / kWarps;
+  const int p_lo = c_lo + warp * wper, p_hi = min(c_hi, p_lo + wper);
+  const int count = max(0, p_hi - p_lo);
+  const char* base = reinterpret_cast<const char*>(tables2) + (size_t)b * ((size_t)NV * G * 256) + lane * 8;
+  const uint32_t* mt = maskT + (size_t)b * n;
+  double acc[NA][NB];
+#pragma unroll
+  for (int a = 0; a < NA; ++a)
+#pragma unroll
+    for (int c = 0; c < NB; ++c) acc[a][c] = 0.0;
+
+  auto stage_block = [&](int blk) {               // descriptors + kept words of pairs p_lo + 32 blk .. + 31 -> ring[blk & 1]
+    const int q = min(p_lo + blk * 32 + lane, N - 1);
+    const uint4* src = reinterpret_cast<const uint4*>(desc4 + (size_t)q * NV);
+    uint4 t[NV / 4];
+#pragma unroll
+    for (int k = 0; k < NV / 4; ++k) t[k] = __ldg(src + k);
+    const uint32_t pw = __ldg(pairs_canon + q);
+    const uint32_t kw = __ldg(mt + (pw >> 16)) & __ldg(mt + (pw & 0xFFFF));
+#pragma unroll
+    for (int k = 0; k < NV / 4; ++k) *reinterpret_cast<uint4*>(&ring[warp][blk & 1][k][lane][0]) = t[k];
+    kring[warp][blk & 1][lane] = kw;
+    __syncwarp();
+  };
+  auto issue = [&](int i) {                        // rows of the warp's i-th pair -> slot i % kDepth
+    const int blk = i >> 5, k = i & 31, slot = i % kDepth;
+#pragma unroll
+    for (int q4 = 0; q4 < NV / 4; ++q4) {
+      const uint4 d = *reinterpret_cast<const uint4*>(&ring[warp][blk & 1][q4][k][0]);
+      const uint32_t dd[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) cp_async8(&rows[warp][slot][q4 * 4 + j][lane], base + ((size_t)(dd[j] & ~31u) << 3));
+    }
+  };
+  if (count > 0) {
+    stage_block(0);
+    if (count > 32) stage_block(1);
+#pragma unroll 1
+    for (int i = 0; i < kDepth; ++i) { if (i < count) issue(i); cp_async_commit(); }
+  }
+#pragma unroll 1
+  for (int i = 0; i < count; ++i) {
+    const int blk = i >> 5, k = i & 31, slot = i % kDepth;
+    cp_async_wait<kDepth - 1>();
+    uint2 e[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) e[v] = rows[warp][slot][v][lane];
+    uint32_t bits[NV];
+#pragma unroll
+    for (int q4 = 0; q4 < NV / 4; ++q4) {
+      const uint4 d = *reinterpret_cast<const uint4*>(&ring[warp][blk & 1][q4][k][0]);
+      bits[q4 * 4] = d.x; bits[q4 * 4 + 1] = d.y; bits[q4 * 4 + 2] = d.z; bits[q4 * 4 + 3] = d.w;
+    }
+    const uint32_t kw = kring[warp][blk & 1][k];
+    if (i + kDepth < count) issue(i + kDepth);
+    cp_async_commit();
+    if (k == 31 && (blk + 2) * 32 < count) stage_block(blk + 2);     // ring[blk & 1] is free from here on (pairs < kDepth ahead live in blk + 1)
+    const bool keep = (kw >> lane) & 1u;
+    double dd[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      uint32_t m;
+      asm("bmsk.wrap.b32 %0, 0, %1;" : "=r"(m) : "r"(bits[v]));
+      uint32_t d = e[v].y + 2u * (uint32_t)__popc(e[v].x & m);            // dev + 2^31
+      if (v < NA) d = keep ? d : 0x80000000u;
+      dd[v] = __hiloint2double(0x43300000, (int)d) - 4503601774854144.0;  // 2^52 + 2^31
+    }
+#pragma unroll
+    for (int a = 0; a < NA; ++a)
+#pragma unroll
+      for (int c = 0; c < NB; ++c) acc[a][c] = fma(dd[a], dd[NA + c], acc[a][c]);
+  }
+  __shared__ double red[kWarps][32];
+#pragma unroll
+  for (int a = 0; a < NA; ++a)
+#pragma unroll
+    for (int c = 0; c < NB; ++c) {
+      red[warp][lane] = acc[a][c];
+      __syncthreads();
+      if (warp == 0) {
+        double t = 0;
+        for (int w = 0; w < kWarps; ++w) t += red[w][lane];
+        atomicAdd(out + ((size_t)(a * NB + c) * batches + b) * 32 + lane, t);
+      }
+      __syncthreads();
+    }
+}
+
+__global__ void rebias_tables(const uint2* __restrict__ src, uint2* __restrict__ dst, size_t entries, int G, const uint32_t* __restrict__ nkept) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= entries) return;
+  const int lane = (int)(i & 31);
+  const size_t b = i / ((size_t)NV * G * 32);
+  const uint2 e = src[i];
+  dst[i] = make_uint2(e.x, 2u * e.y + 1u - nkept[b * 32 + lane] + 0x80000000u);    // 2 C + 1 - N_r + 2^31 (tie-free: dev = 2 C(s) + 1 - N_r)
+}
+
+
+// ---- probe: the table-row fetch pattern alone (random 256-byte rows of one batch block, 16 per pair), trivial compute
+template <int kRowBytes>
+__global__ void __launch_bounds__(1024, 1)
+fetch_only_kernel(const uint32_t* __restrict__ desc4, int N, int G, const uint2* __restrict__ tables2, int splits, uint32_t* __restrict__ sink) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int b = blockIdx.x / splits, s = blockIdx.x % splits;
+  const int per = (N + splits - 1) / splits;
+  const int p_lo = s * per, p_hi = min(N, p_lo + per);
+  const char* base = reinterpret_cast<const char*>(tables2) + (size_t)b * ((size_t)NV * G * 256) + lane * (kRowBytes / 32);
+  uint32_t x = 0;
+  for (int p = p_lo + warp; p < p_hi; p += nw) {
+    const uint4* dp = reinterpret_cast<const uint4*>(desc4 + (size_t)p * NV);
+#pragma unroll
+    for (int k = 0; k < NV / 4; ++k) {
+      const uint4 d = __ldg(dp + k);
+      const uint32_t dd[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const char* a = base + ((size_t)(dd[j] & ~31u) << 3);
+        if (kRowBytes == 256) { const uint2 e = ldg64(a); x ^= e.x + e.y; }
+        else { x ^= __ldg(reinterpret_cast<const uint32_t*>(a)); }
+      }
+    }
+  }
+  if (x == 0x12345678u) sink[0] = x;
+}
 int main(int argc, char** argv) {
   const int n = argc > 1 ? atoi(argv[1]) : 1000;
   const int R = argc > 2 ? atoi(argv[2]) : 1024;
@@ -158,13 +408,14 @@ int main(int argc, char** argv) {
   // per vector: random sorted order
   std::vector<uint32_t> sorted_pairs((size_t)NV * N);
   std::vector<Desc> desc((size_t)N * NV);
+  std::vector<uint32_t> desc4((size_t)N * NV);
   std::vector<std::vector<uint32_t>> pos(NV, std::vector<uint32_t>(N));
   for (int v = 0; v < NV; ++v) {
     std::vector<uint32_t> perm(N);
     std::iota(perm.begin(), perm.end(), 0u);
     std::shuffle(perm.begin(), perm.end(), rng);       // perm[x] = canonical pair at sorted position x
     for (int x = 0; x < N; ++x) { sorted_pairs[(size_t)v * N + x] = canon[perm[x]]; pos[v][perm[x]] = x; }
-    for (int p = 0; p < N; ++p) { const uint32_t x = pos[v][p]; desc[(size_t)p * NV + v] = Desc{((uint32_t)v * G + (x >> 5)) * 256u, (1u << (x & 31)) - 1u}; }
+    for (int p = 0; p < N; ++p) { const uint32_t x = pos[v][p]; desc[(size_t)p * NV + v] = Desc{((uint32_t)v * G + (x >> 5)) * 256u, (1u << (x & 31)) - 1u}; desc4[(size_t)p * NV + v] = (((uint32_t)v * G + (x >> 5)) << 5) | (x & 31); }
   }
   // masks: each replicate drops n/10 stimuli; maskT[b][i] bit r
   std::vector<uint32_t> maskT((size_t)batches * n, 0u);
@@ -178,6 +429,7 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&d_sorted, sorted_pairs.size() * 4)); CK(cudaMemcpy(d_sorted, sorted_pairs.data(), sorted_pairs.size() * 4, cudaMemcpyHostToDevice));
   CK(cudaMalloc(&d_maskT, maskT.size() * 4)); CK(cudaMemcpy(d_maskT, maskT.data(), maskT.size() * 4, cudaMemcpyHostToDevice));
   CK(cudaMalloc(&d_canon, (size_t)N * 4)); CK(cudaMemcpy(d_canon, canon.data(), (size_t)N * 4, cudaMemcpyHostToDevice));
+  uint32_t* d_desc4; CK(cudaMalloc(&d_desc4, desc4.size() * 4)); CK(cudaMemcpy(d_desc4, desc4.data(), desc4.size() * 4, cudaMemcpyHostToDevice));
   CK(cudaMalloc(&d_desc, desc.size() * 8)); CK(cudaMemcpy(d_desc, desc.data(), desc.size() * 8, cudaMemcpyHostToDevice));
   const size_t tab_bytes = (size_t)NV * batches * G * 32 * 8;
   printf("tables: %.1f MB total, %.1f MB per batch\n", tab_bytes / 1e6, tab_bytes / 1e6 / batches);
@@ -185,6 +437,9 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&d_out, (size_t)NA * NB * batches * 32 * 8));
   build_tables<<<dim3(batches, NV), 32>>>(d_sorted, N, G, d_maskT, n, batches, d_tables, d_nkept);
   CK(cudaDeviceSynchronize());
+  uint2* d_tables2; CK(cudaMalloc(&d_tables2, tab_bytes));
+  { const size_t entries = tab_bytes / 8; rebias_tables<<<(unsigned)((entries + 255) / 256), 256>>>(d_tables, d_tables2, entries, G, d_nkept); CK(cudaDeviceSynchronize()); }
+  double* d_outd; CK(cudaMalloc(&d_outd, (size_t)NA * NB * batches * 32 * 8));
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   auto run = [&](int splits, int warps, int flavour) {
     float best = 1e9f;
@@ -192,7 +447,23 @@ int main(int argc, char** argv) {
       CK(cudaMemset(d_out, 0, (size_t)NA * NB * batches * 32 * 8));
       cudaEventRecord(e0);
 #define LAUNCH(W, F) sweep_kernel<W, F><<<batches * splits, W * 32>>>(d_desc, N, G, d_tables, batches, d_nkept, d_canon, d_maskT, n, splits, d_out)
-      if (warps == 8 && flavour == 0) LAUNCH(8, 0);
+#define LAUNCH3(W) sweep3_kernel<W><<<batches * splits, W * 32>>>(d_desc4, N, G, d_tables, batches, d_nkept, d_canon, d_maskT, n, splits, d_out)
+#define LAUNCH5(W, D) do { const size_t sm = (size_t)W * D * NV * 256 + (size_t)W * 2 * NV * 128 + (size_t)W * 2 * 128; \
+        CK(cudaFuncSetAttribute(sweep5_kernel<W, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+        CK(cudaMemset(d_outd, 0, (size_t)NA * NB * batches * 32 * 8)); cudaEventRecord(e0); \
+        sweep5_kernel<W, D><<<batches * splits, W * 32, sm>>>(d_desc4, N, G, d_tables2, batches, d_canon, d_maskT, n, splits, d_outd); } while (0)
+      if (flavour == 52 && warps == 8) LAUNCH5(8, 2);
+      else if (flavour == 53 && warps == 8) LAUNCH5(8, 3);
+      else if (flavour == 54 && warps == 8) LAUNCH5(8, 4);
+      else if (flavour == 54 && warps == 6) LAUNCH5(6, 4);
+      else if (flavour == 56 && warps == 6) LAUNCH5(6, 6);
+      else if (flavour == 54 && warps == 4) LAUNCH5(4, 4);
+      else if (flavour == 58 && warps == 4) LAUNCH5(4, 8);
+      else if (flavour >= 50) { printf("no such variant\n"); return 0.f; }
+      else if (flavour == 3 && warps == 8) LAUNCH3(8);
+      else if (flavour == 3 && warps == 4) LAUNCH3(4);
+      else if (flavour == 3) LAUNCH3(6);
+      else if (warps == 8 && flavour == 0) LAUNCH(8, 0);
       else if (warps == 8) LAUNCH(8, 1);
       else if (warps == 4 && flavour == 0) LAUNCH(4, 0);
       else if (warps == 4) LAUNCH(4, 1);
@@ -207,7 +478,22 @@ int main(int argc, char** argv) {
     return best;
   };
   if (argc > 5) run(atoi(argv[5]), atoi(argv[4]), atoi(argv[3]));
-  else for (int flavour : {0, 1}) for (int warps : {4, 8}) for (int splits : {148, 296}) run(splits, warps, flavour);
+  else { run(148, 8, 54); run(148, 8, 3); }
+  {
+    uint32_t* d_sink; CK(cudaMalloc(&d_sink, 4));
+    for (int rowb : {256, 128}) for (int threads : {256, 512, 1024}) {
+      float best = 1e9f;
+      for (int it = 0; it < 3; ++it) {
+        cudaEventRecord(e0);
+        if (rowb == 256) fetch_only_kernel<256><<<batches * 148, threads>>>(d_desc4, N, G, d_tables2, 148, d_sink);
+        else fetch_only_kernel<128><<<batches * 148, threads>>>(d_desc4, N, G, d_tables2, 148, d_sink);
+        cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+        float ms; cudaEventElapsedTime(&ms, e0, e1); best = std::min(best, ms);
+      }
+      CK(cudaGetLastError());
+      printf("fetch-only rows of %d B, %4d threads/SM: %.3f ms -> %.1f GB/s of rows\n", rowb, threads, best, (double)N * batches * NV * rowb / best / 1e6);
+    }
+  }
   // check a few cells against a direct host computation
   std::vector<unsigned long long> out((size_t)NA * NB * batches * 32);
   CK(cudaMemcpy(out.data(), d_out, out.size() * 8, cudaMemcpyDeviceToHost));
@@ -228,6 +514,14 @@ int main(int argc, char** argv) {
       const long long got = (long long)out[((size_t)(a * NB + c) * batches + r / 32) * 32 + (r & 31)];
       if (got != t) { ++bad; printf("MISMATCH r=%d a=%d c=%d got=%lld want=%lld (Nr=%lld)\n", r, a, c, got, t, Nr); }
     }
+  }
+  {
+    std::vector<double> outd((size_t)NA * NB * batches * 32);
+    CK(cudaMemcpy(outd.data(), d_outd, outd.size() * 8, cudaMemcpyDeviceToHost));
+    int bad5 = 0;
+    for (size_t i = 0; i < outd.size(); ++i) if ((long long)outd[i] != (long long)out[i]) { if (++bad5 < 5) printf("v5 mismatch at %zu: %.1f vs %lld\n", i, outd[i], (long long)out[i]); }
+    printf("v5 vs integer result: %d mismatches of %zu\n", bad5, outd.size());
+    bad += bad5 != 0;
   }
   printf(bad ? "FAILED\n" : "check ok\n");
   return bad != 0;

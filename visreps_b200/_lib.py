@@ -32,6 +32,10 @@ SIGNATURES = {
     "vr_profile_stop": (_i, [_vp, _vp, _vp]),
     "vr_rdm_workspace_bytes": (_sz, [_i, _i64]),
     "vr_rdm_pearson_f32": (_i, [_vp, _i, _i64, _i64, _f, _vp, _vp, _vp, _sz, _vp]),
+    "vr_rdm_moments_f32": (_i, [_vp, _i, _i64, _i64, _vp, _vp, _vp]),
+    "vr_rdm_shift_from_moments": (_i, [_vp, _i, _i64, _vp, _vp]),
+    "vr_rdm_gram_f32": (_i, [_vp, _i, _i64, _i64, _vp, _vp, _i64, _vp, _sz, _vp]),
+    "vr_rdm_finish_f32": (_i, [_vp, _i64, _i, _i64, _vp, _vp, _vp, _f, _vp, _vp, _vp]),
     "vr_rank_rows_workspace_bytes": (_sz, [_i, _i64]),
     "vr_rank_rows_ordinal_f32": (_i, [_vp, _i, _i64, _i64, _vp, _vp, _sz, _vp]),
     "vr_presort_bytes": (_sz, [_i]),
@@ -53,6 +57,11 @@ SIGNATURES = {
     "vr_rank_fuse_max": (_i, []),
     "vr_rank_materialise": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "vr_rank_fused": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _i64, _i64, _vp, _sz, _vp]),
+    "vr_spearman_job_bytes": (_sz, [_i, _i, _i]),
+    "vr_spearman_job_init": (_i, [_vp, _i, _i, _i, _vp, _sz, _vp]),
+    "vr_spearman_job_add": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _vp]),
+    "vr_spearman_sweep_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "vr_spearman_job_sweep": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _i64, _i64, _vp, _sz, _vp]),
     "vr_bootstrap_spearman_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "vr_bootstrap_spearman": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _vp, _vp, _sz, _vp]),
     "vr_bootstrap_column_corr_workspace_bytes": (_sz, [_i, _i, _i]),

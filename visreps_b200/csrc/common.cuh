@@ -16,6 +16,8 @@ void count_launch(unsigned n = 1);
 // Tuning options (vr_set_option; initial values from VR_SYRK_PAIR / VR_SYRK_WAVES, for A/B measurements and tests).
 int option_syrk_pair();
 int option_syrk_waves();
+int option_sweep_tile_a();   // vectors per side in one Spearman sweep launch (1..8)
+int option_sweep_tile_b();
 
 // ---- built-in stage profiler (CUDA events on the launching stream) ---------------------
 // Off by default.  Between vr_profile_start() and vr_profile_stop() every ProfScope records a

@@ -150,7 +150,8 @@ runs_kernel(uint32_t N, uint32_t G, uint32_t n, const __grid_constant__ PresortB
   if (run_compact(N)) {
     const uint32_t gs = s >> 5, ls = s & 31u, ge = e >> 5, le = e & 31u;
     const uint32_t head = (gs << 3) | ((32u - ls) << kRunShloShift);
-    if (ge == gs) word = head | ((32u - le) << kRunSheShift);                       // le > ls: she in 1..31
+    if (e == s + 1u) word = head | 1u | (le ? (32u - le) << kRunSheShift : 0u);     // bit 0: a run of one (sweep.cu); she as below
+    else if (ge == gs) word = head | ((32u - le) << kRunSheShift);                  // le > ls: she in 1..31
     else if (ge == gs + 1u && le == 0u) word = head;                                // she = 0: the whole group
     else if (ge == gs + 1u) word = head | kRunCrossBit | ((32u - le) << kRunSheShift);
     else word = (gs << 3) | ((ls + 1u) << kRunSheShift);                            // shlo = 0: long run

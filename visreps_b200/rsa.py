@@ -259,6 +259,86 @@ def _ptr_array(tensors: Sequence[torch.Tensor]):
     return arr
 
 
+def _int_array(values: Sequence[int]):
+    arr = (C.c_int * len(values))()
+    for k, v in enumerate(values):
+        arr[k] = int(v)
+    return arr
+
+
+import os as _os
+
+# "sweep": one warp per (canonical pair, 32 replicates), csrc/sweep.cu (default).  "legacy": one CTA per (RDM, replicate) with
+# the count table in shared memory, csrc/rank.cu -- kept for A/B measurements (VR_SPEARMAN_ENGINE=legacy).
+SPEARMAN_ENGINE = _os.environ.get("VR_SPEARMAN_ENGINE", "sweep")
+
+
+# Host inputs at a size whose count table fits shared memory (n <= 1277) stay on the legacy kernels: what is exposed after
+# the last host->device copy is then one matrix ranked against the materialised side (3 ms at the NSD shape, HBM streaming),
+# where a sweep of one matrix against eight costs 4 ms of table-row traffic.  Everything else takes the sweep.
+_LEGACY_SMEM_TABLE_MAX_N = 1277
+
+
+class SpearmanJob:
+    """Count tables of up to `slots` presorted RDMs for one set of masks (library-opaque device buffer), and the grouped
+    Spearman sweep over them.  RDMs can be added as they become available; every (A, B) pair of a sweep shares the lookups."""
+
+    def __init__(self, masks: torch.Tensor, n: int, slots: int):
+        lib = _lib.load()
+        self.n, self.R, self.slots, self.masks = int(n), int(masks.shape[0]), int(slots), masks
+        self.buf = torch.empty(lib.vr_spearman_job_bytes(self.n, self.slots, self.R), dtype=torch.uint8, device=masks.device)
+        self.items: List[Optional[PresortedRDM]] = [None] * self.slots
+        _lib.check(lib.vr_spearman_job_init(masks.data_ptr(), self.n, self.R, self.slots, self.buf.data_ptr(), self.buf.numel(),
+                                            _lib.stream_ptr()), "vr_spearman_job_init")
+
+    @staticmethod
+    def bytes_needed(n: int, slots: int, R: int) -> int:
+        return int(_lib.load().vr_spearman_job_bytes(int(n), int(slots), int(R)))
+
+    def add(self, items: Sequence[PresortedRDM], slot0: int) -> None:
+        lib = _lib.load()
+        if any(p.n != self.n for p in items):
+            raise ValueError("RDMs must share the same 2-D shape")
+        _lib.check(lib.vr_spearman_job_add(self.buf.data_ptr(), self.n, self.R, self.slots, _ptr_array([p.blob for p in items]),
+                                           len(items), int(slot0), _lib.stream_ptr()), "vr_spearman_job_add")
+        for k, p in enumerate(items):
+            self.items[slot0 + k] = p
+
+    def sweep(self, slots_a: Sequence[int], slots_b: Sequence[int], out: torch.Tensor, offset: int, stride_a: int, stride_b: int) -> None:
+        """rho of every (a, b, replicate) into the flat fp64 tensor `out` at offset + ia * stride_a + ib * stride_b + r."""
+        lib = _lib.load()
+        dev = self.buf.device
+        ws = _lib.workspace(lib.vr_spearman_sweep_workspace_bytes(self.n, len(slots_a), len(slots_b), self.R), dev, "sweep")
+        _lib.check(lib.vr_spearman_job_sweep(self.buf.data_ptr(), self.n, self.R, self.slots,
+                                             _ptr_array([self.items[k].blob for k in slots_a]), _int_array(slots_a), len(slots_a),
+                                             _ptr_array([self.items[k].blob for k in slots_b]), _int_array(slots_b), len(slots_b),
+                                             out.data_ptr() + 8 * int(offset), int(stride_a), int(stride_b), ws.data_ptr(), ws.numel(),
+                                             _lib.stream_ptr()), "vr_spearman_job_sweep")
+
+
+def _spearman_sweep_grouped(model: Sequence[PresortedRDM], neural: Sequence[PresortedRDM], masks: torch.Tensor, out: torch.Tensor) -> None:
+    """out (nA, nB, R) fp64 <- Spearman of every model x neural x mask, replicates chunked to the memory at hand."""
+    n = model[0].n
+    nA, nB, R = len(model), len(neural), int(masks.shape[0])
+    dev = masks.device
+    free, _total = torch.cuda.mem_get_info(dev)
+    cached = torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
+    budget = max(int(0.5 * (free + cached)), 1 << 28)
+    per_batch = max(1, SpearmanJob.bytes_needed(n, nA + nB, 64) - SpearmanJob.bytes_needed(n, nA + nB, 32))
+    chunk = max(32, min((R + 31) // 32 * 32, budget // per_batch * 32))
+    flat = out.view(-1)
+    for r0 in range(0, R, chunk):
+        rc = min(chunk, R - r0)
+        job = SpearmanJob(masks[r0:r0 + rc], n, nA + nB)
+        job.add(list(model) + list(neural), 0)
+        if rc == R:
+            job.sweep(range(nA), range(nA, nA + nB), flat, 0, nB * R, R)
+        else:
+            part = torch.empty((nA, nB, rc), dtype=torch.float64, device=dev)
+            job.sweep(range(nA), range(nA, nA + nB), part.view(-1), 0, nB * rc, rc)
+            out[:, :, r0:r0 + rc] = part
+
+
 def compare_grouped(model: Sequence[PresortedRDM], neural: Sequence[PresortedRDM], method: str,
                     masks: torch.Tensor) -> torch.Tensor:
     """(nA, nB, R) fp64 device tensor: every model RDM x every neural RDM x every mask."""
@@ -286,6 +366,8 @@ def compare_grouped(model: Sequence[PresortedRDM], neural: Sequence[PresortedRDM
                         _lib.check(lib.vr_kendall_tau_a(ra.data_ptr(), rb.data_ptr(), n, n, masks.data_ptr(), R,
                                                         part[ia, ib].data_ptr(), ws.data_ptr(), ws.numel(),
                                                         _lib.stream_ptr()), "vr_kendall_tau_a")
+            elif method == "spearman" and SPEARMAN_ENGINE == "sweep":
+                _spearman_sweep_grouped(ma, mb, masks, part)
             elif method == "spearman":
                 pa, pb = _ptr_array([p.blob for p in ma]), _ptr_array([p.blob for p in mb])
                 ws = _lib.workspace(lib.vr_bootstrap_spearman_workspace_bytes(n, len(ma), len(mb), R), dev)
@@ -749,8 +831,55 @@ def _spearman_pipeline(inputs_a: Sequence[torch.Tensor], inputs_b: Sequence[torc
     _mark("drawn")
     masks = build_masks(index_sets, n, dev, with_full=True)
     R = int(masks.shape[0])
-    ctx = RankContext(masks, n)
     out = torch.empty((nA, nB, R), dtype=torch.float64, device=dev)
+    if SPEARMAN_ENGINE == "sweep" and (fus_on_device or n > _LEGACY_SMEM_TABLE_MAX_N):
+        # One job holds the count tables of every RDM; the materialised side's tables are built first, every other
+        # matrix is added and swept against them as soon as its copy has landed (its lookups are shared by all pairs
+        # of the sweep), so only the last matrix's RDM + tables + sweep are exposed after the final copy.
+        job = SpearmanJob(masks, n, nA + nB)
+        n_m = len(m_items)
+        m_slots = list(range(n_m))
+        job.add(m_items, 0)
+        _mark("tables of the materialised side")
+        flat = out.view(-1)
+
+        def sweep_fused(ks):                              # fused matrices ks (consecutive slots) x all materialised ones
+            f_slots = [n_m + k for k in ks]
+            if mat_is_a:
+                job.sweep(m_slots, f_slots, flat, ks[0] * R, nB * R, R)
+            else:
+                job.sweep(f_slots, m_slots, flat, ks[0] * nB * R, nB * R, R)
+
+        def add_and_sweep(ks):
+            ks = sorted(ks)
+            runs, cur = [], [ks[0]]
+            for k in ks[1:]:
+                if k == cur[-1] + 1 and len(cur) < 8:
+                    cur.append(k)
+                else:
+                    runs.append(cur)
+                    cur = [k]
+            runs.append(cur)
+            for run in runs:                               # consecutive slots: one table build, one sweep
+                job.add([f_items[k] for k in run], n_m + run[0])
+                sweep_fused(run)
+
+        if fus_on_device:
+            add_and_sweep(list(range(len(fus))))
+        else:
+            ready = [k for k in order if k in f_items]
+            if ready:
+                add_and_sweep(ready)
+                _mark(f"swept batch {sorted(ready)}")
+            for k in order:
+                if k in f_items:
+                    continue
+                f_items[k] = PresortedRDM(rdm_of(staged_f[k], slot_f(k)))
+                add_and_sweep([k])
+                _mark(f"swept {k}")
+        _mark("done")
+        return out, flags
+    ctx = RankContext(masks, n)
     _mark("context")
 
     # materialised side
@@ -886,6 +1015,14 @@ def _pipeline_fits(n: int, nA: int, nB: int, R: int, dev: torch.device) -> bool:
     """The pipelined path keeps all R replicates of the materialised side resident; fall back to the
     replicate-chunked one-call path when that would not fit comfortably."""
     lib = _lib.load()
+    if SPEARMAN_ENGINE == "sweep":
+        key = ("sweep", n, nA, nB, R, dev.index)
+        hit = _fit_cache.get(key)
+        if hit is None:
+            free, _total = torch.cuda.mem_get_info(dev)
+            cached = torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
+            hit = _fit_cache[key] = SpearmanJob.bytes_needed(n, nA + nB, R) < 0.5 * (free + cached)
+        return hit
     n_mat = min(nA, nB)
     # vr_rank_fused addresses a materialised group (<= vr_rank_fuse_max() vectors x R replicates) with 32-bit int4
     # offsets: 2^34 elements.  Beyond that the one-call path chunks the replicates itself.
