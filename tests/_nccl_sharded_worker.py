@@ -37,6 +37,16 @@ def main():
         got3 = vdist.rsa_grouped_sharded(feats, neur, "pearson", n_bootstrap=B, seed=42)
         want3 = vb.rsa_grouped(feats, neur, "pearson", bootstrap=True, n_bootstrap=B, seed=42)
         assert np.array_equal(got3["scores"], want3["scores"])
+        # K-split RDM: every rank runs the SYRK on its column shard, Grams reduced over NCCL before the epilogue
+        from oracle import rsa_oracle as orc
+        for (nk, dk, seed) in ((130, 700, 1), (500, 40000, 2)):
+            rk = np.random.RandomState(seed)
+            xk = torch.from_numpy(np.maximum(rk.standard_normal((nk, dk)).astype(np.float32) + 3.0 * rk.rand(nk, 1).astype(np.float32), 0))
+            got_k = vdist.compute_rdm_sharded(xk.to(dev))
+            one = vb.compute_rdm(xk.to(dev))
+            assert torch.equal(got_k, got_k.T) and float(got_k.diagonal().abs().max()) == 0.0
+            assert float((got_k - one).abs().max()) <= 1e-5, float((got_k - one).abs().max())
+            assert float(np.abs(got_k.cpu().numpy().astype(np.float64) - orc.rdm_truth_f64(xk)).max()) <= 1e-5
         dist.barrier()
         if rank == 0:
             print(f"nccl sharded build ok: world={world}", flush=True)

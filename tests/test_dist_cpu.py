@@ -73,3 +73,62 @@ def test_sharded_bootstrap_over_gloo_matches_single_process(world, total, tmp_pa
     want = _fake_compute(feats, [torch.zeros(40, 2)], "spearman", True, total, 42, (0, total))["scores"]
     np.testing.assert_array_equal(got[:want.size], want.ravel())
     np.testing.assert_array_equal(got[want.size:], np.tile(np.arange(total, dtype=np.float64), 2))
+
+
+def _np_stages():
+    """CPU stand-ins with the arithmetic of the device stages (fp64 moments; fp32-shifted Gram; rsa.py:80-92 epilogue)."""
+    def moments(x):
+        xd = x.double()
+        return torch.stack([xd.sum(1), (xd * xd).sum(1)])
+
+    def gram(x, sums, d_total):
+        shift = (sums[0] / d_total).float()
+        z = x.double() - shift.double()[:, None]
+        return torch.triu(z @ z.T).float(), shift
+
+    def finish(g, sums, shift, d_total, correction):
+        mean = sums[0] / d_total
+        delta = mean - shift.double()
+        var = (sums[1] / d_total - mean * mean).clamp_(min=0)
+        sd = (var + correction).sqrt().float()
+        sd[sd < correction * 10] = 1.0
+        full = torch.triu(g.double()) + torch.triu(g.double(), 1).T
+        cov = (full / d_total - delta[:, None] * delta[None, :]).float()
+        corr = (cov / (sd[:, None] * sd[None, :] + correction)).clamp_(-1, 1)
+        rdm = 1.0 - corr
+        rdm.fill_diagonal_(0.0)
+        return rdm, None
+
+    return moments, gram, finish
+
+
+def _ksplit_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rs = np.random.RandomState(3)
+        x = torch.from_numpy(np.maximum(rs.standard_normal((50, 301)) + 2.0 * rs.rand(50, 1), 0).astype(np.float32))
+        lo, hi = vdist.column_shard(301, rank, world)
+        rdm = vdist.compute_rdm_ksplit(x[:, lo:hi], stages=_np_stages())          # d_total found by an all-reduce
+        rdm2 = vdist.compute_rdm_ksplit(x[:, lo:hi], d_total=301, stages=_np_stages())
+        assert torch.equal(rdm, rdm2)
+        if rank == 0:
+            np.save(out, rdm.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_ksplit_rdm_orchestration_over_gloo(world, tmp_path):
+    """Moments all-reduce -> shared shift -> Gram all-reduce BEFORE the epilogue -> same RDM as the unsplit formula."""
+    from oracle import rsa_oracle as orc
+    spans = [vdist.column_shard(301, r, world) for r in range(world)]
+    assert spans[0][0] == 0 and spans[-1][1] == 301 and all(spans[k][1] == spans[k + 1][0] for k in range(world - 1))
+    assert all(lo % 32 == 0 for lo, _ in spans)
+    out = str(tmp_path / "rdm.npy")
+    mp.spawn(_ksplit_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    rs = np.random.RandomState(3)
+    x = torch.from_numpy(np.maximum(rs.standard_normal((50, 301)) + 2.0 * rs.rand(50, 1), 0).astype(np.float32))
+    got = np.load(out)
+    assert float(np.abs(got - orc.rdm_truth_f64(x)).max()) <= 1e-6
+    assert float(np.abs(got - orc.rdm(x).numpy()).max()) <= 1e-5
