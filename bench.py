@@ -339,56 +339,66 @@ def run_ours(args):
     m = int(n * 0.9)
     N_sub = m * (m - 1) // 2
     roofline = None
-    if dom in ("rank", "rank_fused", "kept", "dot"):
-        # one launch of this family ranks (or counts, or reads) a set of vectors for all B+1 masks
-        fused = prof["rank_fused"]["scopes"] > 0
-        vectors = {"rank": min(nA, nB, 8) if fused else nA + nB, "rank_fused": max(nA, nB), "kept": nA + nB, "dot": nA + nB}[dom]
+    if dom in ("rank", "rank_fused", "kept"):
+        from visreps_b200 import rsa as vrsa_
+        sweep = vrsa_.SPEARMAN_ENGINE == "sweep"
+        G = (N + 31) // 32
+        batches = (B + 1 + 31) // 32
         per_launch_ms = prof[dom]["ms"] / max(1, prof[dom]["scopes"])
-        rankings_per_launch = vectors * (B + 1)
         scopes_per_step = max(1.0, prof[dom]["scopes"] / args.steps)
-        if dom == "rank_fused":
-            # SURVEY.md section 8d unit: 8*N_sub bytes per replicate comparison; the fused launch is the one that
-            # finishes comparisons: nA*nB*(B+1) per step
-            units_per_launch = nA * nB * (B + 1) / scopes_per_step
-            alg_bytes = units_per_launch * 8.0 * N_sub
-            definition = ("SURVEY 8d: 8*N_sub bytes per replicate comparison x the nA*nB*(B+1) comparisons one fused launch "
-                          "finishes, / the launch's CUDA-event time")
+        if sweep and dom == "rank_fused":
+            kernel = f"sweep_kernel<{min(nA, 8)}, {min(nB, 8)}, compact>"
+            # what ONE launch must read at least once: the count-table rows of its vectors ({kept word, count} per 32 sorted
+            # positions, replicate and vector: 8 B each), their run words and the transposed masks; it writes (nA nB splits 32) sums
+            compulsory = (nA + nB) * batches * (G + 1) * 256.0 + (nA + nB) * 4.0 * N + batches * n * 4.0
+            rows_fetched = (nA + nB) * batches * float(N) * 256.0           # one 256-byte row per (pair, vector, batch): L2 -> SM
+            what = ("compulsory bytes = the count-table rows + run words + masks the launch reads at least once from HBM; "
+                    "the rows are then fetched from L2 once per (canonical pair, vector, 32-replicate batch)")
         else:
-            # a launch that only ranks (or counts) finishes no comparison: half the 8d unit per ranked vector
-            units_per_launch = rankings_per_launch
-            alg_bytes = rankings_per_launch * 4.0 * N_sub
-            definition = "4*N_sub bytes per ranked vector (half of SURVEY 8d's 8*N_sub per replicate comparison) x vectors*(B+1) per launch"
-        achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
-        per_vector = rankings_per_launch * 4.0 * N_sub / (per_launch_ms * 1e-3) / 1e9
-        roofline = {"kernel": {"rank": "rank_kernel<materialise>", "rank_fused": "rank_kernel<fused dot>", "kept": "count_kernel", "dot": "dot_kernel"}[dom],
-                    "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": alg_bytes, "units_per_launch": units_per_launch, "ms_per_launch": per_launch_ms,
-                    "definition": definition,
-                    "per_ranked_vector_GBps": per_vector,
-                    "note": "frac > 1 is work sharing, not a faster-than-HBM kernel: every (layer, ROI) pair of a job sees the same index sets "
-                            "(evals.py:356), so one launch finishes nA*nB*(B+1) comparisons from (nA+nB)*(B+1) rankings and reads the materialised "
-                            "side once through L2 (`traffic` is far below the algorithmic bytes). Counting only the vectors this launch ranks "
-                            f"(4*N_sub each) gives {per_vector:.0f} GB/s = {per_vector / hbm_peak:.2f} of peak. ncu (profiles/r1_rank_kernels_nsd_full.txt): "
-                            "the binding resources are the L1/shared-memory data pipe (66 % of peak: random 8-byte count-table lookups plus the "
-                            "materialised streams) and instruction issue (62 %); DRAM runs at 20 % -- the kernel is not HBM bound."}
+            fused = prof["rank_fused"]["scopes"] > 0
+            vectors = {"rank": min(nA, nB, 8) if fused else nA + nB, "rank_fused": max(nA, nB), "kept": nA + nB}[dom]
+            kernel = {"rank": "rank_kernel<materialise>", "rank_fused": "rank_kernel<fused dot>", "kept": "count kernels"}[dom]
+            stride = (N + 31) // 32 * 32
+            if dom == "rank":
+                compulsory = vectors * (B + 1) * stride * 4.0          # the materialised dev vectors it writes
+            elif dom == "rank_fused":
+                compulsory = min(nA, nB, 8) * (B + 1) * stride * 4.0    # the materialised side, read once through L2
+            else:
+                compulsory = vectors * batches * (G + 1) * 256.0
+            rows_fetched = None
+            what = "compulsory bytes = the materialised centred-rank vectors (or count tables) the launch writes / reads once"
+        achieved = compulsory / (per_launch_ms * 1e-3) / 1e9
+        comparisons_per_launch = nA * nB * (B + 1) / scopes_per_step if dom == "rank_fused" else 0
+        roofline = {"kernel": kernel, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                    "traffic": None, "peak_source": peak_src, "compulsory_bytes_per_launch": compulsory, "ms_per_launch": per_launch_ms,
+                    "launches_per_step": scopes_per_step, "definition": what + "; achieved = compulsory bytes / CUDA-event time of the launch",
+                    "work_sharing_equivalent_GBps": comparisons_per_launch * 8.0 * N_sub / (per_launch_ms * 1e-3) / 1e9 if comparisons_per_launch else None,
+                    "work_sharing_equivalent_definition": "SURVEY 8d's 8*N_sub bytes per replicate comparison x the comparisons one launch finishes; NOT a "
+                                                          "roofline fraction: nA*nB*(B+1) comparisons come from (nA+nB)*(B+1) rankings (evals.py:356)"}
+        if rows_fetched:
+            roofline["l2_row_GBps"] = rows_fetched / (per_launch_ms * 1e-3) / 1e9
+            roofline["note"] = ("the sweep is not HBM bound: its table rows are L2 resident (one 64 MB batch block in flight, ncu lts hit rate 83 %, "
+                                "5.7 GB of DRAM reads per launch); the binding resources are instruction issue with two warps per scheduler "
+                                "(64 fp64 accumulators per lane = 255 registers) and the ~900-cycle L2 row latency "
+                                "(profiles/r2_sweep_kernels_nsd_full.txt)")
         try:   # DRAM bytes per launch of this kernel from the committed ncu capture, if it is for this workload
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
             wl = tr.get("workload", {})
-            if (wl.get("n"), wl.get("nA"), wl.get("nB"), wl.get("masks")) == (n, nA, nB, B + 1) and roofline["kernel"] in tr:
-                roofline["traffic"] = tr[roofline["kernel"]]["dram_bytes_per_launch"]
-                roofline["traffic_source"] = "ncu --set full, profiles/r1_rank_kernels_nsd_full.txt"
+            key = "sweep_kernel" if sweep and dom == "rank_fused" else roofline["kernel"]
+            if (wl.get("n"), wl.get("nA"), wl.get("nB"), wl.get("masks")) == (n, nA, nB, B + 1) and key in tr:
+                roofline["traffic"] = tr[key]["dram_bytes_per_launch"]
+                roofline["traffic_source"] = tr[key].get("source", "ncu --set full")
         except Exception:
             pass
         if roofline["traffic"]:
             roofline["dram_GBps"] = roofline["traffic"] / (per_launch_ms * 1e-3) / 1e9
             roofline["dram_frac"] = roofline["dram_GBps"] / hbm_peak
-    elif dom == "rdm_syrk":
+    elif dom in ("rdm_syrk", "rdm_syrk_pair"):
         flops = flops_step
-        tf_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-        ach = flops * args.steps / (prof[dom]["ms"] * 1e-3) / 1e12
+        tf_peak = tf32_peak_info["burst_tflops"] if tf32_peak_info else float(peaks.get("bf16_tflops", 1599.5)) / 2.0
+        ach = 3.0 * flops * args.steps / ((prof["rdm_syrk"]["ms"] + prof["rdm_syrk_pair"]["ms"]) * 1e-3) / 1e12
         roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
-                    "traffic": None, "peak_source": "measured bf16_tflops_sustained"}
+                    "traffic": None, "peak_source": "TF32 dense peak measured in this run" if tf32_peak_info else "bf16 peak / 2"}
     # second roofline object: the tensor-core SYRK family (all RDM builds of the step), useful TF32 work
     roofline_syrk = None
     syrk_ms = prof.get("rdm_syrk", {}).get("ms", 0) + prof.get("rdm_syrk_pair", {}).get("ms", 0)

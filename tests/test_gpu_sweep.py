@@ -142,3 +142,33 @@ def test_sweep_job_is_incremental(dev):
     assert torch.equal(out, want)
     with pytest.raises(ValueError):
         job.add([vrsa.PresortedRDM(vb.compute_rdm(torch.randn(n + 1, 8, device=dev)))], 0)
+
+
+def test_nan_entries_make_only_the_replicates_that_keep_them_nan(dev):
+    """rsa.py:123-125: a replicate is NaN when ITS sub-RDM holds a NaN; replicates that drop the offending stimulus are
+    finite and equal the oracle.  Same rule in both Spearman engines; +NaN and -NaN entries (sorted to opposite ends)."""
+    x, y = cases.pair_inputs("p64")
+    n = x.shape[0]
+    a, b = orc.rdm(x), orc.rdm(y)
+    bad = a.clone()
+    bad[5, :] = float("nan"); bad[:, 5] = float("nan"); bad[5, 5] = 0.0          # stimulus 5 is NaN everywhere
+    neg = torch.tensor(float("nan")).view(torch.int32).bitwise_or(torch.tensor(-2**31, dtype=torch.int32)).view(torch.float32)
+    bad[9, 20] = neg; bad[20, 9] = neg                                          # one -NaN pair (stimuli 9 and 20)
+    idx = orc.draw_subsamples(n, 60, 42)
+    masks = vrsa.build_masks(idx, n, dev, with_full=True)
+    A = vrsa.PresortedRDM.batch([bad.to(dev), a.to(dev)])
+    B = vrsa.PresortedRDM.batch([b.to(dev)])
+    sweep, legacy = _both_engines(A, B, masks)
+    assert np.array_equal(sweep, legacy, equal_nan=True)
+    assert np.isnan(sweep[0, 0, 0]) and np.isfinite(sweep[1, 0]).all()
+    n_clean = 0
+    for r in range(60):
+        kept = set(idx[r].tolist())
+        dirty = 5 in kept or (9 in kept and 20 in kept)
+        assert np.isnan(sweep[0, 0, r + 1]) == dirty, r
+        if not dirty:
+            n_clean += 1
+            sub = torch.from_numpy(idx[r].astype(np.int64))
+            want = orc.rdm_compare(bad[sub][:, sub], b[sub][:, sub], correlation="Spearman")
+            assert abs(sweep[0, 0, r + 1] - want) <= 1e-9
+    assert n_clean >= 1

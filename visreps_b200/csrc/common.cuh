@@ -126,7 +126,17 @@ struct PresortHeader {
   uint32_t G;        // ceil(N/32)
   uint32_t has_nan;  // written on the device
   uint32_t n_runs;   // number of distinct values (device)
+  uint32_t nan_lo;   // NaNs with the sign bit set: they sort to positions [0, nan_lo)            (device)
+  uint32_t nan_hi;   // NaNs without it: positions [N - nan_hi, N).  A replicate's scores are NaN only if it KEEPS one of them
 };
+// Kept entries among the NaN positions of a presorted vector, given C(x) = kept entries at sorted positions < x.
+template <typename CountBefore>
+__host__ __device__ inline uint32_t kept_nans(const PresortHeader* hdr, uint32_t N, uint32_t n_kept, CountBefore count_before) {
+  uint32_t k = 0;
+  if (hdr->nan_lo) k += count_before(hdr->nan_lo);
+  if (hdr->nan_hi) k += n_kept - count_before(N - hdr->nan_hi);
+  return k;
+}
 constexpr uint32_t kPresortMagic = 0x56525053u;  // 'VRPS'
 struct PresortView {
   PresortHeader* hdr;

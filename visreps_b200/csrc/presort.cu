@@ -32,7 +32,10 @@ triu_keys_kernel(const __grid_constant__ PresortBatch batch, int n, int64_t ld, 
   }
   if (j >= (uint32_t)n || j <= i) return;
   const float v = batch.rdm[b][(int64_t)i * ld + j];
-  if (v != v) atomicOr(&hdr->has_nan, 1u);
+  if (v != v) {
+    atomicOr(&hdr->has_nan, 1u);
+    atomicAdd((__float_as_uint(v) & 0x80000000u) ? &hdr->nan_lo : &hdr->nan_hi, 1u);
+  }
   const uint32_t p = triu_pos(i, j, (uint32_t)n);
   keys[(int64_t)b * seg_stride + p] = float_key(v);
   vals[(int64_t)b * seg_stride + p] = pack_pair(i, j);
@@ -45,6 +48,8 @@ __global__ void clear_headers_kernel(const __grid_constant__ PresortBatch batch,
     PresortHeader* hdr = reinterpret_cast<PresortHeader*>(batch.blob[b]);
     hdr->has_nan = 0;
     hdr->n_runs = 0;
+    hdr->nan_lo = 0;
+    hdr->nan_hi = 0;
   }
 }
 

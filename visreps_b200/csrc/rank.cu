@@ -507,7 +507,9 @@ rank_kernel(const __grid_constant__ RankArgs A) {
       const double nan = __longlong_as_double(0x7ff8000000000000LL);
       if (kUntied)                   // ranks are a permutation of 1..N_r: sum of (2 rank - N_r - 1)^2, exact in int64
         ss_item = (double)(((unsigned long long)Ns - 1ull) * Ns * ((unsigned long long)Ns + 1ull) / 3ull);   // < 2^64 for N_r < 2.6e6
-      if (blob.hdr->has_nan) ss_item = nan;
+      if (blob.hdr->has_nan &&                         // NaN only for a replicate that keeps a NaN entry (rsa.py:123-125)
+          kept_nans(blob.hdr, N, Ns, [&](uint32_t x) { const uint2 t = table[x >> 5]; return t.y + __popc(t.x & low_mask(x & 31u)); }) != 0u)
+        ss_item = nan;
       if (!kFused) {
         if (slot == kFuseMax) {
           A.ss[(int64_t)v * R + r] = ss_item;
@@ -549,7 +551,10 @@ rank_finalize_kernel(const __grid_constant__ RankArgs A) {
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
   if (run_compact(N) && hdr->n_runs == N)      // tie-free vector: the sweep did not accumulate squares (closed form)
     ss_item = (double)(((unsigned long long)Ns - 1ull) * Ns * ((unsigned long long)Ns + 1ull) / 3ull);
-  if (hdr->has_nan) ss_item = nan;
+  if (hdr->has_nan) {
+    const uint2* __restrict__ tab = A.tables + (int64_t)(A.table_base + v) * table_vector_stride(A.R, A.Gs) + (int64_t)r * A.Gs;   // finished in place
+    if (kept_nans(hdr, N, Ns, [&](uint32_t x) { const uint2 t = tab[x >> 5]; return t.y + __popc(t.x & low_mask(x & 31u)); }) != 0u) ss_item = nan;
+  }
   if (!kFused) {
     if (slot == kFuseMax) {
       A.ss[(int64_t)v * A.R + r] = ss_item;

@@ -566,6 +566,9 @@ struct FinalizeArgs {
   int64_t strideA, strideB;
   int exact;
   int validA, validB;              // vectors that are not padding aliases
+  const uint2* rows;               // job rows (per-replicate NaN test)
+  int slots;
+  uint32_t Gs, N;
 };
 __global__ void __launch_bounds__(32)
 sweep_finalize_kernel(const __grid_constant__ FinalizeArgs F) {
@@ -594,7 +597,15 @@ sweep_finalize_kernel(const __grid_constant__ FinalizeArgs F) {
     } else {
       ss = (nr * nr * nr - nr - __longlong_as_double(tie)) / 3.0;
     }
-    if (static_cast<const PresortHeader*>(blob)->has_nan) ss = nan;
+    const PresortHeader* hdr = static_cast<const PresortHeader*>(blob);
+    if (hdr->has_nan) {                              // NaN only for a replicate that keeps a NaN entry (rsa.py:123-125)
+      const uint2* rows = F.rows + ((size_t)b * F.slots + slot) * F.Gs * 32;
+      const uint32_t n_kept = F.nk[r];
+      const uint32_t kn = kept_nans(hdr, F.N, n_kept, [&](uint32_t x) {
+        const uint2 e = rows[(size_t)(x >> 5) * 32 + lane];
+        return ((e.y - kDevBias + n_kept) >> 1) + (uint32_t)__popc(e.x & ((1u << (x & 31u)) - 1u)); });
+      if (kn != 0u) ss = nan;
+    }
     return ss;
   };
   const double ssa = ss_of(F.slotA[a], F.blobA[a]), ssc = ss_of(F.slotB[c], F.blobB[c]);
@@ -774,7 +785,7 @@ extern "C" int vr_spearman_job_sweep(void* job, int n, int R, int slots, const v
       if (rc != VR_OK) return rc;
       fin.partial = static_cast<const unsigned long long*>(ws); fin.splits = splits; fin.nA = pa; fin.nB = pb; fin.R = R; fin.batches = J.batches; fin.nk = J.nk; fin.tie = J.tie;
       fin.out = out + (int64_t)a0 * strideA + (int64_t)b0 * strideB; fin.strideA = strideA; fin.strideB = strideB; fin.exact = exact ? 1 : 0;
-      fin.validA = na; fin.validB = nb;
+      fin.validA = na; fin.validB = nb; fin.rows = J.rows; fin.slots = J.slots; fin.Gs = J.Gs; fin.N = J.N;
       sweep_finalize_kernel<<<dim3(J.batches, pa * pb), 32, 0, stream>>>(fin);
       VR_CHECK_LAUNCH();
     }
