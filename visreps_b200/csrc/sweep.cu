@@ -385,6 +385,11 @@ template <int NVEC> struct SweepSmem {
   static constexpr size_t kWarpBytes = (size_t)2 * (NQ + NH) * 32 * 16 + 2 * 32 * 8;
   static constexpr size_t kBytes = kWarpBytes * kSweepWarps;
 };
+// Measured and dropped (round 2, NSD shape, 8 x 8 tile at 10.0 ms): bulk-copy (cp.async.bulk, 256 B per row) fetches into a
+// shared-memory ring -- 19 ms, the copy engine takes ~20 cycles per 256-byte request; per-lane cp.async into a ring -- 9.7 vs
+// 8.4 ms in the microbenchmark (tools/experiments/sweep_bench.cu), the extra LDS traffic costs more than the deeper prefetch
+// gains; two warps per pair exchanging dev values through shared memory (32 accumulators, 16 warps per SM) -- 13 ms, the
+// per-pair barrier serialises the two warps and no more rows are in flight; 4 x 8 / 4 x 4 tiles -- 26 / 15 ms (more lookups).
 // Table rows are fetched into registers kDepth - 1 pairs ahead of the pair being multiplied.  The 8 x 8 tile has room for one
 // pair ahead (64 accumulators = 128 registers); smaller tiles look further ahead, which is what hides the L2 latency when a
 // pair needs only a few rows (a single matrix swept against eight: 9 rows per pair).
