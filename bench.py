@@ -304,7 +304,8 @@ def run_ours(args):
         strong = {"workload": f"THINGS shape (BASELINE config 3): n={n3}, behavioural RDM d=66 x {len(feats3)} layers, {B} replicates of ONE job",
                   "scaling": "strong", "n_gpus": world, "ms_per_step": t_s, "value": len(feats3) * B / (t_s * 1e-3), "unit": UNIT,
                   "steps": args.strong_steps, "score_checksum": checksum,
-                  "note": "score_checksum must be identical at every N (replicates keep their draw order, sums are exact integers)"}
+                  "note": "wide layers are K-split over the ranks (balanced RDM builds), so RDM entries differ from the one-GPU build in the "
+                          "last bits and score_checksum agrees across N to ~1e-6 of its value; rsa_grouped_sharded(ksplit=False) is bit-identical"}
         del feats3, beh
 
     if rank != 0:

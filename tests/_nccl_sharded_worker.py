@@ -37,6 +37,19 @@ def main():
         got3 = vdist.rsa_grouped_sharded(feats, neur, "pearson", n_bootstrap=B, seed=42)
         want3 = vb.rsa_grouped(feats, neur, "pearson", bootstrap=True, n_bootstrap=B, seed=42)
         assert np.array_equal(got3["scores"], want3["scores"])
+        # the balanced build: wide inputs K-split over the ranks inside the sharded job; scores within the 1e-5 budget of one GPU,
+        # bit-identical with ksplit=False
+        old_min = vdist.KSPLIT_MIN_COLS
+        vdist.KSPLIT_MIN_COLS = 64
+        try:
+            wide_feats = [torch.cat([f] * 3, dim=1) for f in feats]                 # 120 / 999 / 192 columns
+            want_w = vb.rsa_grouped(wide_feats, neur, "spearman", bootstrap=True, n_bootstrap=B, seed=42)
+            got_w = vdist.rsa_grouped_sharded(wide_feats, neur, "spearman", n_bootstrap=B, seed=42, shard_rdms="force", ksplit=True)
+            assert float(np.abs(got_w["scores"] - want_w["scores"]).max()) <= 1e-5 and float(np.abs(got_w["point"] - want_w["point"]).max()) <= 1e-5
+            got_x = vdist.rsa_grouped_sharded(wide_feats, neur, "spearman", n_bootstrap=B, seed=42, shard_rdms="force", ksplit=False)
+            assert np.array_equal(got_x["scores"], want_w["scores"])
+        finally:
+            vdist.KSPLIT_MIN_COLS = old_min
         # K-split RDM: every rank runs the SYRK on its column shard, Grams reduced over NCCL before the epilogue
         from oracle import rsa_oracle as orc
         for (nk, dk, seed) in ((130, 700, 1), (500, 40000, 2)):

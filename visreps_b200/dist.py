@@ -56,9 +56,12 @@ def _allgather_rows(mine: torch.Tensor, counts: Sequence[int], group=None) -> to
     return torch.cat([out[r, :counts[r]] for r in range(world)], dim=0)
 
 
+KSPLIT_MIN_COLS = 4096      # an input is K-split over the ranks when every rank gets at least this many columns
+
+
 def rsa_grouped_sharded(model_features: Sequence[torch.Tensor], neural_responses: Sequence[torch.Tensor],
                         method: str = "spearman", n_bootstrap: int = 1000, seed: int = 42, group=None,
-                        compute=None, shard_rdms: bool = True) -> Dict[str, np.ndarray]:
+                        compute=None, shard_rdms: bool = True, ksplit: bool = True) -> Dict[str, np.ndarray]:
     """`rsa_grouped` with the replicates of every pair sharded over the ranks of `group`.
 
     Every rank draws the same index sets from RandomState(seed) (host, cheap) and scores its own contiguous
@@ -67,6 +70,10 @@ def rsa_grouped_sharded(model_features: Sequence[torch.Tensor], neural_responses
     With `shard_rdms` (NCCL, Spearman) the replicate-independent work is sharded too, so that it does not cap the
     scaling: rank r builds and presorts only its share of the RDMs, and one all-gather over NVLink hands every
     rank all presorted blobs (8 bytes per RDM pair, 14 MB at n = 1854) before the replicates are ranked.
+    With `ksplit` the RDMs of wide inputs (>= KSPLIT_MIN_COLS columns per rank) are built cooperatively (feature-sharded
+    SYRK + all-reduce of the Gram): balanced whatever the layer widths, at the price of RDM entries that differ from the
+    single-GPU build in the last bits (different summation order; scores agree to ~1e-7).  `ksplit=False` keeps every RDM on
+    one rank and the result bit-identical to one GPU.
     `compute` is injectable for tests (and selects the replicate-only sharding).  `shard_rdms="force"` takes the
     sharded-build branch at any world size (a one-rank NCCL group exercises the blob exchange on one GPU).
     """
@@ -91,21 +98,46 @@ def rsa_grouped_sharded(model_features: Sequence[torch.Tensor], neural_responses
     from . import _lib
     lib = _lib.load()
     dev = _lib.require_cuda()
-    inputs = list(model_features) + list(neural_responses)
+    inputs = [rsa._flat(t) for t in list(model_features) + list(neural_responses)]
     nA, total = len(model_features), len(inputs)
     n = int(inputs[0].shape[0])
     if any(int(t.shape[0]) != n for t in inputs):
         raise ValueError("all inputs must have the same number of stimuli")
-    # 1. this rank's share of the RDM builds + presorts (contiguous block of the input list)
-    counts = [shard_bounds(total, r, world)[1] - shard_bounds(total, r, world)[0] for r in range(world)]
-    a, b = shard_bounds(total, rank, world)
+    # 1. RDM builds.  Wide inputs are K-split: every rank runs the tensor-core SYRK on its column shard and the Grams are
+    #    all-reduced over NVLink (compute_rdm_ksplit) -- perfectly balanced whatever the layer widths are, where one RDM per
+    #    rank leaves the rank that drew conv1 (39 % of all the columns of an AlexNet) as the straggler.  Narrow inputs are
+    #    built whole by one rank each.  Every RDM is presorted by exactly one rank.
     flags = torch.zeros(total, dtype=torch.int32, device=dev)
-    mine = rsa.PresortedRDM.batch([rsa._rdm_device(rsa._flat(inputs[k]), dev, 1e-12, flags, k) for k in range(a, b)])
+    wide = [k for k in range(total) if ksplit and world > 1 and int(inputs[k].shape[1]) >= KSPLIT_MIN_COLS * world]
+    narrow = [k for k in range(total) if k not in wide]
+    owner = {}
+    for pos, k in enumerate(narrow):
+        owner[k] = pos % world
+    load = [sum(1 for k in narrow if owner[k] == r) for r in range(world)]
+    for k in wide:                                            # presort duty of the K-split RDMs: least loaded rank first
+        r = min(range(world), key=lambda q: (load[q], q))
+        owner[k] = r
+        load[r] += 1
+    rdms = {}
+    for k in wide:
+        c_lo, c_hi = column_shard(int(inputs[k].shape[1]), rank, world)
+        full = compute_rdm_ksplit(inputs[k][:, c_lo:c_hi], d_total=int(inputs[k].shape[1]), group=group)
+        if owner[k] == rank:
+            rdms[k] = full
+    for k in narrow:
+        if owner[k] == rank:
+            rdms[k] = rsa._rdm_device(inputs[k], dev, 1e-12, flags, k)
+    mine_idx = sorted(rdms)
+    mine = rsa.PresortedRDM.batch([rdms[k] for k in mine_idx])
     blob_bytes = int(lib.vr_presort_bytes(n))
     local = torch.stack([it.blob for it in mine]) if mine else torch.empty((0, blob_bytes), dtype=torch.uint8, device=dev)
-    # 2. the exchange step of the sharded build: every rank receives every presorted blob
+    # 2. the exchange step of the sharded build: every rank receives every presorted blob (rank-major order)
+    counts = [sum(1 for k in range(total) if owner[k] == r) for r in range(world)]
     blobs = _allgather_rows(local, counts, group)
-    items = [rsa.PresortedRDM.from_blob(blobs[k], n) for k in range(total)]
+    order = [k for r in range(world) for k in range(total) if owner[k] == r]
+    items = [None] * total
+    for pos, k in enumerate(order):
+        items[k] = rsa.PresortedRDM.from_blob(blobs[pos], n)
     # 3. this rank's replicates (plus the point estimate, one extra mask) for all pairs
     draws = rsa.draw_subsample_masks(n, n_bootstrap, seed, replicate_range=(lo, hi))
     masks = rsa.build_masks(draws, n, dev, with_full=True)
