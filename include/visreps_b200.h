@@ -82,6 +82,14 @@ int vr_rdm_pearson_f32(const float* X, int n, int64_t d, int64_t ldx, float corr
                        float* rdm, int* zero_var_rows,
                        void* ws, size_t ws_bytes, vr_stream_t stream);
 
+/* Same, with the strict upper triangle packed in the row-major order of torch.triu_indices(n, n, 1) written by the epilogue
+ * itself (what compute_rdm_correlation gathers, rsa.py:111-113): triu is n(n-1)/2 fp32; rdm or triu may be NULL, not both. */
+int vr_rdm_pearson_triu_f32(const float* X, int n, int64_t d, int64_t ldx, float correction,
+                            float* rdm, float* triu, int* zero_var_rows,
+                            void* ws, size_t ws_bytes, vr_stream_t stream);
+/* The gather alone, for an existing (n, n) matrix with leading dimension ld. */
+int vr_triu_pack_f32(const float* m, int n, int64_t ld, float* out, vr_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * The same RDM in stages, for rows whose FEATURES are split over several devices (K-split multi-GPU SYRK,
  * the 10,000 x 193,600 stress shape).  Every rank holds a column shard X_r (n, d_r):

@@ -172,3 +172,24 @@ def test_nan_entries_make_only_the_replicates_that_keep_them_nan(dev):
             want = orc.rdm_compare(bad[sub][:, sub], b[sub][:, sub], correlation="Spearman")
             assert abs(sweep[0, 0, r + 1] - want) <= 1e-9
     assert n_clean >= 1
+
+
+def test_rsa_grouped_host_pipeline_through_the_sweep_engine(dev, monkeypatch):
+    """Host inputs whose count tables exceed shared memory (n > 1277), or any host input once the legacy threshold is lowered,
+    are added to the job one matrix at a time as their copies land and swept against the other side: same bits as the batched
+    device-resident job and as the legacy pipeline."""
+    rs = np.random.RandomState(23)
+    n, B = 140, 37
+    z = rs.standard_normal((n, 10)).astype(np.float32)
+    feats = [torch.from_numpy(np.maximum(z @ rs.standard_normal((10, d)).astype(np.float32) + rs.standard_normal((n, d)).astype(np.float32), 0))
+             for d in (300, 40, 1200, 77, 513)]
+    neur = [torch.from_numpy(np.round(z @ rs.standard_normal((10, v)) + rs.standard_normal((n, v)), 2).astype(np.float32)) for v in (25, 60, 33)]
+    on_device = vb.rsa_grouped([f.to(dev) for f in feats], [y.to(dev) for y in neur], "spearman", n_bootstrap=B, seed=42)
+    legacy_host = vb.rsa_grouped([f.pin_memory() for f in feats], neur, "spearman", n_bootstrap=B, seed=42)
+    monkeypatch.setattr(vrsa, "_LEGACY_SMEM_TABLE_MAX_N", 0)                 # force the sweep pipeline for host inputs
+    sweep_host = vb.rsa_grouped([f.pin_memory() for f in feats], neur, "spearman", n_bootstrap=B, seed=42)
+    swapped = vb.rsa_grouped(neur, [f.pin_memory() for f in feats], "spearman", n_bootstrap=B, seed=42)
+    for key in ("point", "scores", "ci_low", "ci_high"):
+        np.testing.assert_array_equal(sweep_host[key], on_device[key])
+        np.testing.assert_array_equal(legacy_host[key], on_device[key])
+    np.testing.assert_array_equal(swapped["scores"], np.transpose(on_device["scores"], (1, 0, 2)))

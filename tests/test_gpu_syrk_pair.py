@@ -119,3 +119,19 @@ def test_device_fp64_truth_agrees_with_the_oracle_truth(dev):
     a = _truth_f64(x).cpu().numpy()
     b = orc.rdm_truth_f64(x.cpu())
     assert float(np.abs(a - b).max()) <= 1e-12
+
+
+def test_packed_upper_triangle_from_the_epilogue(dev):
+    """vr_rdm_pearson_triu_f32 / vr_triu_pack_f32: the vector compute_rdm_correlation gathers (rsa.py:111-113), bit for bit."""
+    from visreps_b200 import rsa as vrsa
+    for n, d in ((1, 5), (2, 9), (67, 130), (500, 20000)):
+        x = _post_relu_rows(n, d, 40 + n, dev)
+        full = vb.compute_rdm(x)
+        iu = torch.triu_indices(n, n, 1, device=dev)
+        want = full[iu[0], iu[1]]
+        got = vrsa.rdm_upper_triangle(x)
+        assert got.shape == want.shape and torch.equal(got, want)
+        if n > 1:
+            out = torch.empty_like(want)
+            _lib.check(_lib.load().vr_triu_pack_f32(full.data_ptr(), n, n, out.data_ptr(), _lib.stream_ptr()), "vr_triu_pack_f32")
+            assert torch.equal(out, want)

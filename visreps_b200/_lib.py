@@ -32,6 +32,8 @@ SIGNATURES = {
     "vr_profile_stop": (_i, [_vp, _vp, _vp]),
     "vr_rdm_workspace_bytes": (_sz, [_i, _i64]),
     "vr_rdm_pearson_f32": (_i, [_vp, _i, _i64, _i64, _f, _vp, _vp, _vp, _sz, _vp]),
+    "vr_rdm_pearson_triu_f32": (_i, [_vp, _i, _i64, _i64, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "vr_triu_pack_f32": (_i, [_vp, _i, _i64, _vp, _vp]),
     "vr_rdm_moments_f32": (_i, [_vp, _i, _i64, _i64, _vp, _vp, _vp]),
     "vr_rdm_shift_from_moments": (_i, [_vp, _i, _i64, _vp, _vp]),
     "vr_rdm_gram_f32": (_i, [_vp, _i, _i64, _i64, _vp, _vp, _i64, _vp, _sz, _vp]),

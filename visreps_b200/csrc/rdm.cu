@@ -169,11 +169,11 @@ row_center_kernel(const float* __restrict__ X, int n, int64_t d, int64_t ldx, fl
 __global__ void __launch_bounds__(256)
 rdm_epilogue_kernel(const float* __restrict__ partial, int splits, int n_pad, int n, int64_t d,
                     const float* __restrict__ stdv, const double* __restrict__ delta, float correction,
-                    float* __restrict__ rdm) {
+                    float* __restrict__ rdm, float* __restrict__ triu) {
   const int j = blockIdx.x * 256 + threadIdx.x;
   const int i = blockIdx.y;
   if (j >= n || j < i) return;
-  if (i == j) { rdm[(int64_t)i * n + i] = 0.f; return; }
+  if (i == j) { if (rdm) rdm[(int64_t)i * n + i] = 0.f; return; }
   double g = 0.0;
   const int64_t plane = (int64_t)n_pad * n_pad;
   for (int s = 0; s < splits; ++s) g += (double)partial[s * plane + (int64_t)i * n_pad + j];
@@ -181,8 +181,19 @@ rdm_epilogue_kernel(const float* __restrict__ partial, int splits, int n_pad, in
   float corr = cov / (stdv[i] * stdv[j] + correction);
   corr = fminf(fmaxf(corr, -1.f), 1.f);
   const float v = 1.0f - corr;
-  rdm[(int64_t)i * n + j] = v;
-  rdm[(int64_t)j * n + i] = v;
+  if (rdm) {
+    rdm[(int64_t)i * n + j] = v;
+    rdm[(int64_t)j * n + i] = v;
+  }
+  if (triu) triu[triu_pos((uint32_t)i, (uint32_t)j, (uint32_t)n)] = v;      // row-major strict upper triangle (rsa.py:111-113)
+}
+
+// Strict upper triangle of an (n, n) matrix in the row-major order of torch.triu_indices(n, n, 1).
+__global__ void __launch_bounds__(256)
+triu_pack_kernel(const float* __restrict__ m, int n, int64_t ld, float* __restrict__ out) {
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  const int i = blockIdx.y;
+  if (j < n && j > i) out[triu_pos((uint32_t)i, (uint32_t)j, (uint32_t)n)] = m[(int64_t)i * ld + j];
 }
 
 // ---- staged form for rows split over feature shards (multi-GPU K split) -----------------------------
@@ -371,10 +382,25 @@ extern "C" size_t vr_rdm_workspace_bytes(int n, int64_t d) {
          arena_bytes((size_t)p.tc_splits * p.n_pad * p.n_pad, 4) + 256;
 }
 
+extern "C" int vr_triu_pack_f32(const float* m, int n, int64_t ld, float* out, vr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  VR_REQUIRE(m && out, "vr_triu_pack_f32: null pointer");
+  VR_REQUIRE(n >= 1 && n <= VR_MAX_STIMULI && ld >= n, "vr_triu_pack_f32: bad shape n=%d ld=%lld", n, (long long)ld);
+  if (n < 2) return VR_OK;
+  triu_pack_kernel<<<dim3((n + 255) / 256, n), 256, 0, stream>>>(m, n, ld, out);
+  VR_CHECK_LAUNCH();
+  return VR_OK;
+}
+
 extern "C" int vr_rdm_pearson_f32(const float* X, int n, int64_t d, int64_t ldx, float correction, float* rdm,
                                   int* zero_var_rows, void* ws, size_t ws_bytes, vr_stream_t stream_) {
+  return vr_rdm_pearson_triu_f32(X, n, d, ldx, correction, rdm, nullptr, zero_var_rows, ws, ws_bytes, stream_);
+}
+
+extern "C" int vr_rdm_pearson_triu_f32(const float* X, int n, int64_t d, int64_t ldx, float correction, float* rdm, float* triu,
+                                       int* zero_var_rows, void* ws, size_t ws_bytes, vr_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  VR_REQUIRE(X && rdm, "vr_rdm_pearson_f32: null pointer");
+  VR_REQUIRE(X && (rdm || triu), "vr_rdm_pearson_f32: null pointer");
   VR_REQUIRE(n >= 1 && n <= VR_MAX_STIMULI && d >= 1 && ldx >= d, "vr_rdm_pearson_f32: bad shape n=%d d=%lld ldx=%lld",
              n, (long long)d, (long long)ldx);
   if (!ws || ws_bytes < vr_rdm_workspace_bytes(n, d)) {
@@ -396,7 +422,7 @@ extern "C" int vr_rdm_pearson_f32(const float* X, int n, int64_t d, int64_t ldx,
   }
   dim3 eg((n + 255) / 256, n);
   ProfScope prof(F_RDM_EPILOGUE, stream);
-  rdm_epilogue_kernel<<<eg, 256, 0, stream>>>(partial, splits, p.n_pad, n, d, stdv, delta, correction, rdm);
+  rdm_epilogue_kernel<<<eg, 256, 0, stream>>>(partial, splits, p.n_pad, n, d, stdv, delta, correction, rdm, triu);
   VR_CHECK_LAUNCH();
   return VR_OK;
 }

@@ -441,6 +441,22 @@ def compute_rdm(representations: torch.Tensor, *, correlation: str = "Pearson", 
     return rdm.to(src)
 
 
+def rdm_upper_triangle(representations: torch.Tensor, correction: float = 1e-12) -> torch.Tensor:
+    """The strict upper triangle of `compute_rdm(representations)` in `torch.triu_indices(n, n, 1)` order (rsa.py:111-113),
+    written by the SYRK epilogue itself: the (n, n) matrix is never formed."""
+    lib = _lib.load()
+    dev = _lib.require_cuda()
+    src = representations.device
+    x = _as_cuda_f32_rows(_flat(representations), dev)
+    n, d = int(x.size(0)), int(x.size(1))
+    out = torch.empty(n * (n - 1) // 2 if n > 1 else 0, dtype=torch.float32, device=dev)
+    if n > 1:
+        ws = _lib.workspace(lib.vr_rdm_workspace_bytes(n, d), dev)
+        _lib.check(lib.vr_rdm_pearson_triu_f32(x.data_ptr(), n, d, x.stride(0), float(correction), None, out.data_ptr(), None,
+                                               ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "vr_rdm_pearson_triu_f32")
+    return out.to(src)
+
+
 def compute_rdm_correlation(rdm1: torch.Tensor, rdm2: torch.Tensor, *, correlation: str = "Kendall") -> float:
     """Correlation of two RDMs over the strict upper triangle (reference: rsa.py:96-129).
 
