@@ -112,6 +112,8 @@ def _ksplit_worker(rank, world, port, out):
         rdm = vdist.compute_rdm_ksplit(x[:, lo:hi], stages=_np_stages())          # d_total found by an all-reduce
         rdm2 = vdist.compute_rdm_ksplit(x[:, lo:hi], d_total=301, stages=_np_stages())
         assert torch.equal(rdm, rdm2)
+        many = vdist.compute_rdm_ksplit_many([x[:, lo:hi], 2.0 * x[:, lo:hi] + 1.0], [301, 301], stages=_np_stages())
+        assert float((many[0] - rdm).abs().max()) <= 1e-6 and float((many[1] - rdm).abs().max()) <= 1e-5   # affine rows: same correlations
         if rank == 0:
             np.save(out, rdm.numpy())
     finally:

@@ -321,11 +321,14 @@ def _spearman_sweep_grouped(model: Sequence[PresortedRDM], neural: Sequence[Pres
     n = model[0].n
     nA, nB, R = len(model), len(neural), int(masks.shape[0])
     dev = masks.device
-    free, _total = torch.cuda.mem_get_info(dev)
-    cached = torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
-    budget = max(int(0.5 * (free + cached)), 1 << 28)
-    per_batch = max(1, SpearmanJob.bytes_needed(n, nA + nB, 64) - SpearmanJob.bytes_needed(n, nA + nB, 32))
-    chunk = max(32, min((R + 31) // 32 * 32, budget // per_batch * 32))
+    key = ("chunk", n, nA, nB, R, dev.index)
+    chunk = _fit_cache.get(key)
+    if chunk is None:       # cudaMemGetInfo costs 0.2-1.5 ms: asked once per problem shape, not once per call
+        free, _total = torch.cuda.mem_get_info(dev)
+        cached = torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
+        budget = max(int(0.5 * (free + cached)), 1 << 28)
+        per_batch = max(1, SpearmanJob.bytes_needed(n, nA + nB, 64) - SpearmanJob.bytes_needed(n, nA + nB, 32))
+        chunk = _fit_cache[key] = max(32, min((R + 31) // 32 * 32, budget // per_batch * 32))
     flat = out.view(-1)
     for r0 in range(0, R, chunk):
         rc = min(chunk, R - r0)
@@ -1055,7 +1058,7 @@ def _pipeline_fits(n: int, nA: int, nB: int, R: int, dev: torch.device) -> bool:
     return hit
 
 
-_fit_cache: Dict[tuple, bool] = {}
+_fit_cache: Dict[tuple, object] = {}
 
 
 class _no_gc:
