@@ -193,3 +193,45 @@ def test_rsa_grouped_host_pipeline_through_the_sweep_engine(dev, monkeypatch):
         np.testing.assert_array_equal(sweep_host[key], on_device[key])
         np.testing.assert_array_equal(legacy_host[key], on_device[key])
     np.testing.assert_array_equal(swapped["scores"], np.transpose(on_device["scores"], (1, 0, 2)))
+
+
+def test_kendall_complement_mode_equals_the_direct_count(dev):
+    """csrc/kendall.cu: ties and inversions counted among the DROPPED entries (complement mode, default) give exactly the tau-a
+    of the direct count among the kept ones, for masks that keep most, half, few and all stimuli, with ties, and equal SciPy."""
+    rs = np.random.RandomState(9)
+    n = 90
+    N = n * (n - 1) // 2
+    a, b = cases.tied_vectors(N, 60, 77)
+    ra, rb = cases.vector_to_rdm(a, n).to(dev), cases.vector_to_rdm((b + 0.3 * rs.standard_normal(N)).astype(np.float32).round(1), n).to(dev)
+    sets = [rs.choice(n, size=m, replace=False) for m in (81, 81, 81, 60, 45, 20, 3, 2, 89, 90)]
+    W = (n + 31) // 32
+    words = np.zeros((len(sets) + 1, W), dtype=np.uint32)
+    words[0] = vrsa.full_mask(n)
+    for r, idx in enumerate(sets):
+        for i in idx:
+            words[r + 1, i >> 5] |= np.uint32(1) << np.uint32(i & 31)
+    masks = torch.from_numpy(words.view(np.int32)).to(dev)
+    A, B = [vrsa._RawRDM(ra)], [vrsa._RawRDM(rb)]
+    out = {}
+    for mode in (1, 0):
+        _lib.set_option("kendall_complement", mode)
+        lib = _lib.load()
+        ws = _lib.workspace(lib.vr_kendall_batch_workspace_bytes(n, masks.shape[0]), dev)
+        res = torch.empty(masks.shape[0], dtype=torch.float64, device=dev)
+        _lib.check(lib.vr_kendall_tau_a(ra.data_ptr(), rb.data_ptr(), n, n, masks.data_ptr(), int(masks.shape[0]), res.data_ptr(),
+                                        ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "vr_kendall_tau_a")
+        out[mode] = res.cpu().numpy()
+    _lib.set_option("kendall_complement", 1)
+    np.testing.assert_array_equal(out[1], out[0])
+    va, vb_ = orc.triu_vector(ra), orc.triu_vector(rb)
+    iu = np.triu_indices(n, 1)
+    for r, idx in enumerate([np.arange(n)] + sets):
+        keep = np.zeros(n, dtype=bool); keep[idx] = True
+        kp = keep[iu[0]] & keep[iu[1]]
+        want = orc.kendall_tau_a(va[kp], vb_[kp])[0]
+        got = out[1][r]
+        assert (np.isnan(want) and np.isnan(got)) or abs(got - want) <= 1e-6, (r, got, want)      # the oracle goes through tau-b in floating point
+    # through the public API, both modes chosen by the kept fraction
+    big = vb.bootstrap_rdm_correlation(ra, rb, "kendall", n_bootstrap=7, seed=42)
+    few = vb.bootstrap_rdm_correlation_grouped([ra], [rb], "kendall", index_sets=np.stack([rs.choice(n, size=30, replace=False) for _ in range(5)]))
+    assert len(big[3]) == 7 and few["scores"].shape == (1, 1, 5) and np.isfinite(few["scores"]).all()

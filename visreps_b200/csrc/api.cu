@@ -20,7 +20,8 @@ void set_error(const char* fmt, ...) {
 // ---- tuning options ---------------------------------------------------------------------
 static std::atomic<int> g_syrk_pair{[] { const char* e = getenv("VR_SYRK_PAIR"); return e ? atoi(e) : 1; }()};
 static std::atomic<int> g_syrk_waves{[] { const char* e = getenv("VR_SYRK_WAVES"); return e ? atoi(e) : 1; }()};
-static std::atomic<int> g_sweep_tile_a{8}, g_sweep_tile_b{8};
+static std::atomic<int> g_sweep_tile_a{8}, g_sweep_tile_b{8}, g_kendall_complement{1};
+int option_kendall_complement() { return g_kendall_complement.load(std::memory_order_relaxed); }
 int option_sweep_tile_a() { return g_sweep_tile_a.load(std::memory_order_relaxed); }
 int option_sweep_tile_b() { return g_sweep_tile_b.load(std::memory_order_relaxed); }
 int option_syrk_pair() { return g_syrk_pair.load(std::memory_order_relaxed); }
@@ -111,6 +112,7 @@ extern "C" int vr_set_option(const char* name, int value) {
   VR_REQUIRE(name, "vr_set_option: null name");
   if (!strcmp(name, "syrk_pair")) { vr::g_syrk_pair.store(value); return VR_OK; }
   if (!strcmp(name, "syrk_waves")) { VR_REQUIRE(value >= 1 && value <= 64, "vr_set_option: syrk_waves=%d outside [1, 64]", value); vr::g_syrk_waves.store(value); return VR_OK; }
+  if (!strcmp(name, "kendall_complement")) { vr::g_kendall_complement.store(value != 0); return VR_OK; }
   if (!strcmp(name, "sweep_tile_a") || !strcmp(name, "sweep_tile_b")) {
     VR_REQUIRE(value >= 1 && value <= 8, "vr_set_option: %s=%d outside [1, 8]", name, value);
     (name[11] == 'a' ? vr::g_sweep_tile_a : vr::g_sweep_tile_b).store(value);
@@ -123,6 +125,7 @@ extern "C" int vr_get_option(const char* name, int* value) {
   VR_REQUIRE(name && value, "vr_get_option: null pointer");
   if (!strcmp(name, "syrk_pair")) { *value = vr::option_syrk_pair(); return VR_OK; }
   if (!strcmp(name, "syrk_waves")) { *value = vr::option_syrk_waves(); return VR_OK; }
+  if (!strcmp(name, "kendall_complement")) { *value = vr::option_kendall_complement(); return VR_OK; }
   if (!strcmp(name, "sweep_tile_a")) { *value = vr::option_sweep_tile_a(); return VR_OK; }
   if (!strcmp(name, "sweep_tile_b")) { *value = vr::option_sweep_tile_b(); return VR_OK; }
   vr::set_error("vr_get_option: unknown option '%s'", name);

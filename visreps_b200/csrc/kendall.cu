@@ -269,6 +269,216 @@ merge_level_kernel(const uint32_t* __restrict__ in_all, uint32_t* __restrict__ o
   if (lane_id() == 0 && local) atomicAdd(acc + (size_t)r * 4 + 3, local);
 }
 
+// ---- complement mode -------------------------------------------------------------------------------------------
+// A 90 % subsample keeps 81 % of the entries: instead of counting ties and inversions among the ~404 k kept entries of every
+// replicate, count them among the ~95 k DROPPED ones and use, for each relation Q in {tied in x, tied in y, tied in both,
+// discordant}:      Q(kept) = Q(all) - sum over dropped entries e of q(e) + Q(dropped)
+// where q(e) = number of entries in relation Q with e (replicate independent, once per RDM pair): a pair with exactly one dropped
+// member is removed once, a pair with two dropped members twice and added back once.  The sum over the dropped entries is taken
+// through the dropped STIMULI (as the Pearson path does):  sum_{i in D} rowsum_q(i) - sum_{i<j in D} q({i, j}).
+// The merge sort that counts inversions then runs on a sequence 4x shorter (83 % of the time of the direct path).
+
+// q[order[k]] = size of the run of equal keys holding sorted position k, minus one (lexicographic on (k0, k1) when k1 is given).
+__global__ void __launch_bounds__(256)
+run_ties_kernel(const uint32_t* __restrict__ k0, const uint32_t* __restrict__ k1, const uint32_t* __restrict__ start,
+                const uint32_t* __restrict__ order, uint32_t N, uint32_t* __restrict__ q) {
+  const uint32_t k = blockIdx.x * 256u + threadIdx.x;
+  if (k >= N) return;
+  const uint32_t a = k0[k], b = k1 ? k1[k] : 0u;
+  uint32_t lo = k + 1u, hi = N;                       // first position whose key is greater
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    const uint32_t am = k0[mid];
+    const bool greater = am > a || (k1 && am == a && k1[mid] > b);
+    if (greater) hi = mid; else lo = mid + 1;
+  }
+  q[order[k]] = lo - start[k] - 1u;
+}
+
+// Bottom-up merge sort of (value, entry) pairs that adds, for every element and level, the elements of the sibling run it is
+// inverted with: disc[entry] = number of entries discordant with it.  Same tiling as the counting kernels below.
+__global__ void __launch_bounds__(256)
+tile_sort_entries_kernel(const uint32_t* __restrict__ vin, const uint32_t* __restrict__ ein, uint32_t N,
+                         uint32_t* __restrict__ vout, uint32_t* __restrict__ eout, uint32_t* __restrict__ disc) {
+  constexpr uint32_t kT = 2048;
+  __shared__ uint32_t val[2][kT];
+  __shared__ uint32_t ent[2][kT];
+  const uint32_t base = blockIdx.x * kT;
+  if (base >= N) return;
+  const uint32_t len = min(kT, N - base);
+  for (uint32_t k = threadIdx.x; k < kT; k += 256u) {
+    val[0][k] = k < len ? vin[base + k] : 0xFFFFFFFFu;
+    ent[0][k] = k < len ? ein[base + k] : 0xFFFFFFFFu;
+  }
+  __syncthreads();
+  int src = 0;
+  // every element has one owner per level and levels are separated by __syncthreads(): plain read-modify-writes of disc[] do not race
+  for (uint32_t L = 1; L < kT; L <<= 1) {
+    const uint32_t* sv = val[src];
+    const uint32_t* se = ent[src];
+    uint32_t* dv = val[src ^ 1];
+    uint32_t* de = ent[src ^ 1];
+    for (uint32_t k = threadIdx.x; k < kT; k += 256u) {
+      const uint32_t v = sv[k], e = se[k];
+      const uint32_t blk = k / (2u * L) * (2u * L);
+      const uint32_t a1 = min(kT, blk + L), b1 = min(kT, blk + 2u * L);
+      uint32_t slot, inv;
+      if (k < a1) {                                                          // left run: right elements strictly smaller
+        uint32_t lo = a1, hi = b1;
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (sv[mid] < v) lo = mid + 1; else hi = mid; }
+        inv = lo - a1;
+        slot = k + (lo - a1);
+      } else {                                                               // right run: left elements strictly greater
+        uint32_t lo = blk, hi = a1;
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (sv[mid] <= v) lo = mid + 1; else hi = mid; }
+        inv = a1 - lo;
+        slot = blk + (k - a1) + (lo - blk);
+      }
+      dv[slot] = v;
+      de[slot] = e;
+      if (inv && e != 0xFFFFFFFFu) disc[e] += inv;                           // padding never counts: it is the largest value and sits last
+    }
+    __syncthreads();
+    src ^= 1;
+  }
+  for (uint32_t k = threadIdx.x; k < len; k += 256u) { vout[base + k] = val[src][k]; eout[base + k] = ent[src][k]; }
+}
+__global__ void __launch_bounds__(256)
+merge_level_entries_kernel(const uint32_t* __restrict__ vin, const uint32_t* __restrict__ ein, uint32_t N, uint32_t L,
+                           uint32_t* __restrict__ vout, uint32_t* __restrict__ eout, uint32_t* __restrict__ disc) {
+  for (uint32_t k = blockIdx.x * 256u + threadIdx.x; k < N; k += gridDim.x * 256u) {
+    const uint32_t v = vin[k], e = ein[k];
+    const uint32_t blk = k / (2u * L) * (2u * L);
+    const uint32_t a1 = min(N, blk + L), b1 = min(N, blk + 2u * L);
+    uint32_t slot, inv;
+    if (k < a1) {
+      uint32_t lo = a1, hi = b1;
+      while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (vin[mid] < v) lo = mid + 1; else hi = mid; }
+      inv = lo - a1;
+      slot = k + (lo - a1);
+    } else {
+      uint32_t lo = blk, hi = a1;
+      while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (vin[mid] <= v) lo = mid + 1; else hi = mid; }
+      inv = a1 - lo;
+      slot = blk + (k - a1) + (lo - blk);
+    }
+    vout[slot] = v;
+    eout[slot] = e;
+    if (inv) disc[e] += inv;
+  }
+}
+
+// rows[q][i] = sum over b != i of q({i, b}).  grid (n, 4), 256 threads.
+struct EntryCounts { const uint32_t* q[4]; };      // per canonical entry: tied in x, tied in y, tied in both, discordant
+__global__ void __launch_bounds__(256)
+entry_row_sums_kernel(const EntryCounts Q, int n, unsigned long long* __restrict__ rows) {
+  __shared__ unsigned long long red[8];
+  const uint32_t i = blockIdx.x;
+  const uint32_t* __restrict__ q = Q.q[blockIdx.y];
+  unsigned long long acc = 0;
+  for (uint32_t b = threadIdx.x; b < (uint32_t)n; b += 256u)
+    if (b != i) acc += q[b < i ? triu_pos(b, i, (uint32_t)n) : triu_pos(i, b, (uint32_t)n)];
+  acc = (unsigned long long)warp_sum_ll((long long)acc);
+  if (lane_id() == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    rows[(size_t)blockIdx.y * n + i] = t;
+  }
+}
+// totals[q] = sum_i rows[q][i] = 4 Q(all).  grid 4, 256 threads.
+__global__ void __launch_bounds__(256)
+entry_totals_kernel(const unsigned long long* __restrict__ rows, int n, unsigned long long* __restrict__ totals) {
+  __shared__ unsigned long long red[8];
+  unsigned long long acc = 0;
+  for (int i = threadIdx.x; i < n; i += 256) acc += rows[(size_t)blockIdx.x * n + i];
+  acc = (unsigned long long)warp_sum_ll((long long)acc);
+  if (lane_id() == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    totals[blockIdx.x] = t;
+  }
+}
+// pairbits <- the DROPPED canonical pairs (positions >= N stay 0)
+__global__ void complement_bits_kernel(uint32_t* __restrict__ pairbits, uint32_t words, uint32_t N, int Rb) {
+  const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= words) return;
+  uint32_t valid = 0xFFFFFFFFu;
+  if (w * 32u + 32u > N) valid = w * 32u >= N ? 0u : ((1u << (N - w * 32u)) - 1u);
+  for (int r = 0; r < Rb; ++r) pairbits[(size_t)r * words + w] = ~pairbits[(size_t)r * words + w] & valid;
+}
+// sub[r][q] = sum over the dropped entries of replicate r of q(e) = sum_{i in D} rows[q][i] - sum_{i<j in D} q({i, j}).
+// grid (Rb), 256 threads; `drop` is scratch of Rb x n stimulus indices.
+__global__ void __launch_bounds__(256)
+dropped_entry_sums_kernel(const uint32_t* __restrict__ masks, int W, int n, const EntryCounts Q, const unsigned long long* __restrict__ rows,
+                          uint32_t* __restrict__ drop, unsigned long long* __restrict__ sub) {
+  __shared__ int s_cnt;
+  __shared__ unsigned long long red[4][8];
+  const int r = blockIdx.x;
+  const uint32_t* __restrict__ mask = masks + (size_t)r * W;
+  uint32_t* __restrict__ list = drop + (size_t)r * n;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < n; i0 += 256) {                                      // dropped stimuli, ascending inside every 256-block
+    const int i = i0 + (int)threadIdx.x;
+    const bool d = i < n && !((mask[i >> 5] >> (i & 31)) & 1u);
+    const unsigned bal = __ballot_sync(0xffffffffu, d);
+    int base = 0;
+    if (lane_id() == 0 && bal) base = atomicAdd(&s_cnt, __popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (d) list[base + __popc(bal & lanemask_lt())] = (uint32_t)i;
+    __syncthreads();
+  }
+  const uint32_t nd = (uint32_t)s_cnt;
+  long long acc[4] = {0, 0, 0, 0};
+  for (uint32_t t = threadIdx.x; t < nd; t += 256u) {
+    const uint32_t i = list[t];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[q] += (long long)rows[(size_t)q * n + i];
+  }
+  const uint32_t npairs = nd * (nd - 1u) / 2u;                                // nd <= 32767: fits
+  for (uint32_t t = threadIdx.x; t < npairs && nd >= 2u; t += 256u) {
+    const uint32_t a = triu_row(t, nd);
+    const uint32_t b = t - a * (2u * nd - a - 1u) / 2u + a + 1u;
+    uint32_t i = list[a], j = list[b];
+    if (i > j) { const uint32_t x = i; i = j; j = x; }
+    const uint32_t p = triu_pos(i, j, (uint32_t)n);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[q] -= (long long)Q.q[q][p];
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const long long v = warp_sum_ll(acc[q]);
+    if (lane_id() == 0) red[q][threadIdx.x >> 5] = (unsigned long long)v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    unsigned long long t = 0;
+    for (int w = 0; w < 8; ++w) t += red[threadIdx.x][w];
+    sub[(size_t)r * 4 + threadIdx.x] = t;
+  }
+}
+// tau-a from the complement: acc[r] / counts[r] describe the DROPPED entries of replicate r.
+__global__ void kendall_finish_complement_kernel(const unsigned long long* __restrict__ acc, const uint32_t* __restrict__ counts,
+                                                 const unsigned long long* __restrict__ totals, const unsigned long long* __restrict__ sub,
+                                                 unsigned long long N, const uint32_t* __restrict__ nan_flag, int Rb, double* __restrict__ out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= Rb) return;
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  const unsigned long long M = N - counts[r];
+  if (M < 2 || *nan_flag) { out[r] = nan; return; }
+  const unsigned long long n0 = M * (M - 1) / 2;
+  unsigned long long q[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) q[k] = totals[k] / 4ull - sub[(size_t)r * 4 + k] + acc[(size_t)r * 4 + k];
+  if (q[0] == n0 || q[1] == n0) { out[r] = nan; return; }
+  const long long cd = (long long)n0 - (long long)q[0] - (long long)q[1] + (long long)q[2] - 2ll * (long long)q[3];
+  out[r] = (double)cd / (double)n0;
+}
+
 // acc[r]: [0] tx  [1] ty  [2] txy  [3] D ; counts[r] = kept entries
 __global__ void kendall_finish_kernel(const unsigned long long* __restrict__ acc, const uint32_t* __restrict__ counts,
                                       const uint32_t* __restrict__ nan_flag, int Rb, double* __restrict__ out) {
@@ -288,15 +498,16 @@ __global__ void kendall_finish_kernel(const unsigned long long* __restrict__ acc
 static size_t kendall_fixed_bytes(int n) {
   const size_t Np = (size_t)round_up(triu_len(n), 32);
   // xkey_c, ykey_c, 4 sort buffers, order_y, ysorted, order_xy, xseq, yseq, 3 run-start arrays
-  return 14 * arena_bytes(Np, 4) + arena_bytes(sort_count_elems(triu_len(n), 1), 4) + 4096;
+  // + complement mode: four per-entry count arrays, 4 n row sums, totals
+  return 18 * arena_bytes(Np, 4) + arena_bytes(sort_count_elems(triu_len(n), 1), 4) + arena_bytes((size_t)4 * n, 8) + 4096;
 }
 static size_t kendall_per_replicate_bytes(int n) {
   const size_t Np = (size_t)round_up(triu_len(n), 32);
   const size_t G = Np / 32, nchunks = (G + kChunkGroups - 1) / kChunkGroups;
   // two y sequences (ping-pong), two kept tables, pair bits, two chunk-total rows, accumulators and counts
-  return 2 * Np * 4 + 2 * G * 8 + G * 4 + 2 * nchunks * 4 + 4 * 8 + 2 * 4;
+  return 2 * Np * 4 + 2 * G * 8 + G * 4 + 2 * nchunks * 4 + 4 * 8 + 2 * 4 + (size_t)n * 4 + 4 * 8;      // + dropped list, sums over the dropped entries
 }
-constexpr size_t kKendallSlack = 8192;       // 256-byte alignment of the per-batch arrays
+constexpr size_t kKendallSlack = 16384;       // 256-byte alignment of the per-batch arrays
 constexpr int kKendallMaxBatch = 64;
 
 }  // namespace vr
@@ -356,6 +567,17 @@ extern "C" int vr_kendall_tau_a(const float* rdmA, const float* rdmB, int n, int
   unsigned long long* acc = a.take<unsigned long long>((size_t)Rb * 4);
   uint32_t* counts = a.take<uint32_t>((size_t)2 * Rb);    // kept entries: [0][r] from the (x, y) order, [1][r] from the y order
   uint32_t* nan_flag = a.take<uint32_t>(8);
+  const bool complement = option_kendall_complement() != 0;
+  uint32_t* qcnt[4] = {nullptr, nullptr, nullptr, nullptr};
+  unsigned long long* rows = nullptr;
+  unsigned long long* totals = nullptr;
+  uint32_t* drop = nullptr;
+  unsigned long long* sub = nullptr;
+  for (int k = 0; k < 4; ++k) qcnt[k] = a.take<uint32_t>(Np);
+  rows = a.take<unsigned long long>((size_t)4 * n);
+  totals = a.take<unsigned long long>(8);
+  drop = a.take<uint32_t>((size_t)Rb * n);
+  sub = a.take<unsigned long long>((size_t)Rb * 4);
   if (!a.ok) { set_error("vr_kendall_tau_a: internal workspace plan overflow"); return VR_ERR_WORKSPACE; }
   ProfScope prof(F_KENDALL, stream);
   const unsigned nblk = (unsigned)((N + 255) / 256);
@@ -386,6 +608,34 @@ extern "C" int vr_kendall_tau_a(const float* rdmA, const float* rdmB, int n, int
   run_start_kernel<<<nblk, 256, 0, stream>>>(ysorted, nullptr, (uint32_t)N, rs_y);
   VR_CHECK_LAUNCH();
 
+  EntryCounts Q{};
+  if (complement) {
+    // per-entry counts, once per RDM pair: run sizes in the three orders, and the discordant partners of every entry from a merge
+    // sort of the y keys in (x, y) order that carries the entry index (k0 / v0 / k1 / v1 are free again)
+    run_ties_kernel<<<nblk, 256, 0, stream>>>(xseq, nullptr, rs_x, order_xy, (uint32_t)N, qcnt[0]);
+    VR_CHECK_LAUNCH();
+    run_ties_kernel<<<nblk, 256, 0, stream>>>(ysorted, nullptr, rs_y, order_y, (uint32_t)N, qcnt[1]);
+    VR_CHECK_LAUNCH();
+    run_ties_kernel<<<nblk, 256, 0, stream>>>(xseq, yseq, rs_xy, order_xy, (uint32_t)N, qcnt[2]);
+    VR_CHECK_LAUNCH();
+    VR_CHECK_CUDA(cudaMemsetAsync(qcnt[3], 0, (size_t)N * 4, stream));
+    const unsigned tiles_all = (unsigned)((N + 2047) / 2048);
+    tile_sort_entries_kernel<<<tiles_all, 256, 0, stream>>>(yseq, order_xy, (uint32_t)N, k0, v0, qcnt[3]);
+    VR_CHECK_LAUNCH();
+    uint32_t *sv = k0, *se = v0, *dv = k1, *de = v1;
+    const unsigned eg = nblk < 4u * kNumSMs ? nblk : 4u * kNumSMs;
+    for (uint64_t L = 2048; L < (uint64_t)N; L <<= 1) {
+      merge_level_entries_kernel<<<eg, 256, 0, stream>>>(sv, se, (uint32_t)N, (uint32_t)L, dv, de, qcnt[3]);
+      VR_CHECK_LAUNCH();
+      uint32_t* t = sv; sv = dv; dv = t;
+      t = se; se = de; de = t;
+    }
+    for (int k = 0; k < 4; ++k) Q.q[k] = qcnt[k];
+    entry_row_sums_kernel<<<dim3(n, 4), 256, 0, stream>>>(Q, n, rows);
+    VR_CHECK_LAUNCH();
+    entry_totals_kernel<<<4, 256, 0, stream>>>(rows, n, totals);
+    VR_CHECK_LAUNCH();
+  }
   KendallOrders ord;
   ord.order[0] = order_xy;
   ord.order[1] = order_y;
@@ -397,6 +647,12 @@ extern "C" int vr_kendall_tau_a(const float* rdmA, const float* rdmB, int n, int
     dim3 pg((words + 255) / 256 < 64 ? (words + 255) / 256 : 64, rb);
     pair_mask_kernel<<<pg, 256, (size_t)(W + 1) * 4, stream>>>(masks + (size_t)r0 * W, rb, n, W, words, pairbits);
     VR_CHECK_LAUNCH();
+    if (complement) {
+      complement_bits_kernel<<<(words + 255) / 256, 256, 0, stream>>>(pairbits, words, (uint32_t)N, rb);
+      VR_CHECK_LAUNCH();
+      dropped_entry_sums_kernel<<<rb, 256, 0, stream>>>(masks + (size_t)r0 * W, W, n, Q, rows, drop, sub);
+      VR_CHECK_LAUNCH();
+    }
     kept_words_kernel<<<dim3(nchunks, rb, 2), 256, 0, stream>>>(ord, pairbits, words, (uint32_t)N, G, tables, chunk_tot, nchunks);
     VR_CHECK_LAUNCH();
     chunk_scan_kernel<<<dim3(rb, 2), 1024, 0, stream>>>(chunk_tot, nchunks, counts);
@@ -414,7 +670,8 @@ extern "C" int vr_kendall_tau_a(const float* rdmA, const float* rdmB, int n, int
       VR_CHECK_LAUNCH();
       uint32_t* t = src; src = dst; dst = t;
     }
-    kendall_finish_kernel<<<(rb + 63) / 64, 64, 0, stream>>>(acc, counts, nan_flag, rb, out + r0);
+    if (complement) kendall_finish_complement_kernel<<<(rb + 63) / 64, 64, 0, stream>>>(acc, counts, totals, sub, (unsigned long long)N, nan_flag, rb, out + r0);
+    else kendall_finish_kernel<<<(rb + 63) / 64, 64, 0, stream>>>(acc, counts, nan_flag, rb, out + r0);
     VR_CHECK_LAUNCH();
   }
   return VR_OK;

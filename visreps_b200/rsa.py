@@ -343,8 +343,12 @@ def _spearman_sweep_grouped(model: Sequence[PresortedRDM], neural: Sequence[Pres
 
 
 def compare_grouped(model: Sequence[PresortedRDM], neural: Sequence[PresortedRDM], method: str,
-                    masks: torch.Tensor) -> torch.Tensor:
-    """(nA, nB, R) fp64 device tensor: every model RDM x every neural RDM x every mask."""
+                    masks: torch.Tensor, kept_stimuli: Optional[int] = None) -> torch.Tensor:
+    """(nA, nB, R) fp64 device tensor: every model RDM x every neural RDM x every mask.
+
+    kept_stimuli: how many stimuli a subsample mask keeps, when the caller knows (the bootstrap: int(0.9 n)).  Kendall counts
+    ties and inversions among the DROPPED entries when most are kept (csrc/kendall.cu, complement mode) and among the kept ones
+    otherwise; the answer is the same either way."""
     lib = _lib.load()
     method = method.lower()
     if method not in _METHODS:
@@ -361,6 +365,7 @@ def compare_grouped(model: Sequence[PresortedRDM], neural: Sequence[PresortedRDM
             full = len(ma) == nA and len(mb) == nB
             part = out if full else torch.empty((len(ma), len(mb), R), dtype=torch.float64, device=dev)
             if method == "kendall":
+                _lib.set_option("kendall_complement", 1 if kept_stimuli is None or kept_stimuli * kept_stimuli >= 0.5 * n * n else 0)
                 ws = _lib.workspace(lib.vr_kendall_batch_workspace_bytes(n, R), dev)
                 for ia, a in enumerate(ma):
                     for ib, b in enumerate(mb):
@@ -537,7 +542,8 @@ def bootstrap_rdm_correlation_grouped(model_rdms: Sequence, neural_rdms: Sequenc
     elif replicate_range is not None:
         index_sets = index_sets[replicate_range[0]:replicate_range[1]]
     masks = build_masks(index_sets, n, dev, with_full=True)
-    out = compare_grouped(A, B, method, masks).cpu().numpy()
+    kept = None if isinstance(index_sets, HostMasks) or index_sets is None or len(index_sets) == 0 else int(np.asarray(index_sets).shape[1])
+    out = compare_grouped(A, B, method, masks, kept_stimuli=kept if kept is not None else int(n * SUBSAMPLE_FRACTION)).cpu().numpy()
     return {"point": out[:, :, 0].copy(), "scores": out[:, :, 1:].copy()}
 
 
