@@ -71,9 +71,20 @@ struct SweepJob {
   uint2* rows;
   int n, R, batches, slots, segments;
   uint32_t N, G, Gs;
-  size_t slot_stride;     // bytes between vectors inside a batch block
-  size_t batch_stride;    // bytes between batch blocks
+  size_t slot_stride;     // bytes between the rows of two vectors
+  size_t batch_stride;    // bytes between the rows of two batches
+  size_t group_stride;    // bytes between the rows of two consecutive 32-groups
+  int batch_inner;        // layout [slot][g][batch][lane] instead of [batch][slot][g][lane]
 };
+// Row {kept, T} x 32 lanes of (batch, vector slot, 32-group g).
+__host__ __device__ inline uint2* job_row(const SweepJob& J, size_t batch, size_t slot, size_t g) {
+  return reinterpret_cast<uint2*>(reinterpret_cast<char*>(J.rows) + batch * J.batch_stride + slot * J.slot_stride + g * J.group_stride);
+}
+// Two vectors (one pair of RDMs) and several batches -- the stress shape: 50 M pairs, tables of 400 MB per (vector, batch), far
+// beyond L2 -- are laid out batch-innermost: the rows of all batches for one (vector, group) are contiguous, so the sweep, which
+// then walks the batches of a pair in its inner loop, reads one 256 x batches byte burst per lookup instead of `batches` row
+// reads in DRAM pages hundreds of MB apart.
+static inline bool sweep_batch_inner(int slots, int64_t batches) { return slots == 2 && batches >= 2 && batches <= 8; }
 // Count segments per (vector, batch): 32 warps x z CTAs, z chosen so that a job with few (vector, batch) pairs -- the
 // stress shape with a handful of masks -- still fills the machine.
 constexpr int kCountCtasRows = 16;
@@ -105,8 +116,16 @@ static inline SweepJob sweep_job_view(void* mem, int n, int slots, int R) {
   j.tie = reinterpret_cast<long long*>(p); p += arena_bytes((size_t)slots * j.batches * 32, 8);
   j.seg = reinterpret_cast<uint32_t*>(p); p += arena_bytes((size_t)slots * j.batches * j.segments * 32, 4);
   j.rows = reinterpret_cast<uint2*>(p);
-  j.slot_stride = (size_t)j.Gs * 256;
-  j.batch_stride = j.slot_stride * slots;
+  j.batch_inner = sweep_batch_inner(slots, j.batches) ? 1 : 0;
+  if (j.batch_inner) {
+    j.batch_stride = 256;
+    j.group_stride = (size_t)256 * j.batches;
+    j.slot_stride = (size_t)j.Gs * j.group_stride;
+  } else {
+    j.group_stride = 256;
+    j.slot_stride = (size_t)j.Gs * 256;
+    j.batch_stride = j.slot_stride * slots;
+  }
   return j;
 }
 
@@ -228,7 +247,6 @@ count_rows_kernel(const __grid_constant__ BlobPtrs blobs, int slot0, const __gri
   for (uint32_t s = 0; s < seg; ++s) running += segs[(size_t)s * 32 + lane];
   const uint32_t nr = J.nk[batch * 32 + lane];
   const uint32_t bias = kDevBias - nr;
-  uint2* rows = J.rows + ((size_t)batch * J.slots + (slot0 + v)) * J.Gs * 32;
   for (uint32_t g0 = g_lo; g0 < g_hi; g0 += 4u) {
     uint32_t bits[4];
 #pragma unroll
@@ -236,13 +254,13 @@ count_rows_kernel(const __grid_constant__ BlobPtrs blobs, int slot0, const __gri
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const uint32_t K = bit_transpose32(bits[q], lane);          // lane r: kept word of replicate r for the group
-      if (g0 + q < g_hi) rows[(size_t)(g0 + q) * 32 + lane] = make_uint2(K, 2u * running + bias);
+      if (g0 + q < g_hi) job_row(J, batch, slot0 + v, g0 + q)[lane] = make_uint2(K, 2u * running + bias);
       running += __popc(K);
     }
   }
   // the sentinel row behind the last group: C = N_r (runs that end at N exactly on a group boundary read it)
-  if (g_hi == J.G && g_lo < g_hi) rows[(size_t)J.G * 32 + lane] = make_uint2(0u, 2u * running + bias);
-  if (J.G == 0 && seg == 0) rows[lane] = make_uint2(0u, bias);
+  if (g_hi == J.G && g_lo < g_hi) job_row(J, batch, slot0 + v, J.G)[lane] = make_uint2(0u, 2u * running + bias);
+  if (J.G == 0 && seg == 0) job_row(J, batch, slot0 + v, 0)[lane] = make_uint2(0u, bias);
 }
 
 // ---- tie sums ---------------------------------------------------------------------------------------------------
@@ -255,7 +273,6 @@ tie_sums_kernel(const __grid_constant__ BlobPtrs blobs, int slot0, const __grid_
   const unsigned lane = lane_id();
   const int v = blockIdx.y, batch = blockIdx.z;
   PresortView blob = presort_view(const_cast<void*>(blobs.p[v]), J.n);
-  const uint2* rows = J.rows + ((size_t)batch * J.slots + (slot0 + v)) * J.Gs * 32;
   Acc acc = 0;
   const uint32_t warps = gridDim.x * 8u;
   for (uint32_t g = blockIdx.x * 8u + (threadIdx.x >> 5); g < J.G; g += warps) {
@@ -267,7 +284,7 @@ tie_sums_kernel(const __grid_constant__ BlobPtrs blobs, int slot0, const __grid_
     const uint32_t next_is_head = (H >> 1) | (first_next << 31);
     uint32_t M = H & ~next_is_head & valid;                                // heads of runs with two or more members
     if (M == 0u) continue;
-    const uint2 row = rows[(size_t)g * 32 + lane];
+    const uint2 row = job_row(J, batch, slot0 + v, g)[lane];
     while (M) {
       const uint32_t s = __ffs(M) - 1u;
       M &= M - 1u;
@@ -278,7 +295,7 @@ tie_sums_kernel(const __grid_constant__ BlobPtrs blobs, int slot0, const __grid_
         t = __popc(row.x & ((e == 32u ? 0xFFFFFFFFu : ((1u << e) - 1u)) & ~((1u << s) - 1u)));
       } else {
         const uint32_t e = __ldg(blob.next_head + g + 1u);                // global position of the run's end
-        const uint2 re = rows[(size_t)(e >> 5) * 32 + lane];
+        const uint2 re = job_row(J, batch, slot0 + v, e >> 5)[lane];
         const uint32_t ce2 = re.y + 2u * __popc(shl_clamp32(re.x, 32u - (e & 31u)));     // 2 C(e) + const
         const uint32_t cs2 = row.y + 2u * __popc(shl_clamp32(row.x, 32u - s));           // 2 C(s) + const
         t = (ce2 - cs2) >> 1;
@@ -557,6 +574,158 @@ sweep_kernel(const __grid_constant__ SweepArgs A) {
     }
 }
 
+// ---- one pair of vectors, batch-innermost rows (sweep_batch_inner) -----------------------------------------------------
+// A warp takes a canonical pair and walks ALL batches of the job for it: the pair's run words are decoded once, and the rows of the
+// batches for one (vector, group) are one contiguous burst.  grid (splits), kSweepThreads; each warp a contiguous share of pairs.
+constexpr int kPairBatches = 8;
+struct SweepPairArgs {
+  SweepVec vec[2];
+  int slot[2];
+  int n;
+  uint32_t N, sbits;
+  SweepJob job;
+  int splits;
+  void* partial;                 // [batch][split][1][32]
+  int exact;
+};
+// The run [s, e) of a pair from its run word (the head tables only for runs the word cannot hold).
+template <bool kCompact>
+__device__ __forceinline__ void run_bounds(uint32_t w, const SweepVec& V, uint32_t sbits, uint32_t& s, uint32_t& e) {
+  if (kCompact) {
+    const uint32_t gs = (w & kRunOffMask) >> 3, shlo = w >> kRunShloShift, she = (w >> kRunSheShift) & 63u;
+    if (shlo != 0u) {
+      s = gs * 32u + (32u - shlo);
+      if (w & kRunSingleBit) e = s + 1u;
+      else if (w & kRunCrossBit) e = (gs + 1u) * 32u + (32u - she);
+      else e = gs * 32u + (32u - she);                                          // she = 0: the group's end
+    } else {
+      const uint32_t ls = she - 1u;
+      s = gs * 32u + ls;
+      const uint32_t above = ls == 31u ? 0u : (__ldg(V.head_bits + gs) >> (ls + 1u));
+      e = above ? s + (uint32_t)__ffs(above) : __ldg(V.next_head + gs + 1);
+    }
+  } else {
+    const uint32_t smask = (1u << sbits) - 1u, esc = (1u << (32u - sbits)) - 1u;
+    const uint32_t len1 = w >> sbits;
+    s = w & smask;
+    e = s + len1 + 1u;
+    if (len1 == esc) {
+      const uint32_t g = s >> 5, ls = s & 31u;
+      const uint32_t above = ls == 31u ? 0u : (__ldg(V.head_bits + g) >> (ls + 1u));
+      e = above ? s + (uint32_t)__ffs(above) : __ldg(V.next_head + g + 1);
+    }
+  }
+}
+
+// Per pair and batch: dev + 2^31 = T(gs) + (T(ge) - T(gs)) / 2 + popc(kept(gs) below s) + popc(kept(ge) below e), ge the group
+// of position e - 1 -- one formula for every run shape; the two rows coincide unless the run leaves its first group.
+template <bool kCompact>
+__global__ void __launch_bounds__(kSweepThreads, 2)
+sweep_pair_kernel(const __grid_constant__ SweepPairArgs A) {
+  __shared__ uint32_t kws[kSweepWarps][kPairBatches][32];                       // kept words of the block's pairs, per batch
+  __shared__ unsigned long long red[kSweepWarps][32];
+  const unsigned lane = lane_id();
+  const int warp = threadIdx.x >> 5;
+  const SweepJob& J = A.job;
+  const int nb = J.batches;                                                   // <= kPairBatches
+  const int sp = blockIdx.x;
+  const uint32_t per = (A.N + A.splits - 1) / A.splits;
+  const uint32_t c_lo = min(A.N, sp * per), c_hi = min(A.N, c_lo + per);
+  const uint32_t wper = ((c_hi - c_lo) + kSweepWarps - 1) / kSweepWarps;
+  const uint32_t p_lo = min(c_hi, c_lo + warp * wper), p_hi = min(c_hi, p_lo + wper);
+  const char* const rows0 = reinterpret_cast<const char*>(J.rows) + (size_t)A.slot[0] * J.slot_stride + lane * 8;
+  const char* const rows1 = reinterpret_cast<const char*>(J.rows) + (size_t)A.slot[1] * J.slot_stride + lane * 8;
+  double acc[kPairBatches];
+#pragma unroll
+  for (int bb = 0; bb < kPairBatches; ++bb) acc[bb] = 0.0;
+
+  for (uint32_t p0 = p_lo; p0 < p_hi; p0 += 32u) {
+    const uint32_t cnt = min(32u, p_hi - p0);
+    const uint32_t p = min(p0 + lane, A.N - 1u);
+    // lane = pair: run bounds of both vectors, kept words of every batch
+    uint32_t g_l[4], m_l[4];                                                    // {gs, ge, below-s mask, below-e mask} x {A, B}
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      uint32_t s_, e_;
+      run_bounds<kCompact>(__ldg(A.vec[v].runs + p), A.vec[v], A.sbits, s_, e_);
+      const uint32_t ge = (e_ - 1u) >> 5, le = e_ - ge * 32u;                   // le in 1..32
+      g_l[2 * v] = s_ >> 5; g_l[2 * v + 1] = ge;
+      m_l[2 * v] = (1u << (s_ & 31u)) - 1u;
+      m_l[2 * v + 1] = le >= 32u ? 0xFFFFFFFFu : (1u << le) - 1u;
+    }
+    {
+      const uint32_t i = triu_row(p, (uint32_t)A.n);
+      const uint32_t j = p - i * (2u * A.n - i - 1u) / 2u + i + 1u;
+      __syncwarp();
+#pragma unroll
+      for (int bb = 0; bb < kPairBatches; ++bb)
+        if (bb < nb) kws[warp][bb][lane] = __ldg(J.maskT + (size_t)bb * A.n + i) & __ldg(J.maskT + (size_t)bb * A.n + j);
+      __syncwarp();
+    }
+#pragma unroll 1
+    for (uint32_t k = 0; k < cnt; ++k) {
+      uint32_t g[4], m[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { g[q] = __shfl_sync(0xffffffffu, g_l[q], k); m[q] = __shfl_sync(0xffffffffu, m_l[q], k); }
+      const char* r0s = rows0 + (size_t)g[0] * J.group_stride;
+      const char* r1s = rows1 + (size_t)g[2] * J.group_stride;
+      uint2 a0[kPairBatches], a1[kPairBatches], b0[kPairBatches], b1[kPairBatches];
+#pragma unroll
+      for (int bb = 0; bb < kPairBatches; ++bb)
+        if (bb < nb) { a0[bb] = ldg_row(r0s + (size_t)bb * 256); b0[bb] = ldg_row(r1s + (size_t)bb * 256); }
+      if (g[1] != g[0]) {
+        const char* r0e = rows0 + (size_t)g[1] * J.group_stride;
+#pragma unroll
+        for (int bb = 0; bb < kPairBatches; ++bb) if (bb < nb) a1[bb] = ldg_row(r0e + (size_t)bb * 256);
+      } else {
+#pragma unroll
+        for (int bb = 0; bb < kPairBatches; ++bb) a1[bb] = a0[bb];
+      }
+      if (g[3] != g[2]) {
+        const char* r1e = rows1 + (size_t)g[3] * J.group_stride;
+#pragma unroll
+        for (int bb = 0; bb < kPairBatches; ++bb) if (bb < nb) b1[bb] = ldg_row(r1e + (size_t)bb * 256);
+      } else {
+#pragma unroll
+        for (int bb = 0; bb < kPairBatches; ++bb) b1[bb] = b0[bb];
+      }
+#pragma unroll
+      for (int bb = 0; bb < kPairBatches; ++bb)
+        if (bb < nb) {
+          const bool keep = (kws[warp][bb][k] >> lane) & 1u;
+          const uint32_t dA = a0[bb].y + ((a1[bb].y - a0[bb].y) >> 1) + __popc(a0[bb].x & m[0]) + __popc(a1[bb].x & m[1]);
+          const uint32_t dB = b0[bb].y + ((b1[bb].y - b0[bb].y) >> 1) + __popc(b0[bb].x & m[2]) + __popc(b1[bb].x & m[3]);
+          acc[bb] = fma(biased_to_double(keep ? dA : kDevBias), biased_to_double(dB), acc[bb]);
+        }
+    }
+  }
+  unsigned long long* out = static_cast<unsigned long long*>(A.partial);
+#pragma unroll 1
+  for (int bb = 0; bb < nb; ++bb) {
+    double v = 0.0;
+#pragma unroll
+    for (int q = 0; q < kPairBatches; ++q) if (q == bb) v = acc[q];
+    red[warp][lane] = A.exact ? (unsigned long long)(long long)v : (unsigned long long)__double_as_longlong(v);
+    __syncthreads();
+    if (warp == 0) {
+      unsigned long long r;
+      if (A.exact) {
+        long long t = 0;
+#pragma unroll
+        for (int w = 0; w < kSweepWarps; ++w) t += (long long)red[w][lane];
+        r = (unsigned long long)t;
+      } else {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kSweepWarps; ++w) t += __longlong_as_double((long long)red[w][lane]);
+        r = (unsigned long long)__double_as_longlong(t);
+      }
+      out[((size_t)bb * A.splits + sp) * 32 + lane] = r;
+    }
+    __syncthreads();
+  }
+}
+
 // rho for every (a, c, replicate): slice sums added in slice order (int64 when exact), then
 // sum(dev_a dev_c) / (sqrt(ss_a) sqrt(ss_c)).  grid (batches, NA * NB), 32 threads.
 struct FinalizeArgs {
@@ -571,9 +740,8 @@ struct FinalizeArgs {
   int64_t strideA, strideB;
   int exact;
   int validA, validB;              // vectors that are not padding aliases
-  const uint2* rows;               // job rows (per-replicate NaN test)
-  int slots;
-  uint32_t Gs, N;
+  SweepJob job;                    // row addressing (per-replicate NaN test)
+  uint32_t N;
 };
 __global__ void __launch_bounds__(32)
 sweep_finalize_kernel(const __grid_constant__ FinalizeArgs F) {
@@ -604,10 +772,9 @@ sweep_finalize_kernel(const __grid_constant__ FinalizeArgs F) {
     }
     const PresortHeader* hdr = static_cast<const PresortHeader*>(blob);
     if (hdr->has_nan) {                              // NaN only for a replicate that keeps a NaN entry (rsa.py:123-125)
-      const uint2* rows = F.rows + ((size_t)b * F.slots + slot) * F.Gs * 32;
       const uint32_t n_kept = F.nk[r];
       const uint32_t kn = kept_nans(hdr, F.N, n_kept, [&](uint32_t x) {
-        const uint2 e = rows[(size_t)(x >> 5) * 32 + lane];
+        const uint2 e = job_row(F.job, b, slot, x >> 5)[lane];
         return ((e.y - kDevBias + n_kept) >> 1) + (uint32_t)__popc(e.x & ((1u << (x & 31u)) - 1u)); });
       if (kn != 0u) ss = nan;
     }
@@ -687,7 +854,7 @@ extern "C" int vr_spearman_job_init(const uint32_t* masks, int n, int R, int slo
   VR_REQUIRE(n >= 2 && n <= VR_MAX_STIMULI && R >= 1 && slots >= 1, "vr_spearman_job_init: bad sizes n=%d R=%d slots=%d", n, R, slots);
   if (job_bytes < sweep_job_bytes(n, slots, R)) { set_error("vr_spearman_job_init: job buffer %zu < %zu", job_bytes, sweep_job_bytes(n, slots, R)); return VR_ERR_WORKSPACE; }
   SweepJob J = sweep_job_view(job, n, slots, R);
-  VR_REQUIRE((size_t)slots * J.slot_stride < ((size_t)1 << 32), "vr_spearman_job_init: %d vectors x %u groups exceed the 4 GB batch block", slots, J.Gs);
+  VR_REQUIRE(J.batch_inner || (size_t)slots * J.slot_stride < ((size_t)1 << 32), "vr_spearman_job_init: %d vectors x %u groups exceed the 4 GB batch block", slots, J.Gs);
   const int W = vr_mask_words(n);
   ProfScope prof(F_KEPT, stream);
   sweep_masks_kernel<<<dim3((n + 255) / 256, J.batches), 256, 0, stream>>>(masks, R, n, W, J.maskT);
@@ -768,6 +935,34 @@ extern "C" int vr_spearman_job_sweep(void* job, int n, int R, int slots, const v
   for (int k = 0; k < nB; ++k) VR_REQUIRE(slotsB_host[k] >= 0 && slotsB_host[k] < slots && blobsB_host[k], "vr_spearman_job_sweep: bad B slot");
   void* partial = ws;
   ProfScope prof(F_RANK_FUSED, stream);
+  if (J.batch_inner) {
+    // (slots == 2: every sweep of this job is one vector against one vector)
+    VR_REQUIRE(J.batches <= kPairBatches, "vr_spearman_job_sweep: internal: %d batches in a batch-inner job", J.batches);
+    for (int a = 0; a < nA; ++a)
+      for (int c = 0; c < nB; ++c) {
+        const int splits = sweep_splits(J.N, J.batches, exact, 2);
+        SweepPairArgs pa{};
+        const void* bl[2] = {blobsA_host[a], blobsB_host[c]};
+        const int sl[2] = {slotsA_host[a], slotsB_host[c]};
+        for (int k = 0; k < 2; ++k) {
+          PresortView pv = presort_view(const_cast<void*>(bl[k]), n);
+          pa.vec[k].runs = pv.runs; pa.vec[k].head_bits = pv.head_bits; pa.vec[k].next_head = pv.next_head; pa.vec[k].row_base = 0u;
+          pa.slot[k] = sl[k];
+        }
+        pa.n = n; pa.N = J.N; pa.sbits = run_sbits(J.N); pa.job = J; pa.splits = splits; pa.partial = partial; pa.exact = exact ? 1 : 0;
+        if (compact) sweep_pair_kernel<true><<<splits, kSweepThreads, 0, stream>>>(pa);
+        else sweep_pair_kernel<false><<<splits, kSweepThreads, 0, stream>>>(pa);
+        VR_CHECK_LAUNCH();
+        FinalizeArgs fin{};
+        fin.partial = static_cast<const unsigned long long*>(ws); fin.splits = splits; fin.nA = 1; fin.nB = 1; fin.R = R; fin.batches = J.batches;
+        fin.nk = J.nk; fin.tie = J.tie; fin.slotA[0] = sl[0]; fin.slotB[0] = sl[1]; fin.blobA[0] = bl[0]; fin.blobB[0] = bl[1];
+        fin.out = out + (int64_t)a * strideA + (int64_t)c * strideB; fin.strideA = strideA; fin.strideB = strideB; fin.exact = exact ? 1 : 0;
+        fin.validA = 1; fin.validB = 1; fin.job = J; fin.N = J.N;
+        sweep_finalize_kernel<<<dim3(J.batches, 1), 32, 0, stream>>>(fin);
+        VR_CHECK_LAUNCH();
+      }
+    return VR_OK;
+  }
   for (int a0 = 0; a0 < nA; a0 += tile_a) {
     const int na = nA - a0 < tile_a ? nA - a0 : tile_a;
     for (int b0 = 0; b0 < nB; b0 += tile_b) {
@@ -790,7 +985,7 @@ extern "C" int vr_spearman_job_sweep(void* job, int n, int R, int slots, const v
       if (rc != VR_OK) return rc;
       fin.partial = static_cast<const unsigned long long*>(ws); fin.splits = splits; fin.nA = pa; fin.nB = pb; fin.R = R; fin.batches = J.batches; fin.nk = J.nk; fin.tie = J.tie;
       fin.out = out + (int64_t)a0 * strideA + (int64_t)b0 * strideB; fin.strideA = strideA; fin.strideB = strideB; fin.exact = exact ? 1 : 0;
-      fin.validA = na; fin.validB = nb; fin.rows = J.rows; fin.slots = J.slots; fin.Gs = J.Gs; fin.N = J.N;
+      fin.validA = na; fin.validB = nb; fin.job = J; fin.N = J.N;
       sweep_finalize_kernel<<<dim3(J.batches, pa * pb), 32, 0, stream>>>(fin);
       VR_CHECK_LAUNCH();
     }
