@@ -42,6 +42,14 @@ print(f"   RDM max-abs error vs fp64 on 64 rows x {n} columns: {err:.3e}")
 assert err <= 1e-5, err
 del x, truth
 b = t("compute_rdm(neural, V=2000)", lambda: vb.compute_rdm(y))
+iu = torch.triu_indices(n, n, 1, device=dev)
+for nm, m in (("model", a), ("neural", b)):
+    v = m[iu[0], iu[1]]
+    u, c = torch.unique(v, return_counts=True)
+    print(f"   {nm} RDM: {v.numel()} entries in [{float(v.min()):.4f}, {float(v.max()):.4f}], {u.numel()} distinct values, "
+          f"{100.0 * float(c[c > 32].sum()) / v.numel():.1f} % of the entries in runs longer than 32")
+    del v, u, c
+del iu
 pa = t("presort(model)", lambda: vrsa.PresortedRDM(a))
 pb = t("presort(neural)", lambda: vrsa.PresortedRDM(b))
 idx = vrsa.draw_index_sets(n, B, 42)

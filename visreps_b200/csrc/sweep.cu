@@ -673,19 +673,22 @@ sweep_pair_kernel(const __grid_constant__ SweepPairArgs A) {
 #pragma unroll
       for (int bb = 0; bb < kPairBatches; ++bb)
         if (bb < nb) { a0[bb] = ldg_row(r0s + (size_t)bb * 256); b0[bb] = ldg_row(r1s + (size_t)bb * 256); }
+      // every load is issued before anything waits on one (the copies below would otherwise serialise the two vectors)
       if (g[1] != g[0]) {
         const char* r0e = rows0 + (size_t)g[1] * J.group_stride;
 #pragma unroll
         for (int bb = 0; bb < kPairBatches; ++bb) if (bb < nb) a1[bb] = ldg_row(r0e + (size_t)bb * 256);
-      } else {
-#pragma unroll
-        for (int bb = 0; bb < kPairBatches; ++bb) a1[bb] = a0[bb];
       }
       if (g[3] != g[2]) {
         const char* r1e = rows1 + (size_t)g[3] * J.group_stride;
 #pragma unroll
         for (int bb = 0; bb < kPairBatches; ++bb) if (bb < nb) b1[bb] = ldg_row(r1e + (size_t)bb * 256);
-      } else {
+      }
+      if (g[1] == g[0]) {
+#pragma unroll
+        for (int bb = 0; bb < kPairBatches; ++bb) a1[bb] = a0[bb];
+      }
+      if (g[3] == g[2]) {
 #pragma unroll
         for (int bb = 0; bb < kPairBatches; ++bb) b1[bb] = b0[bb];
       }
