@@ -78,6 +78,35 @@ def test_sweep_run_shapes_long_runs_cross_group_and_constant(dev):
     assert abs(sweep[0, 1, 0] - want) <= 1e-9 and sweep[0, 1, 0] == sweep[1, 0, 0]
 
 
+@pytest.mark.parametrize("n,R", [(66, 40), (66, 256), (300, 70), (2100, 40)])
+def test_one_pair_jobs_take_the_batch_inner_tables(n, R, dev):
+    """One vector against one vector with 33-256 masks: rows are laid out batch-innermost and `sweep_pair_kernel` walks all
+    batches of a pair (sweep.cu: sweep_batch_inner).  Every run shape (single, inside a group, ending in the next group, longer
+    than a group, longer than the run word holds, at the very end), compact (n <= 2048) and general run words; same bits as
+    the legacy engine, which never sees that layout."""
+    N = n * (n - 1) // 2
+    rs = np.random.RandomState(n + R)
+    base = np.arange(N, dtype=np.float32)
+    v1 = base.copy(); v1[20:45] = 20.0; v1[60:70] = 60.0; v1[100:400] = 100.0; v1[N - 3:] = float(N)
+    v2 = np.floor(base / 31.0).astype(np.float32)
+    v3 = rs.standard_normal(N).astype(np.float32)
+    v4 = np.round(rs.standard_normal(N), 2 if n < 1000 else 3).astype(np.float32)
+    perm = rs.permutation(N)
+    vecs = [v1[perm], v2[rs.permutation(N)], v3, v4]
+    pres = [vrsa.PresortedRDM(_rdm_from_vector(v, n, dev)) for v in vecs]
+    masks = vrsa.build_masks(vrsa.draw_index_sets(n, R - 1, 11), n, dev, with_full=True)
+    for i, j in ((0, 1), (1, 2), (2, 3), (3, 0)):
+        sweep, legacy = _both_engines([pres[i]], [pres[j]], masks)
+        assert sweep.shape == (1, 1, R)
+        if N ** 3 < 9e18:
+            np.testing.assert_array_equal(sweep, legacy)
+        else:
+            np.testing.assert_allclose(sweep, legacy, atol=1e-12, rtol=0)
+    want = orc.rdm_compare(cases.vector_to_rdm(vecs[0], n), cases.vector_to_rdm(vecs[1], n), correlation="Spearman")
+    got = vrsa.compare_grouped([pres[0]], [pres[1]], "spearman", masks).cpu().numpy()
+    assert abs(got[0, 0, 0] - want) <= 1e-9
+
+
 def test_sweep_tiles_and_group_sizes_agree(dev):
     """Any tiling of the (A, B) grid (options sweep_tile_a / sweep_tile_b, padded instantiations for 3, 5, 6, 7 vectors) gives
     the same bits; more than eight vectors per side are tiled by the library."""
