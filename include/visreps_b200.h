@@ -54,7 +54,11 @@ unsigned long long vr_launch_count(void);
 /* Tuning options, for A/B measurements and for tests that must drive one specific kernel (no reference
  * counterpart).  "syrk_pair": 1 (default) = 256 x 256 pair tiles on CTA pairs for long rows, 0 = single-CTA
  * 128 x 128 tiles only.  "syrk_waves": CTA waves the SYRK's K splits are sized for (default 1).
- * Initial values come from the environment (VR_SYRK_PAIR, VR_SYRK_WAVES). */
+ * Initial values come from the environment (VR_SYRK_PAIR, VR_SYRK_WAVES).
+ * "sweep_tile_a" / "sweep_tile_b" (1..8, default 8): vectors per side of one Spearman sweep launch.
+ * "kendall_tree": 1 (default) = bootstrap jobs of 192 or more masks build the merge tree of the RDM pair once and count every
+ * replicate's discordant pairs without sorting, 2 = always, 0 = never.  "kendall_complement": 1 (default) = the sorting
+ * path counts among the dropped entries of a mask, 0 = among the kept ones.  Every setting gives the same bits. */
 int vr_set_option(const char* name, int value);
 int vr_get_option(const char* name, int* value);
 

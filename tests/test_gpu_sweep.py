@@ -242,8 +242,9 @@ def test_kendall_complement_mode_equals_the_direct_count(dev):
     masks = torch.from_numpy(words.view(np.int32)).to(dev)
     A, B = [vrsa._RawRDM(ra)], [vrsa._RawRDM(rb)]
     out = {}
-    for mode in (1, 0):
-        _lib.set_option("kendall_complement", mode)
+    for mode in (1, 0, "tree"):
+        _lib.set_option("kendall_tree", 2 if mode == "tree" else 0)
+        _lib.set_option("kendall_complement", 0 if mode == "tree" else mode)
         lib = _lib.load()
         ws = _lib.workspace(lib.vr_kendall_batch_workspace_bytes(n, masks.shape[0]), dev)
         res = torch.empty(masks.shape[0], dtype=torch.float64, device=dev)
@@ -251,7 +252,9 @@ def test_kendall_complement_mode_equals_the_direct_count(dev):
                                         ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "vr_kendall_tau_a")
         out[mode] = res.cpu().numpy()
     _lib.set_option("kendall_complement", 1)
+    _lib.set_option("kendall_tree", 1)
     np.testing.assert_array_equal(out[1], out[0])
+    np.testing.assert_array_equal(out["tree"], out[0])                 # integer counts in every mode: same bits
     va, vb_ = orc.triu_vector(ra), orc.triu_vector(rb)
     iu = np.triu_indices(n, 1)
     for r, idx in enumerate([np.arange(n)] + sets):
@@ -264,3 +267,34 @@ def test_kendall_complement_mode_equals_the_direct_count(dev):
     big = vb.bootstrap_rdm_correlation(ra, rb, "kendall", n_bootstrap=7, seed=42)
     few = vb.bootstrap_rdm_correlation_grouped([ra], [rb], "kendall", index_sets=np.stack([rs.choice(n, size=30, replace=False) for _ in range(5)]))
     assert len(big[3]) == 7 and few["scores"].shape == (1, 1, 5) and np.isfinite(few["scores"]).all()
+
+
+@pytest.mark.parametrize("n,R,levels", [(20, 5, 3), (66, 40, 7), (300, 70, 25), (300, 70, 100000), (700, 200, 400)])
+def test_kendall_tree_mode_counts_discordant_pairs_without_sorting(n, R, levels, dev):
+    """csrc/kendall.cu tree mode: the merge tree of the RDM pair is built once, replicates ride in the lanes.  Same bits as the
+    sorting path for tiny trees (no merge level), nodes inside one 2048-position segment, nodes stitched from several segments,
+    heavy ties in both vectors, more than 64 replicates (two lane batches per pass) and the automatic choice (R >= 192)."""
+    N = n * (n - 1) // 2
+    rs = np.random.RandomState(n + R)
+    a, b = cases.tied_vectors(N, levels, 31 + n)
+    b = (b + 0.5 * rs.standard_normal(N).astype(np.float32)).round(2 if levels < 1000 else 5).astype(np.float32)
+    ra, rb = cases.vector_to_rdm(a, n).to(dev), cases.vector_to_rdm(b, n).to(dev)
+    masks = vrsa.build_masks(vrsa.draw_index_sets(n, R - 1, 5), n, dev, with_full=True)
+    lib = _lib.load()
+    out = {}
+    try:
+        for mode in (0, 2, 1):
+            _lib.set_option("kendall_tree", mode)
+            ws = _lib.workspace(lib.vr_kendall_batch_workspace_bytes(n, R), dev)
+            res = torch.full((R,), -7.0, dtype=torch.float64, device=dev)
+            l0 = _lib.launch_count()
+            _lib.check(lib.vr_kendall_tau_a(ra.data_ptr(), rb.data_ptr(), n, n, masks.data_ptr(), R, res.data_ptr(),
+                                            ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "vr_kendall_tau_a")
+            out[mode] = res.cpu().numpy()
+    finally:
+        _lib.set_option("kendall_tree", 1)
+    np.testing.assert_array_equal(out[2], out[0])
+    np.testing.assert_array_equal(out[1], out[0])
+    va, vb_ = orc.triu_vector(ra), orc.triu_vector(rb)
+    want = orc.kendall_tau_a(va, vb_)[0]
+    assert abs(out[2][0] - want) <= 1e-6

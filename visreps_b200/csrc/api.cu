@@ -20,8 +20,9 @@ void set_error(const char* fmt, ...) {
 // ---- tuning options ---------------------------------------------------------------------
 static std::atomic<int> g_syrk_pair{[] { const char* e = getenv("VR_SYRK_PAIR"); return e ? atoi(e) : 1; }()};
 static std::atomic<int> g_syrk_waves{[] { const char* e = getenv("VR_SYRK_WAVES"); return e ? atoi(e) : 1; }()};
-static std::atomic<int> g_sweep_tile_a{8}, g_sweep_tile_b{8}, g_kendall_complement{1};
+static std::atomic<int> g_sweep_tile_a{8}, g_sweep_tile_b{8}, g_kendall_complement{1}, g_kendall_tree{1};
 int option_kendall_complement() { return g_kendall_complement.load(std::memory_order_relaxed); }
+int option_kendall_tree() { return g_kendall_tree.load(std::memory_order_relaxed); }
 int option_sweep_tile_a() { return g_sweep_tile_a.load(std::memory_order_relaxed); }
 int option_sweep_tile_b() { return g_sweep_tile_b.load(std::memory_order_relaxed); }
 int option_syrk_pair() { return g_syrk_pair.load(std::memory_order_relaxed); }
@@ -113,6 +114,11 @@ extern "C" int vr_set_option(const char* name, int value) {
   if (!strcmp(name, "syrk_pair")) { vr::g_syrk_pair.store(value); return VR_OK; }
   if (!strcmp(name, "syrk_waves")) { VR_REQUIRE(value >= 1 && value <= 64, "vr_set_option: syrk_waves=%d outside [1, 64]", value); vr::g_syrk_waves.store(value); return VR_OK; }
   if (!strcmp(name, "kendall_complement")) { vr::g_kendall_complement.store(value != 0); return VR_OK; }
+  if (!strcmp(name, "kendall_tree")) {
+    if (value < 0 || value > 2) { vr::set_error("vr_set_option: kendall_tree is 0 (off), 1 (when it pays) or 2 (always)"); return VR_ERR_INVALID; }
+    vr::g_kendall_tree.store(value);
+    return VR_OK;
+  }
   if (!strcmp(name, "sweep_tile_a") || !strcmp(name, "sweep_tile_b")) {
     VR_REQUIRE(value >= 1 && value <= 8, "vr_set_option: %s=%d outside [1, 8]", name, value);
     (name[11] == 'a' ? vr::g_sweep_tile_a : vr::g_sweep_tile_b).store(value);
@@ -126,6 +132,7 @@ extern "C" int vr_get_option(const char* name, int* value) {
   if (!strcmp(name, "syrk_pair")) { *value = vr::option_syrk_pair(); return VR_OK; }
   if (!strcmp(name, "syrk_waves")) { *value = vr::option_syrk_waves(); return VR_OK; }
   if (!strcmp(name, "kendall_complement")) { *value = vr::option_kendall_complement(); return VR_OK; }
+  if (!strcmp(name, "kendall_tree")) { *value = vr::option_kendall_tree(); return VR_OK; }
   if (!strcmp(name, "sweep_tile_a")) { *value = vr::option_sweep_tile_a(); return VR_OK; }
   if (!strcmp(name, "sweep_tile_b")) { *value = vr::option_sweep_tile_b(); return VR_OK; }
   vr::set_error("vr_get_option: unknown option '%s'", name);

@@ -18,6 +18,7 @@ int option_syrk_pair();
 int option_syrk_waves();
 int option_sweep_tile_a();   // vectors per side in one Spearman sweep launch (1..8)
 int option_sweep_tile_b();
+int option_kendall_tree();         // Kendall bootstrap: the once-per-pair merge tree (sort-free replicates): 0 off, 1 when it pays, 2 always
 int option_kendall_complement();   // Kendall bootstrap: count among the dropped entries (1, default) or the kept ones (0)
 
 // ---- built-in stage profiler (CUDA events on the launching stream) ---------------------

@@ -152,7 +152,7 @@ kept_finish_kernel(uint2* __restrict__ tables, const uint32_t* __restrict__ chun
   __syncthreads();
   e.y += s_warp[warp];
   if (g < G) tab[g] = e;
-  if (o == 0 && g < G) {
+  if (o == 0 && g < G && cy) {
     uint32_t* __restrict__ out = cy + (int64_t)r * cy_stride;
     uint32_t w = e.x, pos = e.y;
     while (w) { const int b = __ffs(w) - 1; w &= w - 1u; out[pos++] = yseq[g * 32u + b]; }
@@ -461,6 +461,346 @@ dropped_entry_sums_kernel(const uint32_t* __restrict__ masks, int W, int n, cons
     sub[(size_t)r * 4 + threadIdx.x] = t;
   }
 }
+// ---- tree mode ---------------------------------------------------------------------------------------------------
+// The bottom-up merge sort of the y keys in (x, y) order has the same shape for every replicate: the sorted order of a tree
+// node's kept members is a subsequence of the node's full sorted order.  So the tree is built ONCE per RDM pair -- for every
+// level the entry (as its stimulus pair) at each merged position and one bit telling which child it came from -- and a replicate
+// never sorts: its discordant pairs at a node are the pairs (right-child member, left-child member), both kept, with the right
+// one first in the node's merged order (a left member goes before an equal right member, so ties in y never count).
+// Replicates ride in the lanes (lane = replicate, 32 per batch): the kept bits of 32 merged positions are one AND of two
+// transposed-mask words per position and a 32 x 32 bit transpose; per 32 positions and replicate the count is
+//     (kept right members so far in the node) * popc(L) + cross(R, L),      cross(R, L) = sum_{i<j} R_i L_j,
+// cross = a byte-prefix dot product (dp4a) + four lookups of a 256 x 256 table.  Inside the base blocks of 32 positions the
+// discordant partners of every position are a precomputed 32-bit mask.  A warp takes a segment of 2048 positions of one level;
+// nodes longer than a segment are stitched from the segments' (right, left) totals by a second small kernel.
+constexpr uint32_t kTreeSegChunks = 64;                         // 32-position chunks per warp segment
+constexpr uint32_t kTreeSeg = kTreeSegChunks * 32u;
+constexpr int kTreeMinReplicates = 192;                         // below this the once-per-pair tree costs more than it saves
+constexpr int kTreeMaxStimuli = 16384;                          // transposed masks of a batch live in shared memory
+
+__device__ __forceinline__ uint32_t tree_pack_pair(uint32_t p, uint32_t n) {
+  const uint32_t i = triu_row(p, n);
+  const uint32_t j = p - i * (2u * n - i - 1u) / 2u + i + 1u;
+  return (i << 16) | j;
+}
+__device__ __forceinline__ uint32_t tree_bit_transpose32(uint32_t w, unsigned lane) {      // row = lane, column = bit
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const uint32_t m = s == 16 ? 0x0000FFFFu : s == 8 ? 0x00FF00FFu : s == 4 ? 0x0F0F0F0Fu : s == 2 ? 0x33333333u : 0x55555555u;
+    const uint32_t x = __shfl_xor_sync(0xffffffffu, w, s);
+    w = (lane & s) ? ((w & ~m) | ((x >> s) & m)) : ((w & m) | ((x << s) & ~m));
+  }
+  return w;
+}
+
+// One warp per block of 32 positions of the (x, y) order: the discordant-partner mask of every position (earlier positions of
+// the block with a strictly greater y), the block sorted by y (stable) as the input of the first merge level, and the
+// stimulus pair of every position.
+__global__ void __launch_bounds__(256)
+tree_base_kernel(const uint32_t* __restrict__ yseq, const uint32_t* __restrict__ order_xy, uint32_t N, uint32_t G, uint32_t n,
+                 uint32_t* __restrict__ gt, uint32_t* __restrict__ vals, uint32_t* __restrict__ pos, uint32_t* __restrict__ ij0) {
+  const uint32_t g = blockIdx.x * 8u + (threadIdx.x >> 5);
+  if (g >= G) return;
+  const unsigned lane = lane_id();
+  const uint32_t k = g * 32u + lane;
+  const uint32_t y = k < N ? yseq[k] : 0xFFFFFFFFu;
+  uint32_t mask = 0, rank = 0;
+#pragma unroll
+  for (int a = 0; a < 32; ++a) {
+    const uint32_t ya = __shfl_sync(0xffffffffu, y, a);
+    if ((unsigned)a < lane && ya > y) mask |= 1u << a;
+    rank += (ya < y || (ya == y && (unsigned)a < lane)) ? 1u : 0u;
+  }
+  gt[k] = mask;
+  vals[g * 32u + rank] = y;                                      // padding (the largest key, the last indices) stays behind N
+  pos[g * 32u + rank] = k;
+  ij0[k] = k < N ? tree_pack_pair(order_xy[k], n) : 0u;
+}
+
+// One merge level over the whole sequence (runs of length L -> 2L), keeping what the replicates need: the stimulus pair at every
+// merged position and the child bit.  `side` must be zero on entry.
+__global__ void __launch_bounds__(256)
+tree_merge_kernel(const uint32_t* __restrict__ vin, const uint32_t* __restrict__ pin, uint32_t N, uint32_t L,
+                  uint32_t* __restrict__ vout, uint32_t* __restrict__ pout, const uint32_t* __restrict__ ij0,
+                  uint32_t* __restrict__ ij, uint32_t* __restrict__ side) {
+  for (uint32_t k = blockIdx.x * 256u + threadIdx.x; k < N; k += gridDim.x * 256u) {
+    const uint32_t v = vin[k], p = pin[k];
+    const uint32_t blk = k / (2u * L) * (2u * L);
+    const uint32_t a1 = min(N, blk + L), b1 = min(N, blk + 2u * L);
+    uint32_t slot;
+    if (k < a1) {
+      uint32_t lo = a1, hi = b1;
+      while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (vin[mid] < v) lo = mid + 1; else hi = mid; }
+      slot = k + (lo - a1);
+    } else {
+      uint32_t lo = blk, hi = a1;
+      while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (vin[mid] <= v) lo = mid + 1; else hi = mid; }
+      slot = blk + (k - a1) + (lo - blk);
+      atomicOr(side + (slot >> 5), 1u << (slot & 31u));
+    }
+    vout[slot] = v;
+    pout[slot] = p;
+    ij[slot] = ij0[p];
+  }
+}
+
+// cross[(r << 8) | l] = number of (i < j) with bit i of r and bit j of l set.
+__global__ void tree_cross_table_kernel(uint8_t* __restrict__ cross) {
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 65536u) return;
+  const uint32_t r = idx >> 8, l = idx & 255u;
+  uint32_t c = 0;
+  for (uint32_t j = 1; j < 8u; ++j) if ((l >> j) & 1u) c += __popc(r & ((1u << j) - 1u));
+  cross[idx] = (uint8_t)c;
+}
+
+// mT[b][i]: bit r = stimulus i kept by replicate 32 b + r of the batch.  grid (ceil(n / 256), batches of 32).
+__global__ void __launch_bounds__(256)
+tree_masks_kernel(const uint32_t* __restrict__ masks, int W, int n, int R, uint32_t* __restrict__ mT) {
+  const int i = blockIdx.x * 256 + threadIdx.x, b = blockIdx.y;
+  if (i >= n) return;
+  uint32_t w = 0;
+  for (int r = 0; r < 32 && b * 32 + r < R; ++r) w |= ((masks[(size_t)(b * 32 + r) * W + (i >> 5)] >> (i & 31)) & 1u) << r;
+  mT[(size_t)b * n + i] = w;
+}
+
+struct TreeArgs {
+  const uint32_t* ij;          // [levels + 1][Np]: (i << 16 | j) of the entry at every position; [0] = the (x, y) order itself
+  const uint32_t* side;        // [levels][G]: bit = the position's entry came from the right child
+  const uint32_t* gt;          // [Np]
+  const uint8_t* cross;        // [65536]
+  const uint32_t* mT;          // [batches][n]
+  uint32_t* segtot;            // [batches][levels][nseg][2][32]: kept right / left members of a segment (levels with long nodes)
+  unsigned long long* acc;     // [rb][4], [3] = discordant pairs
+  uint32_t N, Np, G, nseg;
+  int levels, n, rb;
+};
+__device__ __forceinline__ uint32_t byte_counts(uint32_t x) {      // popcount of every byte
+  x = x - ((x >> 1) & 0x55555555u);
+  x = (x & 0x33333333u) + ((x >> 2) & 0x33333333u);
+  return (x + (x >> 4)) & 0x0F0F0F0Fu;
+}
+
+// grid (ceil((levels + 1) * nseg / 8), batches), 256 threads; dynamic shared memory: the cross table and the batch's masks.
+__global__ void __launch_bounds__(256)
+tree_count_kernel(const __grid_constant__ TreeArgs A) {
+  extern __shared__ __align__(16) unsigned char t_smem[];
+  __shared__ unsigned long long s_red[8][32];
+  uint8_t* s_cross = t_smem;
+  uint32_t* s_mT = reinterpret_cast<uint32_t*>(t_smem + 65536);
+  const int batch = blockIdx.y;
+  for (uint32_t q = threadIdx.x; q < 4096u; q += 256u)
+    reinterpret_cast<uint4*>(s_cross)[q] = __ldg(reinterpret_cast<const uint4*>(A.cross) + q);
+  for (int i = threadIdx.x; i < A.n; i += 256) s_mT[i] = A.mT[(size_t)batch * A.n + i];
+  __syncthreads();
+  const unsigned lane = lane_id();
+  const int warp = threadIdx.x >> 5;
+  const uint32_t seg = blockIdx.x * 8u + warp;
+  const uint32_t lv = seg / A.nseg, s = seg % A.nseg;
+  uint32_t inv = 0;
+  if (lv <= (uint32_t)A.levels) {
+    const uint32_t* __restrict__ ijL = A.ij + (size_t)lv * A.Np;
+    const uint32_t ch0 = s * kTreeSegChunks;
+    auto kept_bits = [&](uint32_t ch) {          // lane r: bit p = position 32 ch + p kept by replicate r
+      const uint32_t k = ch * 32u + lane;
+      uint32_t w = 0;
+      if (k < A.N) { const uint32_t ij = __ldg(ijL + k); w = s_mT[ij >> 16] & s_mT[ij & 0xFFFFu]; }
+      return tree_bit_transpose32(w, lane);
+    };
+    if (lv == 0) {
+      for (uint32_t c = 0; c < kTreeSegChunks && ch0 + c < A.G; ++c) {
+        const uint32_t kw = kept_bits(ch0 + c);
+        const uint32_t g = __ldg(A.gt + (size_t)(ch0 + c) * 32u + lane);
+#pragma unroll
+        for (int l = 1; l < 32; ++l) {
+          const uint32_t gl = __shfl_sync(0xffffffffu, g, l);
+          if ((kw >> l) & 1u) inv += __popc(gl & kw);
+        }
+      }
+    } else {
+      const uint32_t t = lv - 1u;
+      const uint32_t cpn = 2u << t;                                               // chunks per node: 2 L / 32
+      const bool big = cpn > kTreeSegChunks;
+      const uint32_t* __restrict__ sideL = A.side + (size_t)t * A.G;
+      uint32_t carry = 0, ltot = 0;
+      for (uint32_t c = 0; c < kTreeSegChunks && ch0 + c < A.G; ++c) {
+        if (!big && (c & (cpn - 1u)) == 0u) carry = 0;
+        const uint32_t kw = kept_bits(ch0 + c);
+        const uint32_t sd = __ldg(sideL + ch0 + c);
+        const uint32_t R = kw & sd, Lm = kw & ~sd;
+        const uint32_t cr = byte_counts(R), cl = byte_counts(Lm);
+        const uint32_t pl = (cl * 0x01010101u) >> 24;
+        uint32_t x = __dp4a(cr * 0x01010100u, cl, 0u);                           // right members in lower bytes x left members of a byte
+#pragma unroll
+        for (int q = 0; q < 4; ++q) x += s_cross[(((R >> (8 * q)) & 255u) << 8) | ((Lm >> (8 * q)) & 255u)];
+        inv += carry * pl + x;
+        carry += (cr * 0x01010101u) >> 24;
+        ltot += pl;
+      }
+      if (big) {
+        uint32_t* o = A.segtot + ((((size_t)batch * A.levels + t) * A.nseg + s) * 2) * 32;
+        o[lane] = carry;
+        o[32 + lane] = ltot;
+      }
+    }
+  }
+  s_red[warp][lane] = inv;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned long long tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += s_red[w][lane];
+    const int r = batch * 32 + (int)lane;
+    if (tot && r < A.rb) atomicAdd(A.acc + (size_t)r * 4 + 3, tot);
+  }
+}
+
+// Nodes longer than a segment: kept right members of the node's earlier segments x kept left members of each segment.
+// grid (levels, batches), 256 threads, lanes = replicates.  A level with eight or more nodes gives every warp whole nodes;
+// the few long nodes at the top are cut into eight consecutive parts, one per warp, joined through shared memory.
+__global__ void __launch_bounds__(256)
+tree_stitch_kernel(const __grid_constant__ TreeArgs A) {
+  __shared__ unsigned long long s_r[8][32], s_l[8][32];
+  const uint32_t t = blockIdx.x;
+  const int batch = blockIdx.y;
+  const uint32_t cpn = 2u << t;
+  if (cpn <= kTreeSegChunks) return;
+  const uint32_t spn = cpn / kTreeSegChunks;                                        // segments per node
+  const uint32_t nodes = (A.nseg + spn - 1u) / spn;
+  const unsigned lane = lane_id();
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t* __restrict__ tot = A.segtot + (((size_t)batch * A.levels + t) * A.nseg) * 64;
+  unsigned long long inv = 0;
+  if (nodes >= 8u) {
+    for (uint32_t node = warp; node < nodes; node += 8u) {
+      unsigned long long before = 0;
+      const uint32_t s1 = min(A.nseg, (node + 1u) * spn);
+      for (uint32_t s = node * spn; s < s1; ++s) {
+        inv += before * tot[(size_t)s * 64 + 32 + lane];
+        before += tot[(size_t)s * 64 + lane];
+      }
+    }
+  } else {
+    for (uint32_t node = 0; node < nodes; ++node) {
+      const uint32_t s0 = node * spn, s1 = min(A.nseg, s0 + spn);
+      const uint32_t per = (s1 - s0 + 7u) / 8u;
+      const uint32_t lo = min(s1, s0 + warp * per), hi = min(s1, lo + per);
+      unsigned long long before = 0, left = 0;
+      for (uint32_t s = lo; s < hi; ++s) {
+        const unsigned long long l = tot[(size_t)s * 64 + 32 + lane];
+        inv += before * l;
+        left += l;
+        before += tot[(size_t)s * 64 + lane];
+      }
+      __syncthreads();
+      s_r[warp][lane] = before;
+      s_l[warp][lane] = left;
+      __syncthreads();
+      unsigned long long earlier = 0;
+      for (uint32_t w = 0; w < warp; ++w) earlier += s_r[w][lane];
+      inv += earlier * left;
+    }
+  }
+  const int r = batch * 32 + (int)lane;
+  if (inv && r < A.rb) atomicAdd(A.acc + (size_t)r * 4 + 3, inv);
+}
+
+// Run heads of a sorted order as bits: position k starts a run when its run start is k itself.
+__global__ void __launch_bounds__(256)
+tree_heads_kernel(const uint32_t* __restrict__ run_start, uint32_t N, uint32_t G, uint32_t* __restrict__ heads) {
+  const uint32_t k = blockIdx.x * 256u + threadIdx.x;
+  const bool head = k >= N || run_start[k] == k;                       // padding: runs of one
+  const uint32_t w = __ballot_sync(0xffffffffu, head);
+  if ((threadIdx.x & 31u) == 0u && (k >> 5) < G) heads[k >> 5] = w;
+}
+__global__ void __launch_bounds__(256)
+tree_pairs_kernel(const uint32_t* __restrict__ order, uint32_t N, uint32_t Np, uint32_t n, uint32_t* __restrict__ ij) {
+  const uint32_t k = blockIdx.x * 256u + threadIdx.x;
+  if (k < Np) ij[k] = k < N ? tree_pack_pair(order[k], n) : 0u;
+}
+
+// Tied pairs among the kept entries, lanes = replicates: sum over the runs of equal keys of t (t - 1) / 2, t = members kept.
+// Three passes share the kernel: runs of equal x and of equal (x, y) in the (x, y) order, runs of equal y in the y order.
+// A warp takes a segment of 2048 positions and every run that STARTS inside it (following a run that leaves the segment to its
+// end); runs of one member cost nothing.  The pass over equal x also counts the kept entries.
+struct TiesArgs {
+  const uint32_t* ij[3];       // stimulus pairs along the order of each pass
+  const uint32_t* heads[3];    // run-head bits, G words
+  const uint32_t* mT;
+  unsigned long long* acc;     // [rb][4]: [0] tx [1] ty [2] txy
+  uint32_t* counts;            // [rb]: kept entries
+  uint32_t N, G, nseg;
+  int n, rb;
+};
+__global__ void __launch_bounds__(256)
+tree_ties_kernel(const __grid_constant__ TiesArgs A) {
+  extern __shared__ __align__(16) uint32_t tie_mT[];
+  const int batch = blockIdx.y;
+  for (int i = threadIdx.x; i < A.n; i += 256) tie_mT[i] = A.mT[(size_t)batch * A.n + i];
+  __syncthreads();
+  const unsigned lane = lane_id();
+  const int warp = threadIdx.x >> 5;
+  const uint32_t seg = blockIdx.x * 8u + warp;
+  const uint32_t pass = seg / A.nseg, s = seg % A.nseg;
+  unsigned long long ties = 0;
+  uint32_t kept_total = 0;
+  if (pass < 3u) {
+    const uint32_t* __restrict__ ijL = A.ij[pass];
+    const uint32_t* __restrict__ H = A.heads[pass];
+    auto kept_bits = [&](uint32_t ch) {
+      const uint32_t k = ch * 32u + lane;
+      uint32_t w = 0;
+      if (k < A.N) { const uint32_t ij = __ldg(ijL + k); w = tie_mT[ij >> 16] & tie_mT[ij & 0xFFFFu]; }
+      return tree_bit_transpose32(w, lane);
+    };
+    const uint32_t ch0 = s * kTreeSegChunks, ch1 = min(A.G, ch0 + kTreeSegChunks);
+    uint32_t open = 0;                 // kept members so far of the run that is open at the end of the previous chunk
+    bool mine = false;                 // ... and whether that run started inside this segment
+    for (uint32_t ch = ch0; ch < A.G; ++ch) {
+      if (ch >= ch1 && !mine) break;   // past the segment: only to finish a run of ours
+      const uint32_t h = __ldg(H + ch);
+      if (ch >= ch1 && h == 0u) {      // the whole chunk continues our run
+        open += __popc(kept_bits(ch));
+        continue;
+      }
+      const uint32_t kw = kept_bits(ch);
+      if (ch < ch1 && pass == 0u) kept_total += __popc(kw);
+      // positions before the first head continue the open run
+      const uint32_t first = h ? (uint32_t)__ffs(h) - 1u : 32u;
+      const uint32_t cont = first >= 32u ? 0xFFFFFFFFu : ((1u << first) - 1u);
+      open += __popc(kw & cont);
+      if (h == 0u) continue;           // (inside the segment) the run goes on
+      if (mine) ties += (unsigned long long)open * (open - 1u) / 2u;
+      if (ch >= ch1) { mine = false; break; }
+      // runs that start in this chunk: all but the last end here too
+      uint32_t rest = h;
+      while (true) {
+        const uint32_t b = (uint32_t)__ffs(rest) - 1u;
+        rest &= rest - 1u;
+        if (rest == 0u) {              // last run of the chunk: stays open
+          open = __popc(kw & ~((1u << b) - 1u));
+          mine = true;
+          break;
+        }
+        const uint32_t e = (uint32_t)__ffs(rest) - 1u;
+        if (e - b >= 2u) {
+          const uint32_t tcount = __popc(kw & ((1u << e) - (1u << b)));
+          ties += tcount * (tcount - 1u) / 2u;
+        }
+      }
+    }
+    if (mine) ties += (unsigned long long)open * (open - 1u) / 2u;     // the order's last run
+  }
+  const int r = batch * 32 + (int)lane;
+  if (pass < 3u && r < A.rb) {
+    const int slot = pass == 0u ? 0 : pass == 1u ? 2 : 1;
+    if (ties) atomicAdd(A.acc + (size_t)r * 4 + slot, ties);
+    if (kept_total) atomicAdd(A.counts + r, kept_total);
+  }
+}
+
+static int tree_levels(int64_t N) { int l = 0; for (int64_t L = 32; L < N; L <<= 1) ++l; return l; }
+
 // tau-a from the complement: acc[r] / counts[r] describe the DROPPED entries of replicate r.
 __global__ void kendall_finish_complement_kernel(const unsigned long long* __restrict__ acc, const uint32_t* __restrict__ counts,
                                                  const unsigned long long* __restrict__ totals, const unsigned long long* __restrict__ sub,
@@ -509,6 +849,20 @@ static size_t kendall_per_replicate_bytes(int n) {
 }
 constexpr size_t kKendallSlack = 16384;       // 256-byte alignment of the per-batch arrays
 constexpr int kKendallMaxBatch = 64;
+// tree mode: stimulus pairs of every level (+ the base order), child bits, base-block masks, the cross table, the transposed
+// masks and the segment totals of the two 32-replicate batches of a 64-replicate pass
+static size_t kendall_tree_bytes(int n) {
+  const int64_t N = triu_len(n);
+  const size_t Np = (size_t)round_up(N, 32), G = Np / 32, nseg = (G + kTreeSegChunks - 1) / kTreeSegChunks;
+  const size_t levels = (size_t)tree_levels(N);
+  return (levels + 1) * arena_bytes(Np, 4) + arena_bytes(levels * G + 1, 4) + arena_bytes(Np, 4) + arena_bytes(65536, 1) +
+         arena_bytes((size_t)2 * n, 4) + arena_bytes((size_t)2 * (levels + 1) * nseg * 64, 4) +
+         arena_bytes(Np, 4) + 3 * arena_bytes(G, 4) + 4096;          // + stimulus pairs of the y order, run-head bits of the three tie passes
+}
+static bool kendall_tree_wanted(int n, int R) {
+  const int opt = option_kendall_tree();
+  return opt != 0 && n <= kTreeMaxStimuli && (opt == 2 || R >= kTreeMinReplicates);
+}
 
 }  // namespace vr
 
@@ -521,7 +875,7 @@ extern "C" size_t vr_kendall_workspace_bytes(int n) {
 extern "C" size_t vr_kendall_batch_workspace_bytes(int n, int R) {
   if (n < 2 || R < 1) return 256;
   const int rb = R < kKendallMaxBatch ? R : kKendallMaxBatch;
-  return kendall_fixed_bytes(n) + (size_t)rb * kendall_per_replicate_bytes(n) + kKendallSlack;
+  return kendall_fixed_bytes(n) + (size_t)rb * kendall_per_replicate_bytes(n) + kKendallSlack + (kendall_tree_wanted(n, R) ? kendall_tree_bytes(n) : 0);
 }
 
 extern "C" int vr_kendall_tau_a(const float* rdmA, const float* rdmB, int n, int64_t ld, const uint32_t* masks, int R,
@@ -538,8 +892,11 @@ extern "C" int vr_kendall_tau_a(const float* rdmA, const float* rdmB, int n, int
   const uint32_t G = (uint32_t)(Np / 32), words = G;
   const uint32_t nchunks = (G + kChunkGroups - 1) / kChunkGroups;
   const int W = vr_mask_words(n);
+  // tree mode when it pays and the workspace has room for the tree next to at least one replicate
+  const bool tree = kendall_tree_wanted(n, R) &&
+                    ws_bytes >= vr_kendall_workspace_bytes(n) + kendall_tree_bytes(n);
   // as many replicates per batch as the workspace holds (every batch is ~15 launches whatever its size)
-  int Rb = (int)((ws_bytes - kendall_fixed_bytes(n) - kKendallSlack) / kendall_per_replicate_bytes(n));
+  int Rb = (int)((ws_bytes - kendall_fixed_bytes(n) - kKendallSlack - (tree ? kendall_tree_bytes(n) : 0)) / kendall_per_replicate_bytes(n));
   if (Rb > kKendallMaxBatch) Rb = kKendallMaxBatch;
   if (Rb > R) Rb = R;
   if (Rb < 1) Rb = 1;
@@ -567,7 +924,7 @@ extern "C" int vr_kendall_tau_a(const float* rdmA, const float* rdmB, int n, int
   unsigned long long* acc = a.take<unsigned long long>((size_t)Rb * 4);
   uint32_t* counts = a.take<uint32_t>((size_t)2 * Rb);    // kept entries: [0][r] from the (x, y) order, [1][r] from the y order
   uint32_t* nan_flag = a.take<uint32_t>(8);
-  const bool complement = option_kendall_complement() != 0;
+  const bool complement = !tree && option_kendall_complement() != 0;
   uint32_t* qcnt[4] = {nullptr, nullptr, nullptr, nullptr};
   unsigned long long* rows = nullptr;
   unsigned long long* totals = nullptr;
@@ -578,6 +935,22 @@ extern "C" int vr_kendall_tau_a(const float* rdmA, const float* rdmB, int n, int
   totals = a.take<unsigned long long>(8);
   drop = a.take<uint32_t>((size_t)Rb * n);
   sub = a.take<unsigned long long>((size_t)Rb * 4);
+  TreeArgs T{};
+  uint32_t *t_ij = nullptr, *t_side = nullptr, *t_gt = nullptr, *t_mT = nullptr, *t_ijy = nullptr, *t_heads[3] = {nullptr, nullptr, nullptr};
+  uint8_t* t_cross = nullptr;
+  if (tree) {
+    T.levels = tree_levels(N);
+    T.N = (uint32_t)N; T.Np = (uint32_t)Np; T.G = G; T.nseg = (G + kTreeSegChunks - 1) / kTreeSegChunks; T.n = n;
+    t_ij = a.take<uint32_t>((size_t)(T.levels + 1) * Np);
+    t_side = a.take<uint32_t>((size_t)T.levels * G + 1);
+    t_gt = a.take<uint32_t>(Np);
+    t_cross = a.take<uint8_t>(65536);
+    t_mT = a.take<uint32_t>((size_t)2 * n);
+    T.segtot = a.take<uint32_t>((size_t)2 * (T.levels + 1) * T.nseg * 64);
+    T.ij = t_ij; T.side = t_side; T.gt = t_gt; T.cross = t_cross; T.mT = t_mT; T.acc = acc;
+    t_ijy = a.take<uint32_t>(Np);
+    for (int k = 0; k < 3; ++k) t_heads[k] = a.take<uint32_t>(G);
+  }
   if (!a.ok) { set_error("vr_kendall_tau_a: internal workspace plan overflow"); return VR_ERR_WORKSPACE; }
   ProfScope prof(F_KENDALL, stream);
   const unsigned nblk = (unsigned)((N + 255) / 256);
@@ -636,6 +1009,37 @@ extern "C" int vr_kendall_tau_a(const float* rdmA, const float* rdmB, int n, int
     entry_totals_kernel<<<4, 256, 0, stream>>>(rows, n, totals);
     VR_CHECK_LAUNCH();
   }
+  const size_t tree_smem = 65536 + (size_t)n * 4;
+  if (tree) {
+    // the merge tree of the y keys in (x, y) order, once per RDM pair (k0 / v0 / k1 / v1 are free again)
+    static unsigned long long attr_done = 0;
+    static unsigned long long attr_ties = 0;
+    VR_CHECK_CUDA(ensure_dynamic_smem(tree_count_kernel, 65536 + kTreeMaxStimuli * 4, &attr_done));
+    VR_CHECK_CUDA(ensure_dynamic_smem(tree_ties_kernel, kTreeMaxStimuli * 4, &attr_ties));
+    tree_cross_table_kernel<<<256, 256, 0, stream>>>(t_cross);
+    VR_CHECK_LAUNCH();
+    const unsigned pblk = (unsigned)((Np + 255) / 256);
+    tree_heads_kernel<<<pblk, 256, 0, stream>>>(rs_x, (uint32_t)N, G, t_heads[0]);
+    VR_CHECK_LAUNCH();
+    tree_heads_kernel<<<pblk, 256, 0, stream>>>(rs_xy, (uint32_t)N, G, t_heads[1]);
+    VR_CHECK_LAUNCH();
+    tree_heads_kernel<<<pblk, 256, 0, stream>>>(rs_y, (uint32_t)N, G, t_heads[2]);
+    VR_CHECK_LAUNCH();
+    tree_pairs_kernel<<<pblk, 256, 0, stream>>>(order_y, (uint32_t)N, (uint32_t)Np, (uint32_t)n, t_ijy);
+    VR_CHECK_LAUNCH();
+    if (T.levels) VR_CHECK_CUDA(cudaMemsetAsync(t_side, 0, (size_t)T.levels * G * 4, stream));
+    tree_base_kernel<<<(G + 7) / 8, 256, 0, stream>>>(yseq, order_xy, (uint32_t)N, G, (uint32_t)n, t_gt, k0, v0, t_ij);
+    VR_CHECK_LAUNCH();
+    uint32_t *sv = k0, *sp = v0, *dv = k1, *dp = v1;
+    const unsigned eg = nblk < 8u * kNumSMs ? nblk : 8u * kNumSMs;
+    int t = 0;
+    for (uint64_t L = 32; L < (uint64_t)N; L <<= 1, ++t) {
+      tree_merge_kernel<<<eg, 256, 0, stream>>>(sv, sp, (uint32_t)N, (uint32_t)L, dv, dp, t_ij, t_ij + (size_t)(t + 1) * Np, t_side + (size_t)t * G);
+      VR_CHECK_LAUNCH();
+      uint32_t* x = sv; sv = dv; dv = x;
+      x = sp; sp = dp; dp = x;
+    }
+  }
   KendallOrders ord;
   ord.order[0] = order_xy;
   ord.order[1] = order_y;
@@ -644,6 +1048,29 @@ extern "C" int vr_kendall_tau_a(const float* rdmA, const float* rdmB, int n, int
   for (int r0 = 0; r0 < R; r0 += Rb) {
     const int rb = R - r0 < Rb ? R - r0 : Rb;
     VR_CHECK_CUDA(cudaMemsetAsync(acc, 0, (size_t)rb * 4 * sizeof(unsigned long long), stream));
+    if (tree) {
+      const unsigned nb32 = (unsigned)((rb + 31) / 32);                      // <= 2: Rb <= 64
+      T.rb = rb;
+      VR_CHECK_CUDA(cudaMemsetAsync(counts, 0, (size_t)rb * sizeof(uint32_t), stream));
+      tree_masks_kernel<<<dim3((n + 255) / 256, nb32), 256, 0, stream>>>(masks + (size_t)r0 * W, W, n, rb, t_mT);
+      VR_CHECK_LAUNCH();
+      TiesArgs ta{};
+      ta.ij[0] = t_ij; ta.ij[1] = t_ij; ta.ij[2] = t_ijy;
+      for (int k = 0; k < 3; ++k) ta.heads[k] = t_heads[k];
+      ta.mT = t_mT; ta.acc = acc; ta.counts = counts; ta.N = (uint32_t)N; ta.G = G; ta.nseg = T.nseg; ta.n = n; ta.rb = rb;
+      tree_ties_kernel<<<dim3((3u * T.nseg + 7u) / 8u, nb32), 256, (size_t)n * 4, stream>>>(ta);
+      VR_CHECK_LAUNCH();
+      const unsigned segs = (unsigned)(T.levels + 1) * T.nseg;
+      tree_count_kernel<<<dim3((segs + 7) / 8, nb32), 256, tree_smem, stream>>>(T);
+      VR_CHECK_LAUNCH();
+      if (T.levels) {
+        tree_stitch_kernel<<<dim3((unsigned)T.levels, nb32), 256, 0, stream>>>(T);
+        VR_CHECK_LAUNCH();
+      }
+      kendall_finish_kernel<<<(rb + 63) / 64, 64, 0, stream>>>(acc, counts, nan_flag, rb, out + r0);
+      VR_CHECK_LAUNCH();
+      continue;
+    }
     dim3 pg((words + 255) / 256 < 64 ? (words + 255) / 256 : 64, rb);
     pair_mask_kernel<<<pg, 256, (size_t)(W + 1) * 4, stream>>>(masks + (size_t)r0 * W, rb, n, W, words, pairbits);
     VR_CHECK_LAUNCH();
