@@ -269,7 +269,7 @@ def test_kendall_complement_mode_equals_the_direct_count(dev):
     assert len(big[3]) == 7 and few["scores"].shape == (1, 1, 5) and np.isfinite(few["scores"]).all()
 
 
-@pytest.mark.parametrize("n,R,levels", [(20, 5, 3), (66, 40, 7), (300, 70, 25), (300, 70, 100000), (700, 200, 400)])
+@pytest.mark.parametrize("n,R,levels", [(20, 5, 3), (66, 40, 7), (66, 300, 9), (300, 70, 25), (300, 70, 100000), (700, 200, 400)])
 def test_kendall_tree_mode_counts_discordant_pairs_without_sorting(n, R, levels, dev):
     """csrc/kendall.cu tree mode: the merge tree of the RDM pair is built once, replicates ride in the lanes.  Same bits as the
     sorting path for tiny trees (no merge level), nodes inside one 2048-position segment, nodes stitched from several segments,

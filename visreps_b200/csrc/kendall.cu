@@ -474,7 +474,8 @@ dropped_entry_sums_kernel(const uint32_t* __restrict__ masks, int W, int n, cons
 // discordant partners of every position are a precomputed 32-bit mask.  A warp takes a segment of 2048 positions of one level;
 // nodes longer than a segment are stitched from the segments' (right, left) totals by a second small kernel.
 constexpr uint32_t kTreeSegChunks = 64;                         // 32-position chunks per warp segment
-constexpr uint32_t kTreeSeg = kTreeSegChunks * 32u;
+constexpr uint32_t kTiesSegChunks = 8;                          // the tie passes need no stitching: short segments, many warps
+constexpr int kTreeBatch = 256;                                 // replicates per pass: eight lane batches
 constexpr int kTreeMinReplicates = 192;                         // below this the once-per-pair tree costs more than it saves
 constexpr int kTreeMaxStimuli = 16384;                          // transposed masks of a batch live in shared memory
 
@@ -552,6 +553,17 @@ __global__ void tree_cross_table_kernel(uint8_t* __restrict__ cross) {
   uint32_t c = 0;
   for (uint32_t j = 1; j < 8u; ++j) if ((l >> j) & 1u) c += __popc(r & ((1u << j) - 1u));
   cross[idx] = (uint8_t)c;
+}
+
+// counts[r] = entries kept by replicate r = pairs of its kept stimuli.  One warp per replicate.
+__global__ void __launch_bounds__(256)
+tree_kept_kernel(const uint32_t* __restrict__ masks, int W, int R, uint32_t* __restrict__ counts) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= R) return;
+  long long m = 0;
+  for (int w = lane_id(); w < W; w += 32) m += __popc(masks[(size_t)r * W + w]);
+  m = warp_sum_ll(m);
+  if (lane_id() == 0) counts[r] = (uint32_t)(m * (m - 1) / 2);
 }
 
 // mT[b][i]: bit r = stimulus i kept by replicate 32 b + r of the batch.  grid (ceil(n / 256), batches of 32).
@@ -720,18 +732,46 @@ tree_pairs_kernel(const uint32_t* __restrict__ order, uint32_t N, uint32_t Np, u
 }
 
 // Tied pairs among the kept entries, lanes = replicates: sum over the runs of equal keys of t (t - 1) / 2, t = members kept.
-// Three passes share the kernel: runs of equal x and of equal (x, y) in the (x, y) order, runs of equal y in the y order.
-// A warp takes a segment of 2048 positions and every run that STARTS inside it (following a run that leaves the segment to its
-// end); runs of one member cost nothing.  The pass over equal x also counts the kept entries.
+// Pass 0 walks the (x, y) order once for the runs of equal x and of equal (x, y), pass 1 the y order for the runs of equal y.
+// A warp takes a segment of 256 positions and every run that STARTS inside it (following a run that leaves the segment to its
+// end); runs of one member cost nothing, chunks made of them are skipped without looking at the masks.
 struct TiesArgs {
-  const uint32_t* ij[3];       // stimulus pairs along the order of each pass
-  const uint32_t* heads[3];    // run-head bits, G words
+  const uint32_t* ij[2];       // stimulus pairs along the (x, y) order and the y order
+  const uint32_t* heads[3];    // run-head bits, G words: equal x, equal (x, y), equal y
   const uint32_t* mT;
   unsigned long long* acc;     // [rb][4]: [0] tx [1] ty [2] txy
-  uint32_t* counts;            // [rb]: kept entries
   uint32_t N, G, nseg;
   int n, rb;
 };
+struct RunState {
+  uint32_t open = 0;           // kept members so far of the run that is open at the end of the previous chunk
+  bool mine = false;           // ... and whether that run started inside this warp's segment
+  unsigned long long ties = 0;
+};
+// One chunk of 32 positions: h = its run heads, kw = this replicate's kept bits, inside = the chunk lies in the warp's segment.
+__device__ __forceinline__ void run_step(RunState& st, uint32_t h, uint32_t kw, bool inside) {
+  if (!inside && !st.mine) return;
+  const uint32_t first = h ? (uint32_t)__ffs(h) - 1u : 32u;                   // positions before the first head continue the open run
+  st.open += __popc(kw & (first >= 32u ? 0xFFFFFFFFu : ((1u << first) - 1u)));
+  if (h == 0u) return;                                                         // the run goes on
+  if (st.mine) st.ties += (unsigned long long)st.open * (st.open - 1u) / 2u;
+  st.mine = false;
+  if (!inside) return;                                                         // runs that start here belong to the next segment
+  // runs that start in this chunk: all but the last end here too; only heads whose next position is not a head start a
+  // run of two or more members
+  const uint32_t last = 31u - (uint32_t)__clz(h);
+  uint32_t multi = h & ~(h >> 1) & ~(1u << last);
+  while (multi) {
+    const uint32_t b = (uint32_t)__ffs(multi) - 1u;
+    multi &= multi - 1u;
+    const uint32_t e = (uint32_t)__ffs(h & ~((2u << b) - 1u)) - 1u;            // the next head: b is not the last one
+    const uint32_t t = __popc(kw & ((1u << e) - (1u << b)));
+    st.ties += t * (t - 1u) / 2u;
+  }
+  st.open = __popc(kw & ~((1u << last) - 1u));
+  st.mine = true;
+}
+// grid (ceil(2 nseg / 8), batches), 256 threads; dynamic shared memory: the batch's transposed masks
 __global__ void __launch_bounds__(256)
 tree_ties_kernel(const __grid_constant__ TiesArgs A) {
   extern __shared__ __align__(16) uint32_t tie_mT[];
@@ -739,63 +779,36 @@ tree_ties_kernel(const __grid_constant__ TiesArgs A) {
   for (int i = threadIdx.x; i < A.n; i += 256) tie_mT[i] = A.mT[(size_t)batch * A.n + i];
   __syncthreads();
   const unsigned lane = lane_id();
-  const int warp = threadIdx.x >> 5;
-  const uint32_t seg = blockIdx.x * 8u + warp;
+  const uint32_t seg = blockIdx.x * 8u + (threadIdx.x >> 5);
   const uint32_t pass = seg / A.nseg, s = seg % A.nseg;
-  unsigned long long ties = 0;
-  uint32_t kept_total = 0;
-  if (pass < 3u) {
-    const uint32_t* __restrict__ ijL = A.ij[pass];
-    const uint32_t* __restrict__ H = A.heads[pass];
-    auto kept_bits = [&](uint32_t ch) {
+  if (pass >= 2u) return;
+  const uint32_t* __restrict__ ijL = A.ij[pass];
+  const uint32_t* __restrict__ H0 = A.heads[pass == 0u ? 0 : 2];                // the coarser runs of the pass
+  const uint32_t* __restrict__ H1 = A.heads[1];                                 // pass 0 only: equal (x, y), a refinement of equal x
+  const uint32_t ch0 = s * kTiesSegChunks, ch1 = min(A.G, ch0 + kTiesSegChunks);
+  RunState coarse, fine;
+  for (uint32_t ch = ch0; ch < A.G; ++ch) {
+    const bool inside = ch < ch1;
+    if (!inside && !coarse.mine && !fine.mine) break;                           // past the segment: only to finish runs of ours
+    const uint32_t h0 = __ldg(H0 + ch);
+    // 32 runs of one member, and the next position starts a run too: nothing to count, no kept bits needed
+    const bool trivial = h0 == 0xFFFFFFFFu && (ch + 1u >= A.G || (__ldg(H0 + ch + 1u) & 1u));
+    uint32_t kw = 0;
+    if (!trivial) {
       const uint32_t k = ch * 32u + lane;
       uint32_t w = 0;
       if (k < A.N) { const uint32_t ij = __ldg(ijL + k); w = tie_mT[ij >> 16] & tie_mT[ij & 0xFFFFu]; }
-      return tree_bit_transpose32(w, lane);
-    };
-    const uint32_t ch0 = s * kTreeSegChunks, ch1 = min(A.G, ch0 + kTreeSegChunks);
-    uint32_t open = 0;                 // kept members so far of the run that is open at the end of the previous chunk
-    bool mine = false;                 // ... and whether that run started inside this segment
-    for (uint32_t ch = ch0; ch < A.G; ++ch) {
-      if (ch >= ch1 && !mine) break;   // past the segment: only to finish a run of ours
-      const uint32_t h = __ldg(H + ch);
-      if (ch >= ch1 && h == 0u) {      // the whole chunk continues our run
-        open += __popc(kept_bits(ch));
-        continue;
-      }
-      const uint32_t kw = kept_bits(ch);
-      if (ch < ch1 && pass == 0u) kept_total += __popc(kw);
-      // positions before the first head continue the open run
-      const uint32_t first = h ? (uint32_t)__ffs(h) - 1u : 32u;
-      const uint32_t cont = first >= 32u ? 0xFFFFFFFFu : ((1u << first) - 1u);
-      open += __popc(kw & cont);
-      if (h == 0u) continue;           // (inside the segment) the run goes on
-      if (mine) ties += (unsigned long long)open * (open - 1u) / 2u;
-      if (ch >= ch1) { mine = false; break; }
-      // runs that start in this chunk: all but the last end here too
-      uint32_t rest = h;
-      while (true) {
-        const uint32_t b = (uint32_t)__ffs(rest) - 1u;
-        rest &= rest - 1u;
-        if (rest == 0u) {              // last run of the chunk: stays open
-          open = __popc(kw & ~((1u << b) - 1u));
-          mine = true;
-          break;
-        }
-        const uint32_t e = (uint32_t)__ffs(rest) - 1u;
-        if (e - b >= 2u) {
-          const uint32_t tcount = __popc(kw & ((1u << e) - (1u << b)));
-          ties += tcount * (tcount - 1u) / 2u;
-        }
-      }
+      kw = tree_bit_transpose32(w, lane);
     }
-    if (mine) ties += (unsigned long long)open * (open - 1u) / 2u;     // the order's last run
+    run_step(coarse, h0, kw, inside);
+    if (pass == 0u) run_step(fine, trivial ? 0xFFFFFFFFu : __ldg(H1 + ch), kw, inside);
   }
+  if (coarse.mine) coarse.ties += (unsigned long long)coarse.open * (coarse.open - 1u) / 2u;     // the order's last run
+  if (fine.mine) fine.ties += (unsigned long long)fine.open * (fine.open - 1u) / 2u;
   const int r = batch * 32 + (int)lane;
-  if (pass < 3u && r < A.rb) {
-    const int slot = pass == 0u ? 0 : pass == 1u ? 2 : 1;
-    if (ties) atomicAdd(A.acc + (size_t)r * 4 + slot, ties);
-    if (kept_total) atomicAdd(A.counts + r, kept_total);
+  if (r < A.rb) {
+    if (coarse.ties) atomicAdd(A.acc + (size_t)r * 4 + (pass == 0u ? 0 : 1), coarse.ties);
+    if (fine.ties) atomicAdd(A.acc + (size_t)r * 4 + 2, fine.ties);
   }
 }
 
@@ -850,14 +863,15 @@ static size_t kendall_per_replicate_bytes(int n) {
 constexpr size_t kKendallSlack = 16384;       // 256-byte alignment of the per-batch arrays
 constexpr int kKendallMaxBatch = 64;
 // tree mode: stimulus pairs of every level (+ the base order), child bits, base-block masks, the cross table, the transposed
-// masks and the segment totals of the two 32-replicate batches of a 64-replicate pass
+// masks and the segment totals of the eight 32-replicate batches of a pass, its accumulators and kept-entry counts
 static size_t kendall_tree_bytes(int n) {
   const int64_t N = triu_len(n);
   const size_t Np = (size_t)round_up(N, 32), G = Np / 32, nseg = (G + kTreeSegChunks - 1) / kTreeSegChunks;
   const size_t levels = (size_t)tree_levels(N);
   return (levels + 1) * arena_bytes(Np, 4) + arena_bytes(levels * G + 1, 4) + arena_bytes(Np, 4) + arena_bytes(65536, 1) +
-         arena_bytes((size_t)2 * n, 4) + arena_bytes((size_t)2 * (levels + 1) * nseg * 64, 4) +
-         arena_bytes(Np, 4) + 3 * arena_bytes(G, 4) + 4096;          // + stimulus pairs of the y order, run-head bits of the three tie passes
+         arena_bytes((size_t)(kTreeBatch / 32) * n, 4) + arena_bytes((size_t)(kTreeBatch / 32) * (levels + 1) * nseg * 64, 4) +
+         arena_bytes(Np, 4) + 3 * arena_bytes(G, 4) +               // stimulus pairs of the y order, run-head bits of the tie passes
+         arena_bytes((size_t)kTreeBatch * 4, 8) + arena_bytes(kTreeBatch, 4) + 4096;
 }
 static bool kendall_tree_wanted(int n, int R) {
   const int opt = option_kendall_tree();
@@ -874,8 +888,9 @@ extern "C" size_t vr_kendall_workspace_bytes(int n) {
 }
 extern "C" size_t vr_kendall_batch_workspace_bytes(int n, int R) {
   if (n < 2 || R < 1) return 256;
+  if (kendall_tree_wanted(n, R)) return vr_kendall_workspace_bytes(n) + kendall_tree_bytes(n);      // replicates need no arrays of their own
   const int rb = R < kKendallMaxBatch ? R : kKendallMaxBatch;
-  return kendall_fixed_bytes(n) + (size_t)rb * kendall_per_replicate_bytes(n) + kKendallSlack + (kendall_tree_wanted(n, R) ? kendall_tree_bytes(n) : 0);
+  return kendall_fixed_bytes(n) + (size_t)rb * kendall_per_replicate_bytes(n) + kKendallSlack;
 }
 
 extern "C" int vr_kendall_tau_a(const float* rdmA, const float* rdmB, int n, int64_t ld, const uint32_t* masks, int R,
@@ -899,7 +914,7 @@ extern "C" int vr_kendall_tau_a(const float* rdmA, const float* rdmB, int n, int
   int Rb = (int)((ws_bytes - kendall_fixed_bytes(n) - kKendallSlack - (tree ? kendall_tree_bytes(n) : 0)) / kendall_per_replicate_bytes(n));
   if (Rb > kKendallMaxBatch) Rb = kKendallMaxBatch;
   if (Rb > R) Rb = R;
-  if (Rb < 1) Rb = 1;
+  if (Rb < 1 || tree) Rb = 1;
   Arena a(ws, ws_bytes);
   uint32_t* xkey_c = a.take<uint32_t>(Np);
   uint32_t* ykey_c = a.take<uint32_t>(Np);
@@ -938,6 +953,8 @@ extern "C" int vr_kendall_tau_a(const float* rdmA, const float* rdmB, int n, int
   TreeArgs T{};
   uint32_t *t_ij = nullptr, *t_side = nullptr, *t_gt = nullptr, *t_mT = nullptr, *t_ijy = nullptr, *t_heads[3] = {nullptr, nullptr, nullptr};
   uint8_t* t_cross = nullptr;
+  unsigned long long* t_acc = nullptr;
+  uint32_t* t_counts = nullptr;
   if (tree) {
     T.levels = tree_levels(N);
     T.N = (uint32_t)N; T.Np = (uint32_t)Np; T.G = G; T.nseg = (G + kTreeSegChunks - 1) / kTreeSegChunks; T.n = n;
@@ -945,9 +962,11 @@ extern "C" int vr_kendall_tau_a(const float* rdmA, const float* rdmB, int n, int
     t_side = a.take<uint32_t>((size_t)T.levels * G + 1);
     t_gt = a.take<uint32_t>(Np);
     t_cross = a.take<uint8_t>(65536);
-    t_mT = a.take<uint32_t>((size_t)2 * n);
-    T.segtot = a.take<uint32_t>((size_t)2 * (T.levels + 1) * T.nseg * 64);
-    T.ij = t_ij; T.side = t_side; T.gt = t_gt; T.cross = t_cross; T.mT = t_mT; T.acc = acc;
+    t_mT = a.take<uint32_t>((size_t)(kTreeBatch / 32) * n);
+    T.segtot = a.take<uint32_t>((size_t)(kTreeBatch / 32) * (T.levels + 1) * T.nseg * 64);
+    t_acc = a.take<unsigned long long>((size_t)kTreeBatch * 4);
+    t_counts = a.take<uint32_t>(kTreeBatch);
+    T.ij = t_ij; T.side = t_side; T.gt = t_gt; T.cross = t_cross; T.mT = t_mT; T.acc = t_acc;
     t_ijy = a.take<uint32_t>(Np);
     for (int k = 0; k < 3; ++k) t_heads[k] = a.take<uint32_t>(G);
   }
@@ -1039,6 +1058,33 @@ extern "C" int vr_kendall_tau_a(const float* rdmA, const float* rdmB, int n, int
       uint32_t* x = sv; sv = dv; dv = x;
       x = sp; sp = dp; dp = x;
     }
+    // replicates: no sort, no tables -- masks, ties, discordant pairs, tau
+    for (int r0 = 0; r0 < R; r0 += kTreeBatch) {
+      const int rb = R - r0 < kTreeBatch ? R - r0 : kTreeBatch;
+      const unsigned nb32 = (unsigned)((rb + 31) / 32);
+      T.rb = rb;
+      VR_CHECK_CUDA(cudaMemsetAsync(t_acc, 0, (size_t)rb * 4 * sizeof(unsigned long long), stream));
+      tree_kept_kernel<<<(rb + 7) / 8, 256, 0, stream>>>(masks + (size_t)r0 * W, W, rb, t_counts);
+      VR_CHECK_LAUNCH();
+      tree_masks_kernel<<<dim3((n + 255) / 256, nb32), 256, 0, stream>>>(masks + (size_t)r0 * W, W, n, rb, t_mT);
+      VR_CHECK_LAUNCH();
+      TiesArgs ta{};
+      ta.ij[0] = t_ij; ta.ij[1] = t_ijy;
+      for (int k = 0; k < 3; ++k) ta.heads[k] = t_heads[k];
+      ta.mT = t_mT; ta.acc = t_acc; ta.N = (uint32_t)N; ta.G = G; ta.nseg = (G + kTiesSegChunks - 1) / kTiesSegChunks; ta.n = n; ta.rb = rb;
+      tree_ties_kernel<<<dim3((2u * ta.nseg + 7u) / 8u, nb32), 256, (size_t)n * 4, stream>>>(ta);
+      VR_CHECK_LAUNCH();
+      const unsigned segs = (unsigned)(T.levels + 1) * T.nseg;
+      tree_count_kernel<<<dim3((segs + 7) / 8, nb32), 256, tree_smem, stream>>>(T);
+      VR_CHECK_LAUNCH();
+      if (T.levels) {
+        tree_stitch_kernel<<<dim3((unsigned)T.levels, nb32), 256, 0, stream>>>(T);
+        VR_CHECK_LAUNCH();
+      }
+      kendall_finish_kernel<<<(rb + 63) / 64, 64, 0, stream>>>(t_acc, t_counts, nan_flag, rb, out + r0);
+      VR_CHECK_LAUNCH();
+    }
+    return VR_OK;
   }
   KendallOrders ord;
   ord.order[0] = order_xy;
@@ -1048,29 +1094,6 @@ extern "C" int vr_kendall_tau_a(const float* rdmA, const float* rdmB, int n, int
   for (int r0 = 0; r0 < R; r0 += Rb) {
     const int rb = R - r0 < Rb ? R - r0 : Rb;
     VR_CHECK_CUDA(cudaMemsetAsync(acc, 0, (size_t)rb * 4 * sizeof(unsigned long long), stream));
-    if (tree) {
-      const unsigned nb32 = (unsigned)((rb + 31) / 32);                      // <= 2: Rb <= 64
-      T.rb = rb;
-      VR_CHECK_CUDA(cudaMemsetAsync(counts, 0, (size_t)rb * sizeof(uint32_t), stream));
-      tree_masks_kernel<<<dim3((n + 255) / 256, nb32), 256, 0, stream>>>(masks + (size_t)r0 * W, W, n, rb, t_mT);
-      VR_CHECK_LAUNCH();
-      TiesArgs ta{};
-      ta.ij[0] = t_ij; ta.ij[1] = t_ij; ta.ij[2] = t_ijy;
-      for (int k = 0; k < 3; ++k) ta.heads[k] = t_heads[k];
-      ta.mT = t_mT; ta.acc = acc; ta.counts = counts; ta.N = (uint32_t)N; ta.G = G; ta.nseg = T.nseg; ta.n = n; ta.rb = rb;
-      tree_ties_kernel<<<dim3((3u * T.nseg + 7u) / 8u, nb32), 256, (size_t)n * 4, stream>>>(ta);
-      VR_CHECK_LAUNCH();
-      const unsigned segs = (unsigned)(T.levels + 1) * T.nseg;
-      tree_count_kernel<<<dim3((segs + 7) / 8, nb32), 256, tree_smem, stream>>>(T);
-      VR_CHECK_LAUNCH();
-      if (T.levels) {
-        tree_stitch_kernel<<<dim3((unsigned)T.levels, nb32), 256, 0, stream>>>(T);
-        VR_CHECK_LAUNCH();
-      }
-      kendall_finish_kernel<<<(rb + 63) / 64, 64, 0, stream>>>(acc, counts, nan_flag, rb, out + r0);
-      VR_CHECK_LAUNCH();
-      continue;
-    }
     dim3 pg((words + 255) / 256 < 64 ? (words + 255) / 256 : 64, rb);
     pair_mask_kernel<<<pg, 256, (size_t)(W + 1) * 4, stream>>>(masks + (size_t)r0 * W, rb, n, W, words, pairbits);
     VR_CHECK_LAUNCH();
