@@ -252,9 +252,11 @@ int vr_bootstrap_pearson(const float* const* rdmA_host, int nA,
  * rsa.py:22-40 (SciPy tau-b rescaled to (C - D) / n0) inside compute_rdm_correlation (rsa.py:122)
  * and inside the bootstrap loops when compare_method = kendall (evals.py:229, utils.py:518).
  * out is (R,) fp64; NaN for < 2 kept pairs, a constant vector or a NaN entry.
- * Replicates are processed in batches of up to 64 (one grid row per replicate); the batch shrinks to
- * what the workspace holds: vr_kendall_workspace_bytes(n) is the minimum (one replicate at a time),
- * vr_kendall_batch_workspace_bytes(n, R) the size at which R replicates run in full batches.
+ * Jobs of 192 or more masks (option "kendall_tree") build the merge tree of the pair once and count every replicate
+ * without sorting, 256 replicates per pass; smaller jobs sort the kept (or dropped) entries of each replicate in
+ * batches of up to 64, the batch shrinking to what the workspace holds.  vr_kendall_workspace_bytes(n) is the
+ * minimum (sorting path, one replicate at a time), vr_kendall_batch_workspace_bytes(n, R) the size at which an
+ * R-mask job takes its fastest path (the tree needs (levels + 2) x 4 N bytes, levels = ceil(log2(N / 32))).
  * ---------------------------------------------------------------------------------- */
 size_t vr_kendall_workspace_bytes(int n);
 size_t vr_kendall_batch_workspace_bytes(int n, int R);
