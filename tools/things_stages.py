@@ -10,6 +10,7 @@ z = synth.latent(n, dev, 1)
 feats = [synth.layer_features(z, d, 10 + i) for i, d in enumerate(synth.ALEXNET_DIMS.values())]
 g = torch.Generator(device=dev).manual_seed(7)
 beh = torch.relu(z @ torch.randn(synth.LATENT, 66, device=dev, generator=g))
+_lib.set_option('sweep_tile_a', int(os.environ.get('TA', 8))); _lib.set_option('sweep_tile_b', int(os.environ.get('TB', 8)))
 for rep in range(3):
     if rep == 2: _lib.profile_start()
     torch.cuda.synchronize(); t = time.perf_counter()
