@@ -360,6 +360,130 @@ sweep5_kernel(const uint32_t* __restrict__ desc4 /*[N][NV]*/, int N, int G, cons
     }
 }
 
+// ---- v3n: v3 with NARROW rows.  Entry = 4 bytes {kept bits of 16 positions | delta << 16}, delta = 2 (C(16 h) - C(start of the
+// 2048-position block)); a second, small table (one row of 32 x 4 bytes per 2048 positions: 2 C(block start) + 1 - N_r + 2^31)
+// supplies the rest.  Half the bytes per lookup from the big table, one more (cache-friendly) lookup.
+__global__ void narrow_tables(const uint2* __restrict__ src /*[b][v][G][32] {kept32, C(32g)}*/, int G, int GB, int batches,
+                              const uint32_t* __restrict__ nkept, uint32_t* __restrict__ rows /*[b][v][2G][32]*/,
+                              uint32_t* __restrict__ base /*[b][v][GB][32]*/) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t entries = (size_t)batches * NV * G * 32;
+  if (i >= entries) return;
+  const int lane = (int)(i & 31);
+  const size_t gi = i >> 5;                       // (b * NV + v) * G + g
+  const int g = (int)(gi % G);
+  const size_t bv = gi / G;
+  const size_t b = bv / NV;
+  const uint2 e = src[i];
+  const uint32_t c_blk = src[((bv * G) + (size_t)(g & ~63)) * 32 + lane].y;     // C at the start of the 2048-position block
+  const uint32_t d0 = 2u * (e.y - c_blk), d1 = d0 + 2u * __popc(e.x & 0xFFFFu);
+  rows[((bv * 2 * G) + 2 * (size_t)g) * 32 + lane] = (e.x & 0xFFFFu) | (d0 << 16);
+  rows[((bv * 2 * G) + 2 * (size_t)g + 1) * 32 + lane] = (e.x >> 16) | (d1 << 16);
+  if ((g & 63) == 0) base[(bv * GB + (g >> 6)) * 32 + lane] = 2u * e.y + 1u - nkept[b * 32 + lane] + 0x80000000u;
+}
+__device__ __forceinline__ uint32_t ldg32(const char* p) {
+  uint32_t r;
+  asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ double b2d(uint32_t v) {     // v = x + 2^31 -> (double)x, one DADD
+  return __hiloint2double(0x43300000, (int)v) - 4503601774854144.0;
+}
+template <int kWarps>
+__global__ void __launch_bounds__(kWarps * 32, 1)
+sweep3n_kernel(const uint32_t* __restrict__ desc4 /*[N][NV]*/, int N, int G, int GB, const uint32_t* __restrict__ rows,
+               const uint32_t* __restrict__ basetab, int batches, const uint32_t* __restrict__ pairs_canon,
+               const uint32_t* __restrict__ maskT, int n, int splits, double* __restrict__ out) {
+  __shared__ __align__(16) uint32_t ring[kWarps][2][NV / 4][32][4];
+  __shared__ uint32_t kring[kWarps][2][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x / splits, s = blockIdx.x % splits;
+  const int per = (N + splits - 1) / splits;
+  const int c_lo = s * per, c_hi = min(N, c_lo + per);
+  const int wper = ((c_hi - c_lo) + kWarps - 1) / kWarps;
+  const int p_lo = c_lo + warp * wper, p_hi = min(c_hi, p_lo + wper);
+  const char* rbase = reinterpret_cast<const char*>(rows) + (size_t)b * ((size_t)NV * 2 * G * 128) + lane * 4;
+  const char* bbase = reinterpret_cast<const char*>(basetab) + (size_t)b * ((size_t)NV * GB * 128) + lane * 4;
+  const uint32_t* mt = maskT + (size_t)b * n;
+  double acc[NA][NB];
+#pragma unroll
+  for (int a = 0; a < NA; ++a)
+#pragma unroll
+    for (int c = 0; c < NB; ++c) acc[a][c] = 0.0;
+  auto stage_block = [&](int p0, int buf) {
+    const int q = min(p0 + lane, N - 1);
+    const uint4* src = reinterpret_cast<const uint4*>(desc4 + (size_t)q * NV);
+#pragma unroll
+    for (int k = 0; k < NV / 4; ++k) cp_async16(&ring[warp][buf][k][lane][0], src + k);
+    cp_async_commit();
+    const uint32_t pw = __ldg(pairs_canon + q);
+    kring[warp][buf][lane] = __ldg(mt + (pw >> 16)) & __ldg(mt + (pw & 0xFFFF));
+  };
+  uint32_t e_next[NV], t_next[NV], bit_next[NV];
+  auto issue = [&](int buf, int k) {
+#pragma unroll
+    for (int q4 = 0; q4 < NV / 4; ++q4) {
+      const uint4 d = *reinterpret_cast<const uint4*>(&ring[warp][buf][q4][k][0]);
+      const uint32_t dd[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int v = q4 * 4 + j;
+        e_next[v] = ldg32(rbase + ((size_t)(dd[j] & ~15u) << 3));                         // half-group (dd >> 4) * 128 bytes
+        const uint32_t g = (dd[j] >> 5) - (uint32_t)v * (uint32_t)G;
+        t_next[v] = ldg32(bbase + ((size_t)((uint32_t)v * (uint32_t)GB + (g >> 6)) << 7));
+        bit_next[v] = dd[j];
+      }
+    }
+  };
+  if (p_lo < p_hi) {
+    stage_block(p_lo, 0);
+    cp_async_wait_all();
+    __syncwarp();
+    issue(0, 0);
+  }
+  int buf = 0;
+  for (int p0 = p_lo; p0 < p_hi; p0 += 32, buf ^= 1) {
+    const int cnt = min(32, p_hi - p0);
+    if (p0 + 32 < p_hi) stage_block(p0 + 32, buf ^ 1);
+    for (int k = 0; k < cnt; ++k) {
+      uint32_t e[NV], t[NV], bit[NV];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) { e[v] = e_next[v]; t[v] = t_next[v]; bit[v] = bit_next[v]; }
+      const uint32_t kw = kring[warp][buf][k];
+      if (k + 1 < cnt) issue(buf, k + 1);
+      else if (p0 + 32 < p_hi) { cp_async_wait_all(); __syncwarp(); issue(buf ^ 1, 0); }
+      const bool keep = (kw >> lane) & 1u;
+      double dd[NV];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const uint32_t low = e[v] & ((1u << (bit[v] & 15u)) - 1u);
+        uint32_t d = t[v] + (e[v] >> 16) + 2u * __popc(low);
+        if (v < NA) d = keep ? d : 0x80000000u;
+        dd[v] = b2d(d);
+      }
+#pragma unroll
+      for (int a = 0; a < NA; ++a)
+#pragma unroll
+        for (int c = 0; c < NB; ++c) acc[a][c] = fma(dd[a], dd[NA + c], acc[a][c]);
+    }
+  }
+  __shared__ double red[kWarps][32];
+#pragma unroll
+  for (int a = 0; a < NA; ++a)
+#pragma unroll
+    for (int c = 0; c < NB; ++c) {
+      red[warp][lane] = acc[a][c];
+      __syncthreads();
+      if (warp == 0) {
+        double t = 0;
+        for (int w = 0; w < kWarps; ++w) t += red[w][lane];
+        atomicAdd(out + ((size_t)(a * NB + c) * batches + b) * 32 + lane, t);
+      }
+      __syncthreads();
+    }
+}
+
+
 __global__ void rebias_tables(const uint2* __restrict__ src, uint2* __restrict__ dst, size_t entries, int G, const uint32_t* __restrict__ nkept) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= entries) return;
@@ -440,6 +564,11 @@ int main(int argc, char** argv) {
   uint2* d_tables2; CK(cudaMalloc(&d_tables2, tab_bytes));
   { const size_t entries = tab_bytes / 8; rebias_tables<<<(unsigned)((entries + 255) / 256), 256>>>(d_tables, d_tables2, entries, G, d_nkept); CK(cudaDeviceSynchronize()); }
   double* d_outd; CK(cudaMalloc(&d_outd, (size_t)NA * NB * batches * 32 * 8));
+  const int GB = (G + 63) / 64;
+  uint32_t *d_rowsn, *d_basen;
+  CK(cudaMalloc(&d_rowsn, (size_t)batches * NV * 2 * G * 128)); CK(cudaMalloc(&d_basen, (size_t)batches * NV * GB * 128));
+  { const size_t entries = (size_t)batches * NV * G * 32; narrow_tables<<<(unsigned)((entries + 255) / 256), 256>>>(d_tables, G, GB, batches, d_nkept, d_rowsn, d_basen); CK(cudaDeviceSynchronize()); }
+  printf("narrow rows: %.1f MB per batch + %.2f MB of block bases\n", (double)NV * 2 * G * 128 / 1e6, (double)NV * GB * 128 / 1e6);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   auto run = [&](int splits, int warps, int flavour) {
     float best = 1e9f;
@@ -452,7 +581,12 @@ int main(int argc, char** argv) {
         CK(cudaFuncSetAttribute(sweep5_kernel<W, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
         CK(cudaMemset(d_outd, 0, (size_t)NA * NB * batches * 32 * 8)); cudaEventRecord(e0); \
         sweep5_kernel<W, D><<<batches * splits, W * 32, sm>>>(d_desc4, N, G, d_tables2, batches, d_canon, d_maskT, n, splits, d_outd); } while (0)
-      if (flavour == 52 && warps == 8) LAUNCH5(8, 2);
+#define LAUNCH3N(W) do { CK(cudaMemset(d_outd, 0, (size_t)NA * NB * batches * 32 * 8)); cudaEventRecord(e0); \
+        sweep3n_kernel<W><<<batches * splits, W * 32>>>(d_desc4, N, G, GB, d_rowsn, d_basen, batches, d_canon, d_maskT, n, splits, d_outd); } while (0)
+      if (flavour == 7 && warps == 8) LAUNCH3N(8);
+      else if (flavour == 7 && warps == 4) LAUNCH3N(4);
+      else if (flavour == 7) LAUNCH3N(6);
+      else if (flavour == 52 && warps == 8) LAUNCH5(8, 2);
       else if (flavour == 53 && warps == 8) LAUNCH5(8, 3);
       else if (flavour == 54 && warps == 8) LAUNCH5(8, 4);
       else if (flavour == 54 && warps == 6) LAUNCH5(6, 4);
@@ -478,7 +612,18 @@ int main(int argc, char** argv) {
     return best;
   };
   if (argc > 5) run(atoi(argv[5]), atoi(argv[4]), atoi(argv[3]));
-  else { run(148, 8, 54); run(148, 8, 3); }
+  else {
+    run(148, 8, 54);
+    std::vector<double> ref((size_t)NA * NB * batches * 32), got(ref.size());
+    CK(cudaMemcpy(ref.data(), d_outd, ref.size() * 8, cudaMemcpyDeviceToHost));
+    run(148, 8, 7); run(296, 8, 7);
+    CK(cudaMemcpy(got.data(), d_outd, got.size() * 8, cudaMemcpyDeviceToHost));
+    size_t badn = 0;
+    for (size_t i = 0; i < ref.size(); ++i) badn += ref[i] != got[i];
+    printf("narrow rows vs wide rows (v5): %zu mismatches of %zu\n", badn, ref.size());
+    run(148, 8, 54);
+    run(148, 8, 3);
+  }
   {
     uint32_t* d_sink; CK(cudaMalloc(&d_sink, 4));
     for (int rowb : {256, 128}) for (int threads : {256, 512, 1024}) {
