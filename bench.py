@@ -277,6 +277,10 @@ def run_ours(args):
     assert np.array_equal(res["scores"], res_dp["scores"])
     del Xh
 
+    # ---- parity gates (SURVEY 8d / BASELINE.md 3.6), part of the cpu_baseline leg: the oracle is the checker only
+    if rank == 0 and cpu_baseline is not None:
+        cpu_baseline["parity_gates"] = parity_gates(vb, X, Y, res, B, dev)
+
     # ---- strong scaling (BASELINE config 3): THINGS shape, 1854 concepts, behavioural RDM (d = 66) vs 8 layers,
     # B replicates of ONE job sharded over the ranks (dist.rsa_grouped_sharded: sharded RDM builds + presorts, blob
     # all-gather over NVLink, replicate shards, one all-gather of the scores in replicate order)
@@ -312,10 +316,6 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
-
-    # ---- parity gates (SURVEY 8d / BASELINE.md 3.6), part of the cpu_baseline leg: the oracle is the checker only
-    if cpu_baseline is not None:
-        cpu_baseline["parity_gates"] = parity_gates(vb, X, Y, res, B, dev)
 
     # a step's host work (index draws, percentiles) overlaps device work; the step time is the max
     # of the device-event time and the wall time between the two synchronised barriers
