@@ -346,9 +346,10 @@ def compare_grouped(model: Sequence[PresortedRDM], neural: Sequence[PresortedRDM
                     masks: torch.Tensor, kept_stimuli: Optional[int] = None) -> torch.Tensor:
     """(nA, nB, R) fp64 device tensor: every model RDM x every neural RDM x every mask.
 
-    kept_stimuli: how many stimuli a subsample mask keeps, when the caller knows (the bootstrap: int(0.9 n)).  Kendall counts
-    ties and inversions among the DROPPED entries when most are kept (csrc/kendall.cu, complement mode) and among the kept ones
-    otherwise; the answer is the same either way."""
+    kept_stimuli: how many stimuli a subsample mask keeps, when the caller knows (the bootstrap: int(0.9 n)).  Kendall jobs of
+    192 or more masks build the merge tree of each RDM pair once and count every replicate without sorting (csrc/kendall.cu,
+    tree mode); smaller jobs sort, counting ties and inversions among the DROPPED entries when most are kept (complement mode)
+    and among the kept ones otherwise; the answer is the same bits every way."""
     lib = _lib.load()
     method = method.lower()
     if method not in _METHODS:
