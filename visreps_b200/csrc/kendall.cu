@@ -593,21 +593,23 @@ __device__ __forceinline__ uint32_t byte_counts(uint32_t x) {      // popcount o
   return (x + (x >> 4)) & 0x0F0F0F0Fu;
 }
 
-// grid (ceil((levels + 1) * nseg / 8), batches), 256 threads; dynamic shared memory: the cross table and the batch's masks.
-__global__ void __launch_bounds__(256)
+// grid (ceil((levels + 1) * nseg / 16), batches), 512 threads (16 warps share one 64 KB cross table: three CTAs per SM);
+// dynamic shared memory: the cross table and the batch's masks.
+constexpr int kTreeCountWarps = 16;
+__global__ void __launch_bounds__(kTreeCountWarps * 32)
 tree_count_kernel(const __grid_constant__ TreeArgs A) {
   extern __shared__ __align__(16) unsigned char t_smem[];
-  __shared__ unsigned long long s_red[8][32];
+  __shared__ unsigned long long s_red[kTreeCountWarps][32];
   uint8_t* s_cross = t_smem;
   uint32_t* s_mT = reinterpret_cast<uint32_t*>(t_smem + 65536);
   const int batch = blockIdx.y;
-  for (uint32_t q = threadIdx.x; q < 4096u; q += 256u)
+  for (uint32_t q = threadIdx.x; q < 4096u; q += kTreeCountWarps * 32u)
     reinterpret_cast<uint4*>(s_cross)[q] = __ldg(reinterpret_cast<const uint4*>(A.cross) + q);
-  for (int i = threadIdx.x; i < A.n; i += 256) s_mT[i] = A.mT[(size_t)batch * A.n + i];
+  for (int i = threadIdx.x; i < A.n; i += kTreeCountWarps * 32) s_mT[i] = A.mT[(size_t)batch * A.n + i];
   __syncthreads();
   const unsigned lane = lane_id();
   const int warp = threadIdx.x >> 5;
-  const uint32_t seg = blockIdx.x * 8u + warp;
+  const uint32_t seg = blockIdx.x * (uint32_t)kTreeCountWarps + warp;
   const uint32_t lv = seg / A.nseg, s = seg % A.nseg;
   uint32_t inv = 0;
   if (lv <= (uint32_t)A.levels) {
@@ -661,7 +663,7 @@ tree_count_kernel(const __grid_constant__ TreeArgs A) {
   if (warp == 0) {
     unsigned long long tot = 0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) tot += s_red[w][lane];
+    for (int w = 0; w < kTreeCountWarps; ++w) tot += s_red[w][lane];
     const int r = batch * 32 + (int)lane;
     if (tot && r < A.rb) atomicAdd(A.acc + (size_t)r * 4 + 3, tot);
   }
@@ -1075,7 +1077,7 @@ extern "C" int vr_kendall_tau_a(const float* rdmA, const float* rdmB, int n, int
       tree_ties_kernel<<<dim3((2u * ta.nseg + 7u) / 8u, nb32), 256, (size_t)n * 4, stream>>>(ta);
       VR_CHECK_LAUNCH();
       const unsigned segs = (unsigned)(T.levels + 1) * T.nseg;
-      tree_count_kernel<<<dim3((segs + 7) / 8, nb32), 256, tree_smem, stream>>>(T);
+      tree_count_kernel<<<dim3((segs + kTreeCountWarps - 1) / kTreeCountWarps, nb32), kTreeCountWarps * 32, tree_smem, stream>>>(T);
       VR_CHECK_LAUNCH();
       if (T.levels) {
         tree_stitch_kernel<<<dim3((unsigned)T.levels, nb32), 256, 0, stream>>>(T);
