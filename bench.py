@@ -67,6 +67,7 @@ def config_dict(args, layers, rois, world):
         "n_stimuli": args.n, "layers": layers, "rois": rois, "n_bootstrap": args.n_bootstrap,
         "pairs_per_gpu": len(layers) * len(rois), "sharding": f"one model per GPU x{world}, 1 all-gather of scores per step",
         "l2_policy": "inputs (2.05 GB of features per model) exceed the 126 MB L2; no flush needed",
+        "index_draws": "replayed from RandomState(seed) inside every timed step (rsa.MASK_CACHE off: nothing reused across steps)",
     }
 
 
@@ -183,6 +184,8 @@ def run_ours(args):
     import torch.distributed as dist
     import visreps_b200 as vb
     from visreps_b200 import _lib, synth
+    from visreps_b200 import rsa as _vrsa
+    _vrsa.MASK_CACHE = False          # every step replays the reference's index draws; the product keeps the last few (seed-keyed)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:

@@ -100,6 +100,40 @@ def test_mask_only_draw_matches_the_index_draw(n, B):
     assert np.array_equal(rng3.get_state()[1], rng4.get_state()[1]) and rng3.get_state()[2] == rng4.get_state()[2]
 
 
+def test_seed_keyed_draws_are_cached_and_caller_generators_are_not():
+    """Draws from a bare seed are a pure function of (n, B, seed, range): the product keeps the last few (the secondary callers
+    bootstrap many pairs with the same seed, run_reconstruction.py:137-158).  A generator passed by the caller is always
+    replayed (its state must advance as the reference loop advances it); MASK_CACHE = False replays every call."""
+    from visreps_b200 import rsa as vrsa
+    vrsa._mask_cache.clear()
+    a = vrsa.draw_subsample_masks(120, 9, seed=5)
+    b = vrsa.draw_subsample_masks(120, 9, seed=5)
+    assert a is b and a.cached
+    c = vrsa.draw_subsample_masks(120, 9, seed=6)
+    assert c is not a and not np.array_equal(c.words.numpy(), a.words.numpy())
+    part = vrsa.draw_subsample_masks(120, 9, seed=5, replicate_range=(2, 7))
+    np.testing.assert_array_equal(part.words.numpy(), a.words.numpy()[2:7])
+    rng = np.random.RandomState(5)
+    d = vrsa.draw_subsample_masks(120, 9, rng=rng)
+    assert d is not a and not d.cached
+    np.testing.assert_array_equal(d.words.numpy(), a.words.numpy())
+    ref = np.random.RandomState(5)
+    for _ in range(9):
+        ref.choice(120, size=108, replace=False)
+    assert rng.randint(0, 2**31 - 1) == ref.randint(0, 2**31 - 1)
+    old = vrsa.MASK_CACHE
+    try:
+        vrsa.MASK_CACHE = False
+        e = vrsa.draw_subsample_masks(120, 9, seed=5)
+        assert e is not a and not e.cached
+        np.testing.assert_array_equal(e.words.numpy(), a.words.numpy())
+    finally:
+        vrsa.MASK_CACHE = old
+    for s_ in range(20):                                           # bounded
+        vrsa.draw_subsample_masks(40, 3, seed=100 + s_)
+    assert len(vrsa._mask_cache) <= vrsa._MASK_CACHE_MAX
+
+
 def test_mask_only_draw_from_a_generator_in_mid_stream():
     from visreps_b200 import rsa as vrsa
     a, b = np.random.RandomState(7), np.random.RandomState(7)
