@@ -298,3 +298,42 @@ def test_kendall_tree_mode_counts_discordant_pairs_without_sorting(n, R, levels,
     va, vb_ = orc.triu_vector(ra), orc.triu_vector(rb)
     want = orc.kendall_tau_a(va, vb_)[0]
     assert abs(out[2][0] - want) <= 1e-6
+
+
+def test_kendall_tree_mode_nan_constant_and_tiny_subsamples(dev):
+    """Tree mode against the sorting path where tau is undefined or degenerate: a constant vector (NaN, rsa.py:29-30), a NaN entry
+    (NaN for every mask), masks that keep 0, 1, 2 and 3 stimuli (fewer than two kept entries -> NaN), and the full mask."""
+    n = 70
+    N = n * (n - 1) // 2
+    rs = np.random.RandomState(4)
+    a = rs.standard_normal(N).astype(np.float32).round(1)
+    b = rs.standard_normal(N).astype(np.float32)
+    const = np.full(N, 2.5, dtype=np.float32)
+    with_nan = b.copy(); with_nan[17] = np.nan
+    sets = [[], [5], [5, 9], [5, 9, 40], list(range(n)), list(range(0, n, 2))] + [list(rs.choice(n, size=63, replace=False)) for _ in range(8)]
+    words = np.zeros((len(sets), (n + 31) // 32), dtype=np.uint32)
+    for r, idx in enumerate(sets):
+        for i in idx:
+            words[r, i >> 5] |= np.uint32(1) << np.uint32(i & 31)
+    masks = torch.from_numpy(words.view(np.int32)).to(dev)
+    lib = _lib.load()
+    R = len(sets)
+    try:
+        for va, vb_ in ((a, b), (const, b), (a, const), (a, with_nan)):
+            ra, rb = cases.vector_to_rdm(va, n).to(dev), cases.vector_to_rdm(vb_, n).to(dev)
+            out = {}
+            for mode in (0, 2):
+                _lib.set_option("kendall_tree", mode)
+                ws = _lib.workspace(lib.vr_kendall_batch_workspace_bytes(n, R), dev)
+                res = torch.full((R,), -7.0, dtype=torch.float64, device=dev)
+                _lib.check(lib.vr_kendall_tau_a(ra.data_ptr(), rb.data_ptr(), n, n, masks.data_ptr(), R, res.data_ptr(),
+                                                ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "vr_kendall_tau_a")
+                out[mode] = res.cpu().numpy()
+            np.testing.assert_array_equal(out[2], out[0])
+            assert np.isnan(out[2][:3]).all()                       # 0, 1 or 2 stimuli: fewer than two kept entries
+            if va is const or vb_ is const or vb_ is with_nan:
+                assert np.isnan(out[2]).all()
+            else:
+                assert np.isfinite(out[2][3:]).all()
+    finally:
+        _lib.set_option("kendall_tree", 1)

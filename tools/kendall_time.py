@@ -5,7 +5,8 @@ import torch
 import visreps_b200 as vb
 from visreps_b200 import synth, _lib
 dev = torch.device("cuda", 0)
-for n, B in ((220, 200), (1000, int(os.environ.get("QB", 100)))):
+sizes = [int(x) for x in os.environ.get("KN", "220,1000").split(",")]
+for n, B in [(n, 200 if n < 500 else int(os.environ.get("QB", 100))) for n in sizes]:
     z = synth.latent(n, dev, 1)
     a = vb.compute_rdm(synth.layer_features(z, 4096, 11))
     b = vb.compute_rdm(z @ torch.randn(synth.LATENT, 500, device=dev) + 0.5 * torch.randn(n, 500, device=dev))
