@@ -279,6 +279,16 @@ int vr_bootstrap_column_corr_f32(const float* y_true, const float* y_pred, int n
                                  int64_t ld_true, int64_t ld_pred, const uint32_t* masks, int R,
                                  double* mean_out, float* per_column, void* ws, size_t ws_bytes, vr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * Percentile confidence interval of bootstrap replicates: replaces np.percentile(scores, [2.5, 97.5]) at
+ * visreps/evals.py:371-372, :520-521 and visreps/analysis/rsa.py:262-263 (NumPy's default 'linear' method) bit for
+ * bit.  scores: rows x B fp64 on the device (row r at scores + r * row_stride); ci_lo / ci_hi: (rows,) fp64.
+ * A row holding a NaN gives NaN bounds.  1 <= B <= vr_percentile_ci_max_replicates().
+ * ---------------------------------------------------------------------------------- */
+int vr_percentile_ci_max_replicates(void);
+int vr_percentile_ci_f64(const double* scores, int rows, int B, int64_t row_stride, double q_lo, double q_hi,
+                         double* ci_lo, double* ci_hi, vr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -337,3 +337,33 @@ def test_kendall_tree_mode_nan_constant_and_tiny_subsamples(dev):
                 assert np.isfinite(out[2][3:]).all()
     finally:
         _lib.set_option("kendall_tree", 1)
+
+
+@pytest.mark.parametrize("b", [1, 2, 3, 10, 40, 41, 100, 999, 1000, 1001, 5000, 16384])
+def test_device_percentile_ci_is_numpy_percentile(b, dev):
+    """vr_percentile_ci_f64 == np.percentile(scores, [2.5, 97.5], axis=-1) bit for bit (evals.py:371-372, rsa.py:262-263):
+    negative values, ties, -0.0, infinities; a row with a NaN gives NaN bounds; strided rows (the [..., 1:] slice rsa_grouped
+    passes); other percentiles."""
+    rs = np.random.RandomState(b)
+    x = rs.standard_normal((3, 4, b + 1)) * 0.3
+    x[0, 1] = np.round(x[0, 1], 1)                                   # ties
+    x[1, 2, ::3] = -0.0
+    if b > 4:
+        x[2, 0, 2] = np.inf; x[2, 0, 3] = -np.inf
+        x[2, 3, b // 2] = np.nan
+    t = torch.from_numpy(x).to(dev)
+    got = vrsa.percentile_ci_device(t[:, :, 1:])
+    assert got is not None and got.shape == (2, 3, 4)
+    with np.errstate(invalid="ignore"):
+        want = np.percentile(x[:, :, 1:], [2.5, 97.5], axis=-1)
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+    lo_hi = vrsa.percentile_ci_device(t[:, :, 1:], 0.0, 100.0).cpu().numpy()
+    with np.errstate(invalid="ignore"):
+        np.testing.assert_array_equal(lo_hi, np.percentile(x[:, :, 1:], [0.0, 100.0], axis=-1))
+    mid = vrsa.percentile_ci_device(t[:, :, 1:], 50.0, 33.3).cpu().numpy()
+    with np.errstate(invalid="ignore"):
+        np.testing.assert_array_equal(mid, np.percentile(x[:, :, 1:], [50.0, 33.3], axis=-1))
+    assert vrsa.percentile_ci_device(t[:, :, 1:].float()) is None     # not fp64: the caller keeps the host routine
+    with np.errstate(invalid="ignore"):
+        l, h = vrsa.percentile_ci(x[:, :, 1:])
+    np.testing.assert_array_equal(np.stack([l, h]), want)              # and the host routine agrees with both

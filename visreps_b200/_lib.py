@@ -73,6 +73,8 @@ SIGNATURES = {
     "vr_kendall_tau_a": (_i, [_vp, _vp, _i, _i64, _vp, _i, _vp, _vp, _sz, _vp]),
     "vr_bootstrap_pearson_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "vr_bootstrap_pearson": (_i, [_vp, _i, _vp, _i, _i, _i64, _vp, _i, _vp, _vp, _sz, _vp]),
+    "vr_percentile_ci_max_replicates": (_i, []),
+    "vr_percentile_ci_f64": (_i, [_vp, _i, _i, _i64, C.c_double, C.c_double, _vp, _vp, _vp]),
 }
 
 

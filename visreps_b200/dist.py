@@ -144,8 +144,13 @@ def rsa_grouped_sharded(model_features: Sequence[torch.Tensor], neural_responses
     draws = rsa.draw_subsample_masks(n, n_bootstrap, seed, replicate_range=(lo, hi))
     masks = rsa.build_masks(draws, n, dev, with_full=True)
     out = rsa.compare_grouped(items[:nA], items[nA:], "spearman", masks)
-    scores = gather_replicate_scores(out[:, :, 1:].contiguous(), n_bootstrap, group).cpu().numpy()
-    ci_low, ci_high = rsa.percentile_ci(scores)
+    gathered = gather_replicate_scores(out[:, :, 1:].contiguous(), n_bootstrap, group)
+    ci = rsa.percentile_ci_device(gathered) if gathered.is_cuda else None
+    scores = gathered.cpu().numpy()
+    if ci is not None:
+        ci_low, ci_high = ci[0].cpu().numpy(), ci[1].cpu().numpy()
+    else:
+        ci_low, ci_high = rsa.percentile_ci(scores)
     return {"point": out[:, :, 0].cpu().numpy(), "scores": scores, "ci_low": ci_low, "ci_high": ci_high}
 
 
