@@ -5,7 +5,8 @@ import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, torch.distributed as dist
 import visreps_b200 as vb
-from visreps_b200 import synth, dist as vdist
+from visreps_b200 import synth, dist as vdist, rsa as vrsa
+vrsa.MASK_CACHE = os.environ.get("MASK_CACHE", "1") != "0"       # 0: every call replays the index draws (as bench.py does)
 rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); lr = int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(lr)
 dev = torch.device("cuda", lr)
