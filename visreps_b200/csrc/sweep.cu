@@ -481,11 +481,16 @@ sweep_kernel(const __grid_constant__ SweepArgs A) {
         if (4 * q + t < NVEC) e[4 * q + t] = ldg_row(bbase + (size_t)oo[t]);
     }
   };
-  auto consume = [&](int i, const uint2 (&e)[NVEC]) {
+  // A pair takes two steps that use different pipes: its ranks (shared-memory descriptors, popc on the XU pipe, integer adds)
+  // and its products (fp64 pipe).  For the smaller tiles the products of pair i - 1 are written next to the ranks of pair i, in
+  // one basic block, so that the scheduler can interleave the two instruction streams inside a warp (THINGS shape, 8 x 1:
+  // 23.9 -> 21.5 ms).  The 8 x 8 tile has no registers to spare for the extra live ranks (254, and 13.5 instead of 12.7 ms
+  // at the NSD shape with the interleaved order), so it keeps ranks -> products per pair.
+  constexpr bool kPipelined = NA * NB < 64;
+  auto ranks = [&](int i, const uint2 (&e)[NVEC], uint32_t (&dev)[NVEC], uint2& mk) {
     const int buf = (i >> 5) & 1, k = i & 31;
-    const uint2 mk = meta[buf][k];
+    mk = meta[buf][k];
     const bool keep = (mk.x >> lane) & 1u;
-    uint32_t dev[NVEC];
 #pragma unroll
     for (int h = 0; h < NH; ++h) {
       const uint4 m = masks[buf][h][k];
@@ -497,29 +502,34 @@ sweep_kernel(const __grid_constant__ SweepArgs A) {
           const uint32_t ps = __popc(e[v].x & mm[2 * t]);
           uint32_t pe = ps + 1u;                                                // a run of one value: C(e) = C(s) + 1
           if (mm[2 * t + 1] != 0u) pe = __popc(e[v].x & mm[2 * t + 1]);
-          dev[v] = e[v].y + ps + pe;
+          const uint32_t d = e[v].y + ps + pe;
+          dev[v] = (v < NA && !keep) ? kDevBias : d;                            // a dropped pair contributes nothing
         }
       }
     }
-    if (mk.y != 0u) {                                                           // rare: a run that ends in a later group
-      const uint32_t p = p_lo + (uint32_t)i;
+  };
+  auto ranks_slow = [&](int i, const uint2 (&e)[NVEC], uint32_t (&dev)[NVEC], const uint2 mk) {   // rare: runs that end in a later group
+    const uint32_t p = p_lo + (uint32_t)i;
+    const bool keep = (mk.x >> lane) & 1u;
 #pragma unroll 1
-      for (uint32_t todo = mk.y; todo; todo &= todo - 1u) {
-        const int v = __ffs(todo) - 1;
-        uint2 ev = e[0];
+    for (uint32_t todo = mk.y; todo; todo &= todo - 1u) {
+      const int v = __ffs(todo) - 1;
+      uint2 ev = e[0];
 #pragma unroll
-        for (int u = 0; u < NVEC; ++u) if (u == v) ev = e[u];
-        const uint32_t dv = dev_slow<kCompact>(__ldg(vecref(v).runs + p), ev, bbase + vecref(v).row_base, vecref(v), A.sbits);
+      for (int u = 0; u < NVEC; ++u) if (u == v) ev = e[u];
+      uint32_t dv = dev_slow<kCompact>(__ldg(vecref(v).runs + p), ev, bbase + vecref(v).row_base, vecref(v), A.sbits);
+      if (v < NA && !keep) dv = kDevBias;
 #pragma unroll
-        for (int u = 0; u < NVEC; ++u) if (u == v) dev[u] = dv;
-      }
+      for (int u = 0; u < NVEC; ++u) if (u == v) dev[u] = dv;
     }
+  };
+  auto products = [&](const uint32_t (&dev)[NVEC]) {
     double dB[NB];
 #pragma unroll
     for (int c = 0; c < NB; ++c) dB[c] = biased_to_double(dev[NA + c]);
 #pragma unroll
     for (int a = 0; a < NA; ++a) {
-      const double dA = biased_to_double(keep ? dev[a] : kDevBias);             // a dropped pair contributes nothing
+      const double dA = biased_to_double(dev[a]);
 #pragma unroll
       for (int c = 0; c < NB; ++c) acc[a][c] = fma(dA, dB[c], acc[a][c]);
     }
@@ -529,6 +539,9 @@ sweep_kernel(const __grid_constant__ SweepArgs A) {
     stage_block(0);
     if (count > 32) stage_block(1);
     uint2 e[D][NVEC];                                                           // register ring, compile-time indices only
+    uint32_t dcur[NVEC];                                                        // ranks of the previous pair (none yet: all products 0)
+#pragma unroll
+    for (int v = 0; v < NVEC; ++v) dcur[v] = kDevBias;
 #pragma unroll
     for (int d = 0; d < D - 1; ++d)
       if (d < count) issue(d, e[d]);
@@ -538,13 +551,26 @@ sweep_kernel(const __grid_constant__ SweepArgs A) {
         const int i = i0 + d;
         if (i < count) {
           if (i + D - 1 < count) issue(i + D - 1, e[(d + D - 1) % D]);
-          consume(i, e[d]);
+          uint2 mk;
+          if constexpr (kPipelined) {
+            uint32_t dnext[NVEC];
+            ranks(i, e[d], dnext, mk);
+            products(dcur);
+            if (mk.y != 0u) ranks_slow(i, e[d], dnext, mk);
+#pragma unroll
+            for (int v = 0; v < NVEC; ++v) dcur[v] = dnext[v];
+          } else {
+            ranks(i, e[d], dcur, mk);
+            if (mk.y != 0u) ranks_slow(i, e[d], dcur, mk);
+            products(dcur);
+          }
           // block (i >> 5) has been read for the last time after its pair 31 (the issue side is at most D - 1 pairs into the
           // next block): its buffer takes block blk + 2
           if ((i & 31) == 31 && ((i >> 5) + 2) * 32 < count) stage_block((i >> 5) + 2);
         }
       }
     }
+    if constexpr (kPipelined) products(dcur);
   }
   // CTA reduction.  Exact mode: a warp's sums are integers below 2^53 (the host sized the slices for it); they are added
   // as int64.  Otherwise fp64 in warp order.
