@@ -774,17 +774,48 @@ def subsample_rank(rdm, masks: torch.Tensor):
     return out[:, :N], ss, nk
 
 
-def _rdm_device(x: torch.Tensor, dev: torch.device, correction: float, flags: torch.Tensor, slot: int) -> torch.Tensor:
+def _rdm_device(x: torch.Tensor, dev: torch.device, correction: float, flags: torch.Tensor, slot: int,
+                ws_slot: str = "main") -> torch.Tensor:
     """compute_rdm without the host round trip for the zero-variance count (collected in `flags`)."""
     lib = _lib.load()
     x = _as_cuda_f32_rows(_flat(x) if x.ndim > 2 else x, dev)
     n, d = int(x.size(0)), int(x.size(1))
     rdm = torch.empty((n, n), dtype=torch.float32, device=dev)
-    ws = _lib.workspace(lib.vr_rdm_workspace_bytes(n, d), dev)
+    ws = _lib.workspace(lib.vr_rdm_workspace_bytes(n, d), dev, ws_slot)
     _lib.check(lib.vr_rdm_pearson_f32(x.data_ptr(), n, d, x.stride(0), float(correction), rdm.data_ptr(),
                                       flags[slot:slot + 1].data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr()),
                "vr_rdm_pearson_f32")
     return rdm
+
+
+RDM_OVERLAP = True        # False: one stream, one matrix after the other (bench.py's per-kernel breakdown is taken that way)
+_rdm_streams: Dict[int, Tuple[torch.cuda.Stream, torch.cuda.Stream]] = {}
+
+
+def _rdm_device_many(xs: Sequence[torch.Tensor], dev: torch.device, correction: float, flags: torch.Tensor,
+                     slots: Sequence[int]) -> List[torch.Tensor]:
+    """RDMs of device-resident inputs, alternating between two streams with a scratch buffer each: the row-centring pass of
+    one matrix (HBM bound, no shared memory) shares the SMs with the tensor-core SYRK of the previous one (one CTA per SM,
+    bound by the tensor pipe) instead of waiting for it."""
+    if len(xs) < 2 or not RDM_OVERLAP:
+        return [_rdm_device(x, dev, correction, flags, k) for x, k in zip(xs, slots)]
+    cur = torch.cuda.current_stream()
+    pair = _rdm_streams.get(dev.index)
+    if pair is None:
+        pair = _rdm_streams[dev.index] = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+    for st in pair:
+        st.wait_stream(cur)
+    out = []
+    for pos, (x, k) in enumerate(zip(xs, slots)):
+        with torch.cuda.stream(pair[pos & 1]):
+            rdm = _rdm_device(x, dev, correction, flags, k, ws_slot=f"rdm{pos & 1}")
+        rdm.record_stream(cur)
+        if isinstance(x, torch.Tensor) and x.is_cuda:
+            x.record_stream(pair[pos & 1])
+        out.append(rdm)
+    for st in pair:
+        cur.wait_stream(st)
+    return out
 
 
 class RankContext:
@@ -888,8 +919,11 @@ def _spearman_pipeline(inputs_a: Sequence[torch.Tensor], inputs_b: Sequence[torc
     f_items: Dict[int, PresortedRDM] = {}
     if fus_on_device and len(mats) + len(fus) <= _MAX_GROUP * 2:
         # everything is here already: one batched presort for both sides (half the sort launches)
-        both = PresortedRDM.batch([rdm_of(st, slot_m(k)) for k, st in enumerate(staged_m)] +
-                                  [rdm_of(staged_f[k], slot_f(k)) for k in range(len(fus))])
+        for _xd, ev in list(staged_m) + [staged_f[k] for k in range(len(fus))]:
+            if ev is not None:
+                compute.wait_event(ev)
+        both = PresortedRDM.batch(_rdm_device_many([st[0] for st in staged_m] + [staged_f[k][0] for k in range(len(fus))], dev, correction, flags,
+                                                   [slot_m(k) for k in range(len(staged_m))] + [slot_f(k) for k in range(len(fus))]))
         m_items = both[:len(mats)]
         f_items = dict(enumerate(both[len(mats):]))
     else:
@@ -1070,8 +1104,11 @@ def _rsa_grouped(model_features, neural_responses, method, bootstrap, n_bootstra
                                             n_bootstrap if bootstrap else 0, correction, dev)
     else:
         flags = torch.zeros(nA + nB, dtype=torch.int32, device=dev)
-        rdms = [_rdm_device(x, dev, correction, flags, k)
-                for k, x in enumerate(list(model_features) + list(neural_responses))]
+        every = list(model_features) + list(neural_responses)
+        if all(isinstance(x, torch.Tensor) and x.is_cuda for x in every):
+            rdms = _rdm_device_many(every, dev, correction, flags, list(range(len(every))))
+        else:
+            rdms = [_rdm_device(x, dev, correction, flags, k) for k, x in enumerate(every)]
         prepared = _prepare_many(rdms, method)
         if index_sets is None:
             index_sets = draw()
